@@ -1,0 +1,110 @@
+/* lizard_b200.h -- C ABI of liblizard_b200.so: the Lizard block codec hot path on NVIDIA B200 (sm_100a).
+ *
+ * Two groups of entry points:
+ *
+ *  (1) DROP-IN symbols: same names, argument meaning, return values and error conventions as the
+ *      reference library, so an application (or the reference's own frame layer / bench / CLI) can be
+ *      relinked against this library unchanged.  All pointers are HOST pointers, as in the reference.
+ *        reference declaration                              replaced implementation
+ *        lib/lizard_compress.h:82    Lizard_versionNumber
+ *        lib/lizard_compress.h:97    Lizard_compress          lib/lizard_compress.c:596-606
+ *        lib/lizard_compress.h:136   Lizard_compressBound     lib/lizard_compress.c:67
+ *        lib/lizard_compress.h:146   Lizard_sizeofState       lib/lizard_compress.c:311-323
+ *        lib/lizard_compress.h:147   Lizard_compress_extState lib/lizard_compress.c:583-593
+ *        lib/lizard_decompress.h:73  Lizard_decompress_safe   lib/lizard_decompress.c:267-270
+ *      Compression output is byte-identical to the reference built with -DLIZARD_RESET_MEM
+ *      (hash table empty at the start of every call), for the levels whose parsers are implemented on
+ *      the GPU: 10, 11, 30, 31 (fastSmall / fast) and 21, 22, 41, 42 (priceFast).  Any other level
+ *      makes the compress entry points return 0 ("failed"), never a CPU fallback.
+ *      Decompression accepts every level 10..49 (the block format only has two codeword flavours).
+ *
+ *  (2) BATCH symbols (LizardB200_*): what the reference's per-block loops
+ *      (lib/lizard_frame.c:544-556 compressUpdate, :1148-1169 decodeCBlock, programs/bench.c:231-286)
+ *      turn into: n independent units per call, one GPU launch.  Host-pointer and device-pointer variants.
+ *
+ * A unit's compressed form is exactly what one Lizard_compress call returns; a unit's decoded size is
+ * exactly what Lizard_decompress_safe returns (negative values are the reference's error codes).
+ *
+ * There is no CPU fallback anywhere: if no usable CUDA device exists every entry point fails
+ * (compress -> 0, decompress -> LIZARDB200_ERR_NO_DEVICE, batch calls -> negative status).
+ */
+#ifndef LIZARD_B200_H
+#define LIZARD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__cplusplus)
+extern "C" {
+#endif
+
+#define LIZARD_B200_VERSION_NUMBER 10000          /* same numbering as LIZARD_VERSION_NUMBER 1.0.0 */
+#define LIZARD_MIN_CLEVEL   10
+#define LIZARD_MAX_CLEVEL   49
+#define LIZARD_BLOCK_SIZE   (1 << 17)
+#define LIZARD_MAX_INPUT_SIZE 0x7E000000
+#define LIZARD_COMPRESSBOUND(isize) \
+    ((unsigned)(isize) > (unsigned)LIZARD_MAX_INPUT_SIZE ? 0 : (isize) + 1 + 1 + (((isize) / LIZARD_BLOCK_SIZE) + 1) * 4)
+
+/* status codes of the batch API (all negative); per-unit results use the reference's conventions */
+#define LIZARDB200_OK               0
+#define LIZARDB200_ERR_NO_DEVICE   (-1001)   /* no CUDA device / driver, or kernels not built for this GPU */
+#define LIZARDB200_ERR_CUDA        (-1002)   /* a CUDA call failed; see LizardB200_lastError() */
+#define LIZARDB200_ERR_ARGUMENT    (-1003)
+#define LIZARDB200_ERR_LEVEL       (-1004)   /* compression level whose parser is not implemented on the GPU */
+#define LIZARDB200_ERR_MEMORY      (-1005)
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) drop-in symbols
+ * ------------------------------------------------------------------------------------------- */
+int Lizard_versionNumber(void);
+int Lizard_compressBound(int inputSize);
+int Lizard_sizeofState(int compressionLevel);
+/* returns compressed size, or 0 when it failed / did not fit maxDstSize */
+int Lizard_compress(const char* src, char* dst, int srcSize, int maxDstSize, int compressionLevel);
+/* `state` is accepted for signature compatibility (must be pointer-aligned, else 0); the device keeps its own */
+int Lizard_compress_extState(void* state, const char* src, char* dst, int srcSize, int maxDstSize, int compressionLevel);
+/* returns decoded size (>= 0) or a negative error exactly as the reference:
+ * -1 for a bad level byte / block header / stream, -(tokenIndex)-1 from the token loops */
+int Lizard_decompress_safe(const char* src, char* dst, int compressedSize, int maxDecompressedSize);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) batch symbols
+ * ------------------------------------------------------------------------------------------- */
+/* Select the CUDA device used by this thread's subsequent calls (default 0). Returns LIZARDB200_OK or error. */
+int LizardB200_setDevice(int device);
+/* 1 if a usable sm_100 device is present and the context could be created, else 0 */
+int LizardB200_available(void);
+const char* LizardB200_lastError(void);
+
+/* Host-pointer batch: unit i = src[i][0..srcSize[i]) -> dst[i][0..dstCapacity[i]); result[i] as Lizard_compress
+ * (0 = failed / did not fit).  Inputs are staged through pinned memory, one launch for the whole batch. */
+int LizardB200_compress_batch(const void* const* src, const int* srcSize,
+                              void* const* dst, const int* dstCapacity, int* result,
+                              int nUnits, int compressionLevel);
+/* result[i] as Lizard_decompress_safe */
+int LizardB200_decompress_batch(const void* const* src, const int* compressedSize,
+                                void* const* dst, const int* dstCapacity, int* result, int nUnits);
+
+/* Contiguous host buffers, units described by offset/size arrays (what a frame or a file splitter has).
+ * dstStride: unit i is written at dst + i*dstStride with capacity dstCapacityEach. */
+int LizardB200_compress_blocks(const void* src, size_t srcSize, int blockSize,
+                               void* dst, size_t dstStride, int dstCapacityEach, int* result,
+                               int compressionLevel);
+
+/* Device-pointer variants: everything (payload, offset/size tables, results) already lives in device memory
+ * of the current device; the call only enqueues kernels on `cudaStream` (a cudaStream_t, may be NULL) and
+ * returns without synchronising.  Workspace is owned by the library and grown on demand. */
+int LizardB200_decompress_device(const void* dSrc, const uint64_t* dSrcOff, const uint32_t* dSrcLen,
+                                 void* dDst, const uint64_t* dDstOff, const uint32_t* dDstCap,
+                                 int* dResult, unsigned nUnits, void* cudaStream);
+int LizardB200_compress_device(const void* dSrc, const uint64_t* dSrcOff, const uint32_t* dSrcLen,
+                               void* dDst, const uint64_t* dDstOff, const uint32_t* dDstCap,
+                               int* dResult, unsigned nUnits, int compressionLevel, void* cudaStream);
+/* number of kernel launches issued by this library since load (bench.py reports it as gpu_launches) */
+unsigned long long LizardB200_launchCount(void);
+
+#if defined(__cplusplus)
+}
+#endif
+#endif /* LIZARD_B200_H */

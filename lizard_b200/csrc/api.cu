@@ -1,0 +1,359 @@
+// api.cu -- C-ABI shim of liblizard_b200.so (see include/lizard_b200.h): context, workspaces, kernel
+// launches, host staging.  Host-side logic only; the codec lives in decode.cuh / encode.cuh.
+#include "../../include/lizard_b200.h"
+#include "decode.cuh"
+#include "encode.cuh"
+
+#include <cuda_runtime.h>
+#include <mutex>
+#include <vector>
+#include <string>
+#include <atomic>
+#include <cstring>
+#include <cstdio>
+
+using namespace lzb;
+
+namespace {
+
+constexpr int kDecWarps = 8;                 // warps per CTA in the decode kernel
+constexpr int kMaxDevices = 16;
+
+__global__ void __launch_bounds__(kDecWarps * 32)
+lizard_decode_units_kernel(DecodeBatch b)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    DecWarpShared* sh = reinterpret_cast<DecWarpShared*>(smem_raw) + warp;
+    const size_t gwarp = (size_t)blockIdx.x * kDecWarps + warp;
+    u8* scratch = b.scratch + gwarp * kDecScratchPerWarp;
+    for (;;) {
+        u32 unit = 0;
+        if (lane == 0) unit = atomicAdd(b.counter, 1u);
+        unit = __shfl_sync(LZB_FULL, unit, 0);
+        if (unit >= b.n_units) break;
+        const int r = decode_unit(b.src_base + b.src_off[unit], b.src_len[unit],
+                                  b.dst_base + b.dst_off[unit], b.dst_cap[unit], scratch, sh, lane);
+        if (lane == 0) b.result[unit] = r;
+        __syncwarp();
+    }
+}
+
+thread_local std::string g_last_error;
+thread_local int g_device = 0;
+std::atomic<unsigned long long> g_launches{0};
+
+struct DeviceBuffer {
+    void* p = nullptr; size_t bytes = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        size_t want = n + n / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, n); want = n; }
+        if (e == cudaSuccess) bytes = want;
+        return e;
+    }
+};
+struct PinnedBuffer {
+    void* p = nullptr; size_t bytes = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMallocHost(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+};
+
+struct Context {
+    std::mutex mu;
+    bool ready = false, failed = false;
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    int dec_grid = 0;
+    DeviceBuffer dec_scratch, enc_scratch, counters;
+    u32 counter_slot = 0;
+    // staging for the host-pointer entry points
+    PinnedBuffer pin_in, pin_out, pin_tab;
+    DeviceBuffer d_in, d_out, d_tab;
+    EncodeConfig enc_cfg;
+};
+Context g_ctx[kMaxDevices];
+
+bool fail(const char* what, cudaError_t e)
+{
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    g_last_error = buf;
+    return false;
+}
+#define CU_OK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(#call, e_); return LIZARDB200_ERR_CUDA; } } while (0)
+
+constexpr int kCounterSlots = 1024;
+
+// bring the per-device context up (called with ctx.mu held)
+int ensure_context(Context& c, int device)
+{
+    if (c.ready) { cudaSetDevice(device); return LIZARDB200_OK; }
+    if (c.failed) return LIZARDB200_ERR_NO_DEVICE;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n) {
+        c.failed = true;
+        g_last_error = e != cudaSuccess ? std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)
+                                        : std::string("no such CUDA device");
+        return LIZARDB200_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        c.failed = true; fail("cudaSetDevice", e); return LIZARDB200_ERR_NO_DEVICE;
+    }
+    if (prop.major != 10) {   // the fatbin holds sm_100a SASS only
+        c.failed = true;
+        g_last_error = "liblizard_b200 is built for sm_100a (B200) only; found " + std::string(prop.name);
+        return LIZARDB200_ERR_NO_DEVICE;
+    }
+    c.device = device;
+    c.sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        c.failed = true; fail("cudaStreamCreate", e); return LIZARDB200_ERR_CUDA;
+    }
+    const size_t dec_smem = sizeof(DecWarpShared) * kDecWarps;
+    e = cudaFuncSetAttribute(lizard_decode_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
+    if (e != cudaSuccess) { c.failed = true; fail("cudaFuncSetAttribute(decode)", e); return LIZARDB200_ERR_CUDA; }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lizard_decode_units_kernel, kDecWarps * 32, dec_smem);
+    if (per_sm < 1) per_sm = 1;
+    c.dec_grid = c.sm_count * per_sm;
+    if ((e = c.dec_scratch.reserve((size_t)c.dec_grid * kDecWarps * kDecScratchPerWarp)) != cudaSuccess) {
+        c.failed = true; fail("cudaMalloc(decode scratch)", e); return LIZARDB200_ERR_MEMORY;
+    }
+    if ((e = c.counters.reserve(kCounterSlots * sizeof(u32))) != cudaSuccess) {
+        c.failed = true; fail("cudaMalloc(counters)", e); return LIZARDB200_ERR_MEMORY;
+    }
+    int er = encode_context_init(c.enc_cfg, c.sm_count, c.enc_scratch.p ? 0 : 0);
+    if (er != 0) { c.failed = true; g_last_error = "encode kernel attribute setup failed"; return LIZARDB200_ERR_CUDA; }
+    if ((e = c.enc_scratch.reserve(c.enc_cfg.scratch_bytes)) != cudaSuccess) {
+        c.failed = true; fail("cudaMalloc(encode scratch)", e); return LIZARDB200_ERR_MEMORY;
+    }
+    c.ready = true;
+    return LIZARDB200_OK;
+}
+
+// a fresh zeroed work-queue counter for one launch
+u32* next_counter(Context& c, cudaStream_t s)
+{
+    u32* p = (u32*)c.counters.p + (c.counter_slot++ % kCounterSlots);
+    cudaMemsetAsync(p, 0, sizeof(u32), s);
+    return p;
+}
+
+int launch_decode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* dSrcLen,
+                  void* dDst, const u64* dDstOff, const u32* dDstCap, int* dResult, u32 n, cudaStream_t s)
+{
+    if (n == 0) return LIZARDB200_OK;
+    DecodeBatch b;
+    b.src_base = (const u8*)dSrc; b.src_off = dSrcOff; b.src_len = dSrcLen;
+    b.dst_base = (u8*)dDst; b.dst_off = dDstOff; b.dst_cap = dDstCap;
+    b.result = dResult; b.n_units = n;
+    b.scratch = (u8*)c.dec_scratch.p;
+    b.counter = next_counter(c, s);
+    u32 warps_needed = n;
+    int grid = (int)((warps_needed + kDecWarps - 1) / kDecWarps);
+    if (grid > c.dec_grid) grid = c.dec_grid;
+    lizard_decode_units_kernel<<<grid, kDecWarps * 32, sizeof(DecWarpShared) * kDecWarps, s>>>(b);
+    g_launches++;
+    CU_OK(cudaGetLastError());
+    return LIZARDB200_OK;
+}
+
+int launch_encode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* dSrcLen,
+                  void* dDst, const u64* dDstOff, const u32* dDstCap, int* dResult, u32 n, int level, cudaStream_t s)
+{
+    if (n == 0) return LIZARDB200_OK;
+    LevelParams lp = level_params(level);
+    if (lp.parser == kParserUnsupported) { g_last_error = "compression level not implemented on the GPU"; return LIZARDB200_ERR_LEVEL; }
+    EncodeBatch b;
+    b.src_base = (const u8*)dSrc; b.src_off = dSrcOff; b.src_len = dSrcLen;
+    b.dst_base = (u8*)dDst; b.dst_off = dDstOff; b.dst_cap = dDstCap;
+    b.result = dResult; b.n_units = n; b.level = level;
+    b.scratch = (u8*)c.enc_scratch.p;
+    b.counter = next_counter(c, s);
+    int launches = 0;
+    cudaError_t e = encode_launch(c.enc_cfg, b, s, &launches);
+    g_launches += (unsigned long long)launches;
+    if (e != cudaSuccess) { fail("encode launch", e); return LIZARDB200_ERR_CUDA; }
+    return LIZARDB200_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Shared body of the host-pointer batch calls: stage inputs + tables, run, fetch results + outputs.
+template <bool kCompress>
+int run_host_batch(const void* const* src, const int* srcSize, void* const* dst, const int* dstCap,
+                   int* result, int n, int level)
+{
+    if (n < 0 || (n > 0 && (!src || !srcSize || !dst || !dstCap || !result))) return LIZARDB200_ERR_ARGUMENT;
+    if (n == 0) return LIZARDB200_OK;
+    Context& c = g_ctx[g_device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    int st = ensure_context(c, g_device);
+    if (st != LIZARDB200_OK) return st;
+    if (kCompress && level_params(level).parser == kParserUnsupported) {
+        g_last_error = "compression level not implemented on the GPU";
+        return LIZARDB200_ERR_LEVEL;
+    }
+
+    // layout: every unit 16-byte aligned in both arenas
+    std::vector<u64> in_off(n), out_off(n);
+    size_t in_total = 0, out_total = 0;
+    for (int i = 0; i < n; ++i) {
+        if (srcSize[i] < 0 || dstCap[i] < 0) return LIZARDB200_ERR_ARGUMENT;
+        in_off[i] = in_total;   in_total += align_up((size_t)srcSize[i] + 16, 16);
+        out_off[i] = out_total; out_total += align_up((size_t)dstCap[i] + 32, 16);
+    }
+    const size_t tab_bytes = (size_t)n * (8 + 4 + 8 + 4 + 4);
+    CU_OK(c.pin_in.reserve(in_total));
+    CU_OK(c.pin_tab.reserve(tab_bytes));
+    CU_OK(c.d_in.reserve(in_total));
+    CU_OK(c.d_out.reserve(out_total));
+    CU_OK(c.d_tab.reserve(tab_bytes));
+    CU_OK(c.pin_out.reserve(out_total));
+
+    u8* tab = (u8*)c.pin_tab.p;
+    u64* t_in_off = (u64*)tab;
+    u64* t_out_off = t_in_off + n;
+    u32* t_in_len = (u32*)(t_out_off + n);
+    u32* t_out_cap = t_in_len + n;
+    int* t_res = (int*)(t_out_cap + n);
+    for (int i = 0; i < n; ++i) {
+        memcpy((u8*)c.pin_in.p + in_off[i], src[i], (size_t)srcSize[i]);
+        t_in_off[i] = in_off[i]; t_out_off[i] = out_off[i];
+        t_in_len[i] = (u32)srcSize[i]; t_out_cap[i] = (u32)dstCap[i];
+    }
+    u8* dtab = (u8*)c.d_tab.p;
+    cudaStream_t s = c.stream;
+    CU_OK(cudaMemcpyAsync(c.d_in.p, c.pin_in.p, in_total, cudaMemcpyHostToDevice, s));
+    CU_OK(cudaMemcpyAsync(dtab, tab, tab_bytes - (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    const u64* d_in_off = (const u64*)dtab;
+    const u64* d_out_off = d_in_off + n;
+    const u32* d_in_len = (const u32*)(d_out_off + n);
+    const u32* d_out_cap = d_in_len + n;
+    int* d_res = (int*)(d_out_cap + n);
+    if (kCompress) st = launch_encode(c, c.d_in.p, d_in_off, d_in_len, c.d_out.p, d_out_off, d_out_cap, d_res, (u32)n, level, s);
+    else           st = launch_decode(c, c.d_in.p, d_in_off, d_in_len, c.d_out.p, d_out_off, d_out_cap, d_res, (u32)n, s);
+    if (st != LIZARDB200_OK) return st;
+    CU_OK(cudaMemcpyAsync(t_res, d_res, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CU_OK(cudaMemcpyAsync(c.pin_out.p, c.d_out.p, out_total, cudaMemcpyDeviceToHost, s));
+    CU_OK(cudaStreamSynchronize(s));
+    for (int i = 0; i < n; ++i) {
+        result[i] = t_res[i];
+        if (t_res[i] > 0) memcpy(dst[i], (u8*)c.pin_out.p + out_off[i], (size_t)t_res[i]);
+    }
+    return LIZARDB200_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int Lizard_versionNumber(void) { return LIZARD_B200_VERSION_NUMBER; }
+int Lizard_compressBound(int isize) { return compress_bound(isize); }
+
+int Lizard_sizeofState(int level)
+{
+    // lib/lizard_compress.c:311-323: struct + hash table + chain table + 5 stream buffers + Huffman bound.
+    // The device keeps its own state; the figure is reproduced so callers that malloc it keep working.
+    if (level > (int)kMaxLevel) level = kMaxLevel;
+    if (level < (int)kMinLevel) level = kDefaultLevel;
+    static const unsigned char hash_log[40] = {12,18,18,18,18,18,18,18,18,23, 14,14,18,18,23,23,23,23,23,23,
+                                               12,18,14,18,18,18,18,18,18,23, 14,14,18,18,23,23,23,23,23,23};
+    static const unsigned char content_log[40] = {0,0,0,16,16,16,16,16,17,17, 0,22,22,22,22,22,23,23,23,25,
+                                                  0,0,0,0,16,16,16,16,16,17, 0,22,22,22,22,22,22,23,23,25};
+    const size_t struct_bytes = 2384;   // sizeof(Lizard_stream_t) on LP64
+    const size_t huf_bound = 129 + (kBlockSizePad + (kBlockSizePad >> 8) + 8);
+    size_t total = struct_bytes + (size_t(4) << hash_log[level - 10]) + (size_t(4) << content_log[level - 10])
+                 + 5 * (size_t)kBlockSizePad + huf_bound;
+    return (int)total;
+}
+
+int LizardB200_setDevice(int device)
+{
+    if (device < 0 || device >= kMaxDevices) return LIZARDB200_ERR_ARGUMENT;
+    g_device = device;
+    Context& c = g_ctx[device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    return ensure_context(c, device);
+}
+int LizardB200_available(void)
+{
+    Context& c = g_ctx[g_device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    return ensure_context(c, g_device) == LIZARDB200_OK;
+}
+const char* LizardB200_lastError(void) { return g_last_error.c_str(); }
+unsigned long long LizardB200_launchCount(void) { return g_launches.load(); }
+
+int LizardB200_decompress_device(const void* dSrc, const uint64_t* dSrcOff, const uint32_t* dSrcLen,
+                                 void* dDst, const uint64_t* dDstOff, const uint32_t* dDstCap,
+                                 int* dResult, unsigned nUnits, void* stream)
+{
+    Context& c = g_ctx[g_device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    int st = ensure_context(c, g_device);
+    if (st != LIZARDB200_OK) return st;
+    return launch_decode(c, dSrc, (const u64*)dSrcOff, dSrcLen, dDst, (const u64*)dDstOff, dDstCap, dResult, nUnits, (cudaStream_t)stream);
+}
+int LizardB200_compress_device(const void* dSrc, const uint64_t* dSrcOff, const uint32_t* dSrcLen,
+                               void* dDst, const uint64_t* dDstOff, const uint32_t* dDstCap,
+                               int* dResult, unsigned nUnits, int level, void* stream)
+{
+    Context& c = g_ctx[g_device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    int st = ensure_context(c, g_device);
+    if (st != LIZARDB200_OK) return st;
+    return launch_encode(c, dSrc, (const u64*)dSrcOff, dSrcLen, dDst, (const u64*)dDstOff, dDstCap, dResult, nUnits, level, (cudaStream_t)stream);
+}
+
+int LizardB200_decompress_batch(const void* const* src, const int* cSize, void* const* dst, const int* dstCap,
+                                int* result, int n)
+{
+    return run_host_batch<false>(src, cSize, dst, dstCap, result, n, 0);
+}
+int LizardB200_compress_batch(const void* const* src, const int* srcSize, void* const* dst, const int* dstCap,
+                              int* result, int n, int level)
+{
+    return run_host_batch<true>(src, srcSize, dst, dstCap, result, n, level);
+}
+
+int Lizard_decompress_safe(const char* src, char* dst, int compressedSize, int maxDecompressedSize)
+{
+    // lib/lizard_decompress.c:139: inputSize < 1 -> 0 before anything is read
+    if (compressedSize < 1) return 0;
+    if (maxDecompressedSize < 0) return -1;
+    const void* s = src; void* d = dst; int r = -1;
+    int st = LizardB200_decompress_batch(&s, &compressedSize, &d, &maxDecompressedSize, &r, 1);
+    return st == LIZARDB200_OK ? r : st;
+}
+
+int Lizard_compress(const char* src, char* dst, int srcSize, int maxDstSize, int level)
+{
+    if (srcSize < 0 || maxDstSize < 0) return 0;
+    // lib/lizard_compress.c:303-308 Lizard_verifyCompressionLevel
+    if (level > (int)kMaxLevel) level = kMaxLevel;
+    if (level < (int)kMinLevel) level = kDefaultLevel;
+    const void* s = src; void* d = dst; int r = 0;
+    int st = LizardB200_compress_batch(&s, &srcSize, &d, &maxDstSize, &r, 1, level);
+    return st == LIZARDB200_OK ? r : 0;
+}
+int Lizard_compress_extState(void* state, const char* src, char* dst, int srcSize, int maxDstSize, int level)
+{
+    if (((size_t)state & (sizeof(void*) - 1)) != 0) return 0;   // lib/lizard_compress.c:586
+    return Lizard_compress(src, dst, srcSize, maxDstSize, level);
+}
+
+}  // extern "C"

@@ -1,0 +1,38 @@
+"""Test-only loaders for the checkers: the compiled reference (oracle/_ref) and our C restatement (oracle/liboracle.so)."""
+import ctypes
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _bind(L):
+    L.Lizard_compressBound.argtypes = [ctypes.c_int]
+    L.Lizard_sizeofState.argtypes = [ctypes.c_int]
+    L.Lizard_compress.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.Lizard_decompress_safe.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    return L
+
+
+def ref_parity():
+    """Reference compiled with -DLIZARD_RESET_MEM: the bit-exact target for compression."""
+    p = os.path.join(REF_DIR, "liblizard_ref_parity.so")
+    return _bind(ctypes.CDLL(p)) if os.path.exists(p) else None
+
+
+def ref_speed():
+    p = os.path.join(REF_DIR, "liblizard_ref_speed.so")
+    return _bind(ctypes.CDLL(p)) if os.path.exists(p) else None
+
+
+def ref_compress(L, data: bytes, level: int, cap: int = None) -> bytes:
+    cap = L.Lizard_compressBound(len(data)) if cap is None else cap
+    dst = ctypes.create_string_buffer(max(cap, 1))
+    n = L.Lizard_compress(data, dst, len(data), cap, level)
+    return dst.raw[:n]
+
+
+def ref_decompress(L, comp: bytes, cap: int):
+    dst = ctypes.create_string_buffer(max(cap, 1))
+    r = L.Lizard_decompress_safe(comp, dst, len(comp), cap)
+    return r, (dst.raw[:r] if r > 0 else b"")
