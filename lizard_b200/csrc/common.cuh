@@ -10,7 +10,9 @@
 #if defined(__CUDACC__)
 #define LZ_HD __host__ __device__ __forceinline__
 #define LZ_D  __device__ __forceinline__
+#define LZ_HDM __host__ __device__ __forceinline__
 #else
+#define LZ_HDM inline
 #define LZ_HD static inline
 #define LZ_D  static inline
 #endif
