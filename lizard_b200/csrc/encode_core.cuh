@@ -362,7 +362,7 @@ template <class W> LZ_HD void parse_price_fast(const ParseCtx& c, u32 b0, u32 b1
 // ---- Huffman stage of one stream --------------------------------------------------------------------------
 struct EncHufWork {               // per-warp scratch for the entropy stage
     HufEncScratch ws;
-    u32 seg_count[4][256];
+    u32 (*seg_count)[256];        // [4][256] per-segment byte histograms (shared memory on the device)
     u32 count[256];
     HufPlan plan;
     u32 pack[(kBlockSizePad + 512) / 4 + 64];   // aligned staging of packed segments

@@ -24,7 +24,8 @@ extern "C" int lzb_host_compress(const unsigned char* src, int n, unsigned char*
     if (lp.parser == lzb::kParserUnsupported) return 0;
     lzb::u32* table = (lzb::u32*)malloc(sizeof(lzb::u32) << lp.hashLog);
     lzb::EncWork* work = (lzb::EncWork*)malloc(sizeof(lzb::EncWork));
+    work->huf.seg_count = (lzb::u32 (*)[256])malloc(4 * 256 * sizeof(lzb::u32));
     int r = lzb::encode_unit<lzb::HostLanes>(src, (lzb::u32)n, dst, (lzb::u32)cap, level, table, work);
-    free(table); free(work);
+    free(work->huf.seg_count); free(table); free(work);
     return r;
 }
