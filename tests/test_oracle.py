@@ -1,0 +1,275 @@
+"""CPU tests that PIN the oracle (oracle/lizard_oracle.c, our plain-C restatement) and the host build of the
+lane-generic codec code (lizard_b200/libhostshim.so, TEST-ONLY) against the unmodified reference compiled
+from /root/reference (oracle/_ref) and against the committed golden fixtures generated from that build."""
+import ctypes
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import lizard_b200 as lz
+from tests import refs
+
+BS = lz.BLOCK_SIZE
+LEVELS = [10, 11, 21, 22, 30, 31, 41, 42]
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _oracle():
+    p = os.path.join(refs.ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(p):
+        pytest.skip("oracle/liboracle.so not built (run __graft_entry__.build())")
+    L = ctypes.CDLL(p)
+    L.oracle_Lizard_compress.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.oracle_Lizard_decompress_safe.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    L.oracle_HUF_compress.restype = ctypes.c_size_t
+    L.oracle_HUF_compress.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    L.oracle_HUF_decompress.restype = ctypes.c_size_t
+    L.oracle_HUF_decompress.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    return L
+
+
+def _shim():
+    p = os.path.join(refs.ROOT, "lizard_b200", "libhostshim.so")
+    if not os.path.exists(p):
+        pytest.skip("libhostshim.so not built")
+    L = ctypes.CDLL(p)
+    L.lzb_host_compress.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    L.lzb_host_huf_decompress.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_char_p, ctypes.c_uint]
+    return L
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    return _oracle()
+
+
+@pytest.fixture(scope="module")
+def shim():
+    return _shim()
+
+
+@pytest.fixture(scope="module")
+def ref():
+    L = refs.ref_parity()
+    if L is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    return L
+
+
+def o_compress(L, data, level, cap=None):
+    cap = lz_bound(len(data)) if cap is None else cap
+    dst = ctypes.create_string_buffer(max(cap, 1) + 64)
+    n = L.oracle_Lizard_compress(data, dst, len(data), cap, level)
+    return dst.raw[:n]
+
+
+def shim_compress(L, data, level, cap=None):
+    cap = lz_bound(len(data)) if cap is None else cap
+    dst = ctypes.create_string_buffer(max(cap, 1) + 64)
+    n = L.lzb_host_compress(data, len(data), dst, cap, level)
+    return dst.raw[:n]
+
+
+def o_decompress(L, comp, cap):
+    dst = ctypes.create_string_buffer(max(cap, 1) + 64)
+    r = L.oracle_Lizard_decompress_safe(comp, dst, len(comp), cap)
+    return r, (dst.raw[:r] if r > 0 else b"")
+
+
+def lz_bound(n):
+    return n + 2 + (n // BS + 1) * 4
+
+
+def _inputs(seed, count):
+    rnd = random.Random(seed)
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        kind = rnd.randrange(7)
+        n = rnd.choice([0, 1, 5, 19, 20, 21, 22, 40, 100, 1000, 1025, 2000, 4096, 30000, 65536, 131071, 131072,
+                        131073, 200000])
+        if kind == 0:
+            out.append(lz.datagen(n, rnd.choice([10, 30, 50, 70, 90, 100]), rnd.randrange(1000)))
+        elif kind == 1:
+            out.append(bytes(n))
+        elif kind == 2:
+            out.append(rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+        elif kind == 3:
+            out.append(rng.integers(0, 4, n, dtype=np.uint8).tobytes())
+        elif kind == 4:
+            out.append((b"abcdefgh" * (n // 8 + 1))[:n])
+        elif kind == 5:
+            out.append(rng.choice(np.array([65, 66, 67, 200], dtype=np.uint8), size=n, p=[0.9, 0.05, 0.04, 0.01]).tobytes())
+        else:
+            p = rng.dirichlet(np.ones(256) * 0.05)
+            out.append(rng.choice(256, size=n, p=p).astype(np.uint8).tobytes())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# golden fixtures (generated from the compiled reference by tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------
+def _golden():
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        return json.load(f)
+
+
+def _golden_input(spec):
+    if spec["kind"] == "datagen":
+        return lz.datagen(spec["size"], spec["pct"], spec["seed"])
+    if spec["kind"] == "zeros":
+        return bytes(spec["size"])
+    if spec["kind"] == "pattern":
+        return (b"abcdefgh" * (spec["size"] // 8 + 1))[: spec["size"]]
+    raise ValueError(spec)
+
+
+def test_datagen_matches_reference_md5():
+    g = _golden()
+    for spec in g["datagen_md5"]:
+        assert hashlib.md5(lz.datagen(spec["size"], spec["pct"], spec["seed"])).hexdigest() == spec["md5"]
+
+
+def test_oracle_and_shim_compress_match_golden(oracle, shim):
+    for case in _golden()["compress"]:
+        data = _golden_input(case["input"])
+        for impl, fn in (("oracle", o_compress), ("shim", shim_compress)):
+            L = oracle if impl == "oracle" else shim
+            if case["mode"] == "single":
+                got = fn(L, data, case["level"])
+            else:
+                got = b"".join(fn(L, data[i:i + BS], case["level"], case.get("cap")) for i in range(0, len(data), BS))
+            assert len(got) == case["size"], (impl, case)
+            assert hashlib.sha256(got).hexdigest() == case["sha256"], (impl, case)
+
+
+def test_oracle_decompress_matches_golden_vectors(oracle):
+    for case in _golden()["vectors"]:
+        comp = bytes.fromhex(case["compressed_hex"])
+        r, out = o_decompress(oracle, comp, case["cap"])
+        assert r == case["result"], case["name"]
+        if r > 0:
+            assert hashlib.sha256(out).hexdigest() == case["sha256"], case["name"]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# live comparison with the compiled reference (only where oracle/_ref exists)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("level", LEVELS)
+def test_compress_parity_datagen_blocks(ref, oracle, shim, level):
+    data = lz.datagen(1 << 20)
+    for i in range(0, len(data), BS):
+        blk = data[i:i + BS]
+        want = refs.ref_compress(ref, blk, level, BS - 1)
+        assert o_compress(oracle, blk, level, BS - 1) == want, (level, i)
+        assert shim_compress(shim, blk, level, BS - 1) == want, (level, i)
+
+
+@pytest.mark.parametrize("level", [10, 21, 41])
+def test_compress_parity_multi_inner_block(ref, oracle, shim, level):
+    data = lz.datagen((1 << 20) + 4321, 50, 2)
+    want = refs.ref_compress(ref, data, level)
+    assert o_compress(oracle, data, level) == want
+    assert shim_compress(shim, data, level) == want
+
+
+def test_compress_parity_fuzz(ref, oracle, shim):
+    rnd = random.Random(3)
+    for data in _inputs(3, 250):
+        level = rnd.choice(LEVELS)
+        bound = lz_bound(len(data))
+        cap = rnd.choice([bound, bound, max(len(data) - 1, 1), len(data) // 2 + 1, rnd.randrange(1, bound + 1)])
+        want = refs.ref_compress(ref, data, level, cap)
+        assert o_compress(oracle, data, level, cap) == want, (level, len(data), cap)
+        assert shim_compress(shim, data, level, cap) == want, (level, len(data), cap)
+
+
+def test_decompress_parity_valid_and_corrupt(ref, oracle):
+    rnd = random.Random(9)
+    for data in _inputs(9, 120):
+        level = rnd.choice([10, 21, 41, 30, 17, 24])
+        comp = refs.ref_compress(ref, data, level)
+        r, out = o_decompress(oracle, comp, len(data))
+        assert r == len(data) and out == data
+        for _ in range(8):
+            bad = bytearray(comp)
+            mode = rnd.randrange(3)
+            if mode == 0 and bad:
+                bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+            elif mode == 1:
+                bad = bad[: rnd.randrange(0, len(bad) + 1)]
+            elif bad:
+                bad[rnd.randrange(min(len(bad), 30))] = rnd.randrange(256)
+            bad = bytes(bad)
+            cap = rnd.choice([len(data), len(data), max(len(data) - 1, 0), len(data) + 50])
+            rr, ro = refs.ref_decompress(ref, bad, cap)
+            r, out = o_decompress(oracle, bad, cap)
+            assert r == rr, (level, len(data), len(bad), cap)
+            if rr > 0:
+                assert out == ro
+
+
+def test_huffman_stage_parity(ref, oracle, shim):
+    spd = refs.ref_speed()
+    spd.HUF_compress.restype = ctypes.c_size_t
+    spd.HUF_compress.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    spd.HUF_decompress.restype = ctypes.c_size_t
+    spd.HUF_decompress.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t]
+    spd.HUF_isError.argtypes = [ctypes.c_size_t]
+    rnd = random.Random(4)
+    rng = np.random.default_rng(4)
+    for _ in range(300):
+        n = rnd.choice([13, 50, 300, 1025, 5000, 20000, 70000, 131072])
+        k = rnd.choice([2, 3, 16, 100, 256])
+        p = rng.dirichlet(np.ones(k) * rnd.choice([0.1, 0.5, 2.0]))
+        data = rng.choice(k, size=n, p=p).astype(np.uint8).tobytes()
+        cap = n + n // 256 + 8 + 129
+        a = ctypes.create_string_buffer(cap + 16)
+        b = ctypes.create_string_buffer(cap + 16)
+        ca = spd.HUF_compress(a, cap, data, n)
+        cb = oracle.oracle_HUF_compress(b, cap, data, n)
+        if spd.HUF_isError(ca):
+            assert cb == ctypes.c_size_t(-1).value
+            continue
+        assert ca == cb and (ca <= 1 or a.raw[:ca] == b.raw[:cb]), (n, k)
+        if ca <= 1:
+            continue
+        comp = bytearray(a.raw[:ca])
+        for trial in range(5):
+            bad = bytes(comp) if trial == 0 else bytes(_damage(comp, rnd))
+            nn = n if trial < 3 else n + rnd.choice([-1, 1])
+            d1 = ctypes.create_string_buffer(nn + 16)
+            d2 = ctypes.create_string_buffer(nn + 16)
+            d3 = ctypes.create_string_buffer(nn + 16)
+            r1 = spd.HUF_decompress(d1, nn, bad, len(bad))
+            r2 = oracle.oracle_HUF_decompress(d2, nn, bad, len(bad))
+            r3 = shim.lzb_host_huf_decompress(d3, nn, bad, len(bad))
+            e1 = bool(spd.HUF_isError(r1))
+            assert e1 == (r2 == ctypes.c_size_t(-1).value) == (r3 < 0), (n, k, trial)
+            if not e1:
+                assert d1.raw[:nn] == d2.raw[:nn] == d3.raw[:nn]
+
+
+def _damage(comp, rnd):
+    bad = bytearray(comp)
+    mode = rnd.randrange(3)
+    if mode == 0:
+        bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+    elif mode == 1:
+        bad = bad[: rnd.randrange(1, len(bad) + 1)]
+    else:
+        bad[-1] = rnd.randrange(256)
+    return bad
+
+
+def test_reference_facts_from_survey(ref):
+    """SURVEY.md section 8c regression facts, reproduced with the compiled reference itself."""
+    data = lz.datagen(4 << 20)
+    assert hashlib.md5(data).hexdigest() == "b4ac2db04e3844e152d1c9987ed8a711"
+    for level, single, blocks in ((10, 2475712, 2647396), (21, 2239670, 2431837), (41, 1413150, 1521776)):
+        assert len(refs.ref_compress(ref, data, level)) == single
+        assert sum(len(refs.ref_compress(ref, data[i:i + BS], level)) for i in range(0, len(data), BS)) == blocks
