@@ -91,6 +91,9 @@ int LizardB200_decompress_batch(const void* const* src, const int* compressedSiz
 int LizardB200_compress_blocks(const void* src, size_t srcSize, int blockSize,
                                void* dst, size_t dstStride, int dstCapacityEach, int* result,
                                int compressionLevel);
+/* Inverse: unit i = src + i*srcStride, compressedSize[i] bytes -> dst + i*blockSize (capacity blockSize). */
+int LizardB200_decompress_blocks(const void* src, size_t srcStride, const int* compressedSize, size_t nUnits,
+                                 void* dst, int blockSize, int* result);
 
 /* Device-pointer variants: everything (payload, offset/size tables, results) already lives in device memory
  * of the current device; the call only enqueues kernels on `cudaStream` (a cudaStream_t, may be NULL) and

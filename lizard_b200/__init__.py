@@ -45,6 +45,10 @@ def lib():
         dev_args = [ctypes.c_void_p] * 7 + [ctypes.c_uint]
         L.LizardB200_decompress_device.argtypes = dev_args + [ctypes.c_void_p]
         L.LizardB200_compress_device.argtypes = dev_args + [ctypes.c_int, ctypes.c_void_p]
+        L.LizardB200_compress_blocks.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
+                                                 ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+        L.LizardB200_decompress_blocks.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                                   ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         _lib = L
     return _lib
 

@@ -330,6 +330,86 @@ int LizardB200_compress_batch(const void* const* src, const int* srcSize, void* 
     return run_host_batch<true>(src, srcSize, dst, dstCap, result, n, level);
 }
 
+
+// Contiguous host buffers (what a frame writer / file splitter has).  Copies go straight from / to the
+// caller's memory (fast when it is pinned); tables are built on the host.
+int LizardB200_compress_blocks(const void* src, size_t srcSize, int blockSize,
+                               void* dst, size_t dstStride, int dstCapacityEach, int* result, int level)
+{
+    if (blockSize <= 0 || dstCapacityEach < 0 || (srcSize && (!src || !dst || !result))) return LIZARDB200_ERR_ARGUMENT;
+    const size_t n = (srcSize + (size_t)blockSize - 1) / (size_t)blockSize;
+    if (n == 0) return LIZARDB200_OK;
+    if ((size_t)dstCapacityEach > dstStride) return LIZARDB200_ERR_ARGUMENT;
+    Context& c = g_ctx[g_device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    int st = ensure_context(c, g_device);
+    if (st != LIZARDB200_OK) return st;
+    if (level_params(level).parser == kParserUnsupported) { g_last_error = "compression level not implemented on the GPU"; return LIZARDB200_ERR_LEVEL; }
+    const size_t tab_bytes = n * (8 + 4 + 8 + 4 + 4);
+    CU_OK(c.pin_tab.reserve(tab_bytes));
+    CU_OK(c.d_tab.reserve(tab_bytes));
+    CU_OK(c.d_in.reserve(srcSize + 64));
+    CU_OK(c.d_out.reserve(n * dstStride + 64));
+    u64* t_in_off = (u64*)c.pin_tab.p; u64* t_out_off = t_in_off + n;
+    u32* t_in_len = (u32*)(t_out_off + n); u32* t_out_cap = t_in_len + n; int* t_res = (int*)(t_out_cap + n);
+    for (size_t i = 0; i < n; ++i) {
+        t_in_off[i] = i * (size_t)blockSize; t_out_off[i] = i * dstStride;
+        const size_t left = srcSize - i * (size_t)blockSize;
+        t_in_len[i] = (u32)(left < (size_t)blockSize ? left : (size_t)blockSize);
+        t_out_cap[i] = (u32)dstCapacityEach;
+    }
+    cudaStream_t s = c.stream;
+    u8* dtab = (u8*)c.d_tab.p;
+    CU_OK(cudaMemcpyAsync(c.d_in.p, src, srcSize, cudaMemcpyHostToDevice, s));
+    CU_OK(cudaMemcpyAsync(dtab, c.pin_tab.p, tab_bytes - n * 4, cudaMemcpyHostToDevice, s));
+    const u64* d_in_off = (const u64*)dtab; const u64* d_out_off = d_in_off + n;
+    const u32* d_in_len = (const u32*)(d_out_off + n); const u32* d_out_cap = d_in_len + n; int* d_res = (int*)(d_out_cap + n);
+    st = launch_encode(c, c.d_in.p, d_in_off, d_in_len, c.d_out.p, d_out_off, d_out_cap, d_res, (u32)n, level, s);
+    if (st != LIZARDB200_OK) return st;
+    CU_OK(cudaMemcpyAsync(t_res, d_res, n * 4, cudaMemcpyDeviceToHost, s));
+    CU_OK(cudaMemcpyAsync(dst, c.d_out.p, n * dstStride, cudaMemcpyDeviceToHost, s));
+    CU_OK(cudaStreamSynchronize(s));
+    memcpy(result, t_res, n * 4);
+    return LIZARDB200_OK;
+}
+
+int LizardB200_decompress_blocks(const void* src, size_t srcStride, const int* compressedSize, size_t nUnits,
+                                 void* dst, int blockSize, int* result)
+{
+    if (blockSize <= 0 || (nUnits && (!src || !dst || !result || !compressedSize))) return LIZARDB200_ERR_ARGUMENT;
+    const size_t n = nUnits;
+    if (n == 0) return LIZARDB200_OK;
+    Context& c = g_ctx[g_device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    int st = ensure_context(c, g_device);
+    if (st != LIZARDB200_OK) return st;
+    const size_t tab_bytes = n * (8 + 4 + 8 + 4 + 4);
+    CU_OK(c.pin_tab.reserve(tab_bytes));
+    CU_OK(c.d_tab.reserve(tab_bytes));
+    CU_OK(c.d_in.reserve(n * srcStride + 64));
+    CU_OK(c.d_out.reserve(n * (size_t)blockSize + 64));
+    u64* t_in_off = (u64*)c.pin_tab.p; u64* t_out_off = t_in_off + n;
+    u32* t_in_len = (u32*)(t_out_off + n); u32* t_out_cap = t_in_len + n; int* t_res = (int*)(t_out_cap + n);
+    for (size_t i = 0; i < n; ++i) {
+        if (compressedSize[i] < 0 || (size_t)compressedSize[i] > srcStride) return LIZARDB200_ERR_ARGUMENT;
+        t_in_off[i] = i * srcStride; t_out_off[i] = i * (size_t)blockSize;
+        t_in_len[i] = (u32)compressedSize[i]; t_out_cap[i] = (u32)blockSize;
+    }
+    cudaStream_t s = c.stream;
+    u8* dtab = (u8*)c.d_tab.p;
+    CU_OK(cudaMemcpyAsync(c.d_in.p, src, n * srcStride, cudaMemcpyHostToDevice, s));
+    CU_OK(cudaMemcpyAsync(dtab, c.pin_tab.p, tab_bytes - n * 4, cudaMemcpyHostToDevice, s));
+    const u64* d_in_off = (const u64*)dtab; const u64* d_out_off = d_in_off + n;
+    const u32* d_in_len = (const u32*)(d_out_off + n); const u32* d_out_cap = d_in_len + n; int* d_res = (int*)(d_out_cap + n);
+    st = launch_decode(c, c.d_in.p, d_in_off, d_in_len, c.d_out.p, d_out_off, d_out_cap, d_res, (u32)n, s);
+    if (st != LIZARDB200_OK) return st;
+    CU_OK(cudaMemcpyAsync(t_res, d_res, n * 4, cudaMemcpyDeviceToHost, s));
+    CU_OK(cudaMemcpyAsync(dst, c.d_out.p, n * (size_t)blockSize, cudaMemcpyDeviceToHost, s));
+    CU_OK(cudaStreamSynchronize(s));
+    memcpy(result, t_res, n * 4);
+    return LIZARDB200_OK;
+}
+
 int Lizard_decompress_safe(const char* src, char* dst, int compressedSize, int maxDecompressedSize)
 {
     // lib/lizard_decompress.c:139: inputSize < 1 -> 0 before anything is read
