@@ -80,6 +80,9 @@ struct HostLanes {
     LZ_HDM static int bcast(int v) { return v; }
     LZ_HDM static u32 sum(u32 v) { return v; }
     LZ_HDM static u32 excl_scan(u32 v, u32* total) { *total = v; return 0; }
+    LZ_HDM static u32 ballot(bool p) { return p ? 1u : 0u; }
+    LZ_HDM static u32 shfl(u32 v, u32) { return v; }
+    LZ_HDM static u32 match_any(u32) { return 1u; }
 };
 #if defined(__CUDACC__)
 struct WarpLanes {
@@ -100,6 +103,9 @@ struct WarpLanes {
         *total = __shfl_sync(0xffffffffu, x, 31);
         return x - v;
     }
+    __device__ __forceinline__ static u32 ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+    __device__ __forceinline__ static u32 shfl(u32 v, u32 src) { return __shfl_sync(0xffffffffu, v, (int)src); }
+    __device__ __forceinline__ static u32 match_any(u32 v) { return __match_any_sync(0xffffffffu, v); }
 };
 #endif
 
@@ -256,6 +262,167 @@ last_literals:
     emit_last_literals<W>(s, src, anchor, b1);
 }
 
+// ---- lane-parallel building blocks ---------------------------------------------------------------------
+LZ_HD u32 ctz32(u32 v)
+{
+#if defined(__CUDA_ARCH__)
+    return (u32)(__ffs((int)v) - 1);
+#else
+    return (u32)__builtin_ctz(v);
+#endif
+}
+
+// Position of the j-th probe of one fastSmall search relative to its first probe: the stride grows by one
+// every 64 probes (step = searchMatchNb++ >> 6, lizard_parser_fastsmall.h:69-75), so the offsets are
+// 0,1,2,...,65,67,69,... independent of the data.
+LZ_HD u32 probe_offset(u32 j)
+{
+    if (j == 0) return 0;
+    const u32 m = 62 + j;
+    if (m < 64) return 1;
+    const u32 q = m >> 6;
+    return 1 + 32 * q * (q - 1) + q * (m - 64 * q + 1);
+}
+
+// Lizard_count with the lanes comparing consecutive 8-byte groups
+template <class W> LZ_HD u32 count_match_par(const u8* a, const u8* b, const u8* limit)
+{
+    u32 total = 0;
+    for (;;) {
+        const u32 off = total + 8 * W::lane();
+        const u8* pa = a + off;
+        u32 n = 0; bool full = false;
+        if (pa + 8 <= limit) {
+            const u64 d = ld64(pa) ^ ld64(b + off);
+            if (d == 0) { n = 8; full = true; }
+            else {
+#if defined(__CUDA_ARCH__)
+                n = (u32)(__ffsll((long long)d) - 1) >> 3;
+#else
+                n = (u32)__builtin_ctzll(d) >> 3;
+#endif
+            }
+        } else {
+            while (pa + n < limit && pa[n] == b[off + n]) n++;
+        }
+        const u32 stop = W::ballot(!full);
+        if (stop) { const u32 f = ctz32(stop); return total + 8 * f + W::shfl(n, f); }
+        total += 8 * W::lanes();
+    }
+}
+
+// backward extension: how many bytes before (ip, mpos) are equal, not crossing anchor / position 0
+template <class W> LZ_HD u32 extend_back_par(const u8* src, u32 ip, u32 mpos, u32 anchor)
+{
+    u32 done = 0;
+    for (;;) {
+        const u32 k = done + W::lane() + 1;
+        const bool can = ip >= anchor + k && mpos >= k;
+        const bool eq = can && src[ip - k] == src[mpos - k];
+        const u32 bad = W::ballot(!eq);
+        if (bad) return done + ctz32(bad);
+        done += W::lanes();
+    }
+}
+
+// Lizard_compress_fastSmall / Lizard_compress_fast with the no-match run probed W::lanes() positions at a
+// time.  Exactness argument: inside one search the probe positions do not depend on the data, each probe
+// reads its bucket after all earlier probes wrote theirs, and the search stops at the first probe that
+// matches.  So lanes evaluate probes j0..j0+L-1 together; a lane's candidate is the latest earlier lane of
+// the same batch with the same bucket, else the table; the lowest hitting lane wins and only buckets of
+// lanes up to the winner are committed (last writer per bucket).
+template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, EncStreams& s)
+{
+    const u8* const src = c.src;
+    u32* const table = c.table;
+    const u32 hl = c.hash_log;
+    const u32 lane = W::lane(), NL = W::lanes();
+    const bool wr = lane == 0;
+    const u32 max_dist = (1u << c.window_log) - 1;
+    const u32 bias = kDictSize;
+    const u32 low_limit = (bias + max_dist >= b0 + bias) ? bias : b0 + bias - max_dist;
+    u32 anchor = b0, ip = b0;
+    u32 ml = 0, mpos = 0;
+    if (b1 - b0 < kMinInputForLz) goto last_literals;
+    {
+        const u32 mflimit = b1 - kMfLimit;
+        const u8* const matchlimit = src + b1 - kLastLiterals;
+        if (wr) table[hash5(ld64(src + ip), hl)] = ip + bias;
+        W::sync();
+        ip++;
+        for (;;) {
+            {   // ---- search: batches of NL probes ----
+                const u32 ip0 = ip;
+                u32 j0 = 0;
+                for (;;) {
+                    const u32 j = j0 + lane;
+                    const u32 P = ip0 + probe_offset(j);
+                    const bool valid = ip0 + probe_offset(j + 1) <= mflimit;   // else this probe ends the block
+                    u64 v = 0; u32 h = 0x80000000u | lane;                     // unique key: matches nobody
+                    if (valid) { v = ld64(src + P); h = hash5(v, hl); }
+                    const u32 peers = W::match_any(h);
+                    const u32 below = peers & ((1u << lane) - 1);
+                    const u32 pl = below ? highbit32(below) : lane;
+                    const u32 prevP = W::shfl(P, pl);
+                    const u32 cur = P + bias;
+                    u32 cand = 0;
+                    if (valid) cand = below ? prevP + bias : table[h];
+                    bool hit = false;
+                    if (valid && cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset)
+                        hit = ld32(src + (cand - bias)) == (u32)v;
+                    const u32 hits = W::ballot(hit);
+                    const u32 term = W::ballot(!valid);
+                    const u32 w_lane = hits ? ctz32(hits) : 32;
+                    const u32 t_lane = term ? ctz32(term) : 32;
+                    const bool matched = w_lane < t_lane;
+                    // lanes whose table write happens in program order before the search stops
+                    u32 commit;
+                    if (matched) commit = (w_lane >= 31) ? 0xffffffffu : ((2u << w_lane) - 1);
+                    else commit = (t_lane >= 32) ? 0xffffffffu : ((1u << t_lane) - 1);
+                    W::sync();
+                    if ((commit >> lane) & 1) {
+                        const u32 grp = peers & commit;
+                        if (highbit32(grp) == lane) table[h] = cur;
+                    }
+                    W::sync();
+                    if (matched) { ip = W::shfl(P, w_lane); mpos = W::shfl(cand, w_lane) - bias; break; }
+                    if (t_lane < 32) { goto last_literals; }
+                    j0 += NL;
+                }
+                ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
+                const u32 back = extend_back_par<W>(src, ip, mpos, anchor);
+                ip -= back; mpos -= back; ml += back;
+            }
+            for (;;) {   // _next_match
+                emit_lz4<W>(s, src, anchor, ip, ml + kMinMatch, ip - mpos);
+                ip += ml + kMinMatch;
+                anchor = ip;
+                if (ip > mflimit) goto last_literals;
+                if (wr) table[hash5(ld64(src + ip - 2), hl)] = ip - 2 + bias;
+                W::sync();
+                const u64 v = ld64(src + ip);
+                const u32 h = hash5(v, hl);
+                const u32 cand = table[h];
+                W::sync();
+                if (wr) table[h] = ip + bias;
+                W::sync();
+                const u32 cur = ip + bias;
+                if (cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset) {
+                    mpos = cand - bias;
+                    if (ld32(src + mpos) == (u32)v) {
+                        ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
+                        continue;
+                    }
+                }
+                break;
+            }
+            ip++;
+        }
+    }
+last_literals:
+    emit_last_literals<W>(s, src, anchor, b1);
+}
+
 // conditional table update of the priceFast family (lizard_parser_pricefast.h:170-171)
 LZ_HD void pf_update(u32* slot, u32 cur, bool wr)
 {
@@ -347,6 +514,129 @@ template <class W> LZ_HD void parse_price_fast(const ParseCtx& c, u32 b0, u32 b1
                 }
             }
             // _Encode
+            emit_lizv1<W>(s, src, anchor, ip, ml, ip - ref, last_off);
+            ip += ml;
+            anchor = ip;
+            if (!ml2) break;
+            ip = start2; ref = ref2; ml = ml2; ml2 = 0;
+            encode_now = false;
+        }
+    }
+    }
+    emit_last_literals<W>(s, src, anchor, b1);
+}
+
+// Lizard_compress_priceFast with the no-match run probed W::lanes() consecutive positions at a time.
+// Per position the reference (lizard_parser_pricefast.h:158-173) tests the repeat offset first, then the
+// bucket's candidate, then conditionally refreshes the bucket.  last_off is constant during a no-match run,
+// positions advance by one, so L lanes evaluate L consecutive positions; the only cross-lane dependency is
+// the bucket value, which each lane reconstructs by replaying the conditional updates of the earlier lanes
+// that share its bucket.  The lowest hitting lane wins; buckets of lanes up to the winner are committed.
+template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u32 b1, EncStreams& s, u32 min_match_long)
+{
+    const u8* const src = c.src;
+    u32* const table = c.table;
+    const u32 hl = c.hash_log;
+    const u32 lane = W::lane(), NL = W::lanes();
+    const bool wr = lane == 0;
+    const u32 bias = kDictSize;
+    const u32 max_dist = (1u << c.window_log) - 1;
+    u32 anchor = b0, ip = b0 + 1;
+    u32 last_off = 0;
+    if (b1 - b0 >= kMfLimit) {
+    const u32 mflimit = b1 - kMfLimit;
+    const u8* const matchlimit = src + b1 - kLastLiterals;
+    while (ip < mflimit) {
+        u32 ml = 0, ref = 0;
+        {   // ---- batch of NL positions ----
+            const u32 P = ip + lane;
+            const bool valid = P < mflimit;
+            const u32 cur = P + bias;
+            const u32 low = (bias + max_dist >= cur) ? bias : cur - max_dist;
+            u64 v = 0; u32 h = 0x80000000u | lane;
+            if (valid) { v = ld64(src + P); h = hash5(v, hl); }
+            const u32 peers = W::match_any(h);
+            u32 below = peers & ((1u << lane) - 1);
+            u32 seen = valid ? table[h] : 0;
+            while (below) {                                   // replay earlier same-bucket lanes, in order
+                const u32 bl = ctz32(below); below &= below - 1;
+                const u32 pb = ip + bl + bias;
+                if (seen >= pb || pb >= seen + kMinOffset) seen = pb;
+            }
+            bool rep_hit = false, hash_hit = false;
+            if (valid) {
+                if (last_off >= kMinOffset && last_off <= P && cur - last_off >= low)
+                    rep_hit = ld32(src + (P - last_off)) == (u32)v;
+                if (!rep_hit && seen < cur && seen >= low) {
+                    const u32 m = seen - bias;
+                    if (P - m >= kMinOffset && ld32(src + m) == (u32)v) {
+                        if (P - m < kMax16BitOffset) hash_hit = true;
+                        else hash_hit = count_match(src + P + kMinMatch, src + m + kMinMatch, matchlimit) + kMinMatch >= min_match_long;
+                    }
+                }
+            }
+            const u32 newval = (seen >= cur || cur >= seen + kMinOffset) ? cur : seen;
+            const u32 hits = W::ballot(rep_hit || hash_hit);
+            const u32 vmask = W::ballot(valid);
+            const u32 w_lane = hits ? ctz32(hits) : 32;
+            const u32 commit = (w_lane < 32) ? ((w_lane >= 31) ? 0xffffffffu : ((2u << w_lane) - 1)) : vmask;
+            W::sync();
+            if ((commit >> lane) & 1) {
+                const u32 grp = peers & commit;
+                if (highbit32(grp) == lane) table[h] = newval;
+            }
+            W::sync();
+            if (w_lane == 32) { ip += NL; continue; }
+            ip = W::shfl(P, w_lane);
+            const u32 is_rep = W::shfl(rep_hit ? 1u : 0u, w_lane);
+            ref = is_rep ? ip - last_off : W::shfl(seen, w_lane) - bias;
+            ml = count_match_par<W>(src + ip + kMinMatch, src + ref + kMinMatch, matchlimit) + kMinMatch;
+        }
+
+        u32 ml2 = 0, start2 = 0, ref2 = 0;
+        bool encode_now = false;
+        if (ip - ref == last_off) { ref = ip; encode_now = true; }
+        else { const u32 back = extend_back_par<W>(src, ip, ref, anchor); ip -= back; ref -= back; ml += back; }
+
+        for (;;) {
+            if (!encode_now) {
+                while (true) {
+                    if (ip + ml >= mflimit) break;
+                    start2 = ip + ml - 2;
+                    {   // Lizard_FindMatchFaster (uniform: one position)
+                        const u32 cur2 = start2 + bias;
+                        const u32 low2 = (bias + max_dist >= cur2) ? bias : cur2 - max_dist;
+                        const u64 v2 = ld64(src + start2);
+                        u32* slot2 = &table[hash5(v2, hl)];
+                        const u32 cand2 = *slot2;
+                        ml2 = 0;
+                        bool ok = false; u32 m = 0;
+                        if (cand2 < cur2 && cand2 >= low2) {
+                            m = cand2 - bias;
+                            ok = start2 - m >= kMinOffset && ld32(src + m) == (u32)v2;
+                        }
+                        W::sync();
+                        pf_update(slot2, cur2, wr);
+                        W::sync();
+                        if (ok) {
+                            const u32 mlt = count_match_par<W>(src + start2 + kMinMatch, src + m + kMinMatch, matchlimit) + kMinMatch;
+                            if (mlt >= min_match_long || start2 - m < kMax16BitOffset) { ml2 = mlt; ref2 = m; }
+                        }
+                    }
+                    if (!ml2) break;
+                    {   const u32 back = extend_back_par<W>(src, start2, ref2, ip); start2 -= back; ref2 -= back; ml2 += back; }
+                    if (ml2 <= ml) { ml2 = 0; break; }
+                    if (start2 <= ip) { ip = start2; ref = ref2; ml = ml2; ml2 = 0; break; }
+                    if (start2 - ip < 3) { ip = start2; ref = ref2; ml = ml2; ml2 = 0; continue; }
+                    if (start2 < ip + ml) {
+                        const u32 corr = ml - (start2 - ip);
+                        start2 += corr; ref2 += corr; ml2 -= corr;
+                        if (ml2 < 3) ml2 = 0;
+                        if (ml2 < min_match_long && start2 - ref2 >= kMax16BitOffset) ml2 = 0;
+                    }
+                    break;
+                }
+            }
             emit_lizv1<W>(s, src, anchor, ip, ml, ip - ref, last_off);
             ip += ml;
             anchor = ip;
@@ -507,6 +797,7 @@ template <class W> LZ_HD int write_block(const EncStreams& s, const u8* in, u32 
         else return 0;
     }
     if ((u32)(oend - start) < in_size + 4 || oend - start < 0) return 1;
+    W::sync();      // the abandoned stream bytes (written by lane 0) must not land after the raw copy
     if (wr) { dst[start] = (u8)kFlagRaw; wr_le24(dst + start + 1, in_size); }
     lanes_copy<W>(dst + start + 4, in, in_size);
     op = start + 4 + (long)in_size;
@@ -543,8 +834,8 @@ template <class W> LZ_HD int encode_unit(const u8* src, u32 src_size, u8* dst, u
         EncStreams s;
         s.lits = work->lits; s.flags = work->flags; s.off16 = work->off16; s.off24 = work->off24;
         s.nl = s.nf = s.n16 = s.n24 = 0;
-        if (lp.parser == kParserPriceFast) parse_price_fast<W>(pc, pos, pos + part, s, lp.minMatchLongOff);
-        else parse_fast<W>(pc, pos, pos + part, s);
+        if (lp.parser == kParserPriceFast) parse_price_fast_par<W>(pc, pos, pos + part, s, lp.minMatchLongOff);
+        else parse_fast_par<W>(pc, pos, pos + part, s);
         W::sync();
         if (write_block<W>(s, src + pos, part, dst, op, oend, lp.huffman != 0, &work->huf)) return 0;
         W::sync();

@@ -29,3 +29,137 @@ extern "C" int lzb_host_compress(const unsigned char* src, int n, unsigned char*
     free(work->huf.seg_count); free(table); free(work);
     return r;
 }
+
+// =====================================================================================================
+// 32-lane warp emulator (TEST-ONLY).  The lane-parallel code paths (ballot / shuffle / match_any based)
+// only exist for 32 lanes, and there is no GPU in the build container, so the CPU suite runs them on 32
+// cooperative coroutines (ucontext): every collective is a rendezvous of all lanes, exactly the
+// warp-synchronous model the kernels are written in.  Shared data (hash table, streams) is ordinary memory.
+// =====================================================================================================
+#include <ucontext.h>
+#include <vector>
+
+namespace emu {
+constexpr int kLanes = 32;
+struct Warp {
+    ucontext_t sched;
+    ucontext_t ctx[kLanes];
+    std::vector<char> stack[kLanes];
+    int cur = 0;
+    bool done[kLanes];
+    unsigned long long slot[kLanes];
+    int arrived = 0, readers = 0;
+    unsigned gen = 0, gen2 = 0;
+    void (*body)(void*) = nullptr;
+    void* arg = nullptr;
+};
+static Warp* g = nullptr;
+
+static void yield() { swapcontext(&g->ctx[g->cur], &g->sched); }
+
+// all lanes deposit a value; returns when every lane has deposited; out[] is a private copy
+static void exchange(unsigned long long v, unsigned long long* out)
+{
+    Warp* w = g;
+    const int me = w->cur;
+    w->slot[me] = v;
+    {   unsigned my = w->gen;
+        if (++w->arrived == kLanes) { w->arrived = 0; w->gen++; }
+        else while (w->gen == my) yield(); }
+    for (int i = 0; i < kLanes; ++i) out[i] = w->slot[i];
+    {   unsigned my = w->gen2;
+        if (++w->readers == kLanes) { w->readers = 0; w->gen2++; }
+        else while (w->gen2 == my) yield(); }
+}
+
+static void trampoline()
+{
+    Warp* w = g;
+    w->body(w->arg);
+    w->done[w->cur] = true;
+    swapcontext(&w->ctx[w->cur], &w->sched);
+}
+
+static void run(void (*body)(void*), void* arg)
+{
+    Warp w;
+    g = &w;
+    w.body = body; w.arg = arg;
+    for (int i = 0; i < kLanes; ++i) {
+        w.done[i] = false;
+        w.stack[i].resize(256 * 1024);
+        getcontext(&w.ctx[i]);
+        w.ctx[i].uc_stack.ss_sp = w.stack[i].data();
+        w.ctx[i].uc_stack.ss_size = w.stack[i].size();
+        w.ctx[i].uc_link = &w.sched;
+        makecontext(&w.ctx[i], (void (*)())trampoline, 0);
+    }
+    for (;;) {
+        bool any = false;
+        for (int i = 0; i < kLanes; ++i) {
+            if (w.done[i]) continue;
+            any = true;
+            w.cur = i;
+            swapcontext(&w.sched, &w.ctx[i]);
+        }
+        if (!any) break;
+    }
+    g = nullptr;
+}
+}  // namespace emu
+
+struct EmuLanes {
+    static constexpr bool kDevice = false;
+    static lzb::u32 lane() { return (lzb::u32)emu::g->cur; }
+    static lzb::u32 lanes() { return emu::kLanes; }
+    static void sync() { unsigned long long t[emu::kLanes]; emu::exchange(0, t); }
+    static int bcast(int v) { unsigned long long t[emu::kLanes]; emu::exchange((unsigned long long)(unsigned)v, t); return (int)(unsigned)t[0]; }
+    static lzb::u32 sum(lzb::u32 v) { unsigned long long t[emu::kLanes]; emu::exchange(v, t); lzb::u32 s = 0; for (auto x : t) s += (lzb::u32)x; return s; }
+    static lzb::u32 excl_scan(lzb::u32 v, lzb::u32* total)
+    {
+        unsigned long long t[emu::kLanes]; emu::exchange(v, t);
+        lzb::u32 pre = 0, tot = 0;
+        for (int i = 0; i < emu::kLanes; ++i) { if (i < emu::g->cur) pre += (lzb::u32)t[i]; tot += (lzb::u32)t[i]; }
+        *total = tot; return pre;
+    }
+    static lzb::u32 ballot(bool p)
+    {
+        unsigned long long t[emu::kLanes]; emu::exchange(p ? 1 : 0, t);
+        lzb::u32 m = 0; for (int i = 0; i < emu::kLanes; ++i) if (t[i]) m |= 1u << i; return m;
+    }
+    static lzb::u32 shfl(lzb::u32 v, lzb::u32 src)
+    {
+        unsigned long long t[emu::kLanes]; emu::exchange(v, t); return (lzb::u32)t[src & 31];
+    }
+    static lzb::u32 match_any(lzb::u32 v)
+    {
+        unsigned long long t[emu::kLanes]; emu::exchange(v, t);
+        lzb::u32 m = 0; for (int i = 0; i < emu::kLanes; ++i) if ((lzb::u32)t[i] == v) m |= 1u << i; return m;
+    }
+};
+
+struct EmuCompressArgs { const unsigned char* src; int n; unsigned char* dst; int cap; int level; lzb::u32* table; lzb::EncWork* work; int result; };
+static void emu_compress_body(void* p)
+{
+    EmuCompressArgs* a = (EmuCompressArgs*)p;
+    int r = lzb::encode_unit<EmuLanes>(a->src, (lzb::u32)a->n, a->dst, (lzb::u32)a->cap, a->level, a->table, a->work);
+    if (EmuLanes::lane() == 0) a->result = r;
+}
+
+// Lizard_compress through the 32-lane emulation of the device code path
+extern "C" int lzb_emu_compress(const unsigned char* src, int n, unsigned char* dst, int cap, int level)
+{
+    if (n < 0 || cap < 0) return 0;
+    if (level > 49) level = 49;
+    if (level < 10) level = 17;
+    lzb::LevelParams lp = lzb::level_params(level);
+    if (lp.parser == lzb::kParserUnsupported) return 0;
+    EmuCompressArgs a;
+    a.src = src; a.n = n; a.dst = dst; a.cap = cap; a.level = level; a.result = 0;
+    a.table = (lzb::u32*)malloc(sizeof(lzb::u32) << lp.hashLog);
+    a.work = (lzb::EncWork*)malloc(sizeof(lzb::EncWork));
+    a.work->huf.seg_count = (lzb::u32 (*)[256])malloc(4 * 256 * sizeof(lzb::u32));
+    emu::run(emu_compress_body, &a);
+    free(a.work->huf.seg_count); free(a.table); free(a.work);
+    return a.result;
+}

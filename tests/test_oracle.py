@@ -39,6 +39,7 @@ def _shim():
     L = ctypes.CDLL(p)
     L.lzb_host_compress.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
     L.lzb_host_huf_decompress.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_char_p, ctypes.c_uint]
+    L.lzb_emu_compress.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
     return L
 
 
@@ -71,6 +72,14 @@ def shim_compress(L, data, level, cap=None):
     cap = lz_bound(len(data)) if cap is None else cap
     dst = ctypes.create_string_buffer(max(cap, 1) + 64)
     n = L.lzb_host_compress(data, len(data), dst, cap, level)
+    return dst.raw[:n]
+
+
+def emu_compress(L, data, level, cap=None):
+    """The device code path (ballot / shuffle / match_any, 32 lanes) run on the coroutine warp emulator."""
+    cap = lz_bound(len(data)) if cap is None else cap
+    dst = ctypes.create_string_buffer(max(cap, 1) + 64)
+    n = L.lzb_emu_compress(data, len(data), dst, cap, level)
     return dst.raw[:n]
 
 
@@ -186,6 +195,18 @@ def test_compress_parity_fuzz(ref, oracle, shim):
         want = refs.ref_compress(ref, data, level, cap)
         assert o_compress(oracle, data, level, cap) == want, (level, len(data), cap)
         assert shim_compress(shim, data, level, cap) == want, (level, len(data), cap)
+
+
+@pytest.mark.parametrize("level", LEVELS)
+def test_warp_emulated_device_path_bit_exact(ref, shim, level):
+    """32-lane lane-parallel parsers + Huffman packer (the code the GPU runs) vs the reference."""
+    rnd = random.Random(level)
+    data = lz.datagen(BS + 3000, 50, level)
+    assert emu_compress(shim, data[:BS], level, BS - 1) == refs.ref_compress(ref, data[:BS], level, BS - 1)
+    assert emu_compress(shim, data, level) == refs.ref_compress(ref, data, level)      # two inner blocks
+    for d in _inputs(100 + level, 14):
+        cap = rnd.choice([lz_bound(len(d)), max(len(d) - 1, 1), len(d) // 2 + 1])
+        assert emu_compress(shim, d, level, cap) == refs.ref_compress(ref, d, level, cap), (level, len(d), cap)
 
 
 def test_decompress_parity_valid_and_corrupt(ref, oracle):
