@@ -69,6 +69,62 @@ int Lizard_compress_extState(void* state, const char* src, char* dst, int srcSiz
 int Lizard_decompress_safe(const char* src, char* dst, int compressedSize, int maxDecompressedSize);
 
 /* ---------------------------------------------------------------------------------------------
+ * (1b) drop-in frame layer: same names, types and error values as lib/lizard_frame.h:57-297 and
+ *      lib/lizard_frame_static.h:56-67.  Frame format: doc/lizard_Frame_format.md (magic 0x184D2206).
+ *      All full blocks handed to one LizardF_compressUpdate / LizardF_compressFrame / LizardF_decompress
+ *      call are processed by ONE batch on the GPU (reference loops: lib/lizard_frame.c:544-556, 1010-1320).
+ *      Only LizardF_blockIndependent is supported (linked blocks need the out-of-scope streaming dictionary
+ *      API): a linked request / frame returns -LizardF_ERROR_blockMode_invalid.  NOTE that, as in the
+ *      reference, a zeroed LizardF_preferences_t means blockLinked: set blockMode = LizardF_blockIndependent
+ *      (the reference CLI does, programs/lizardio.c:109).
+ * ------------------------------------------------------------------------------------------- */
+typedef size_t LizardF_errorCode_t;
+typedef enum { LizardF_default = 0, LizardF_max128KB = 1, LizardF_max256KB = 2, LizardF_max1MB = 3, LizardF_max4MB = 4,
+               LizardF_max16MB = 5, LizardF_max64MB = 6, LizardF_max256MB = 7 } LizardF_blockSizeID_t;
+typedef enum { LizardF_blockLinked = 0, LizardF_blockIndependent } LizardF_blockMode_t;
+typedef enum { LizardF_noContentChecksum = 0, LizardF_contentChecksumEnabled } LizardF_contentChecksum_t;
+typedef enum { LizardF_frame = 0, LizardF_skippableFrame } LizardF_frameType_t;
+typedef struct {
+    LizardF_blockSizeID_t     blockSizeID;
+    LizardF_blockMode_t       blockMode;
+    LizardF_contentChecksum_t contentChecksumFlag;
+    LizardF_frameType_t       frameType;
+    unsigned long long        contentSize;
+    unsigned                  reserved[2];
+} LizardF_frameInfo_t;
+typedef struct {
+    LizardF_frameInfo_t frameInfo;
+    int      compressionLevel;
+    unsigned autoFlush;
+    unsigned reserved[4];
+} LizardF_preferences_t;
+typedef struct { unsigned stableSrc; unsigned reserved[3]; } LizardF_compressOptions_t;
+typedef struct { unsigned stableDst; unsigned reserved[3]; } LizardF_decompressOptions_t;
+typedef struct LizardF_cctx_s* LizardF_compressionContext_t;
+typedef struct LizardF_dctx_s* LizardF_decompressionContext_t;
+#define LIZARDF_VERSION 100
+
+unsigned    LizardF_isError(LizardF_errorCode_t code);
+const char* LizardF_getErrorName(LizardF_errorCode_t code);
+size_t LizardF_compressFrameBound(size_t srcSize, const LizardF_preferences_t* preferencesPtr);
+size_t LizardF_compressFrame(void* dstBuffer, size_t dstMaxSize, const void* srcBuffer, size_t srcSize,
+                             const LizardF_preferences_t* preferencesPtr);
+LizardF_errorCode_t LizardF_createCompressionContext(LizardF_compressionContext_t* cctxPtr, unsigned version);
+LizardF_errorCode_t LizardF_freeCompressionContext(LizardF_compressionContext_t cctx);
+size_t LizardF_compressBegin(LizardF_compressionContext_t cctx, void* dstBuffer, size_t dstMaxSize, const LizardF_preferences_t* prefsPtr);
+size_t LizardF_compressBound(size_t srcSize, const LizardF_preferences_t* prefsPtr);
+size_t LizardF_compressUpdate(LizardF_compressionContext_t cctx, void* dstBuffer, size_t dstMaxSize, const void* srcBuffer,
+                              size_t srcSize, const LizardF_compressOptions_t* cOptPtr);
+size_t LizardF_flush(LizardF_compressionContext_t cctx, void* dstBuffer, size_t dstMaxSize, const LizardF_compressOptions_t* cOptPtr);
+size_t LizardF_compressEnd(LizardF_compressionContext_t cctx, void* dstBuffer, size_t dstMaxSize, const LizardF_compressOptions_t* cOptPtr);
+LizardF_errorCode_t LizardF_createDecompressionContext(LizardF_decompressionContext_t* dctxPtr, unsigned version);
+LizardF_errorCode_t LizardF_freeDecompressionContext(LizardF_decompressionContext_t dctx);
+size_t LizardF_getFrameInfo(LizardF_decompressionContext_t dctx, LizardF_frameInfo_t* frameInfoPtr,
+                            const void* srcBuffer, size_t* srcSizePtr);
+size_t LizardF_decompress(LizardF_decompressionContext_t dctx, void* dstBuffer, size_t* dstSizePtr,
+                          const void* srcBuffer, size_t* srcSizePtr, const LizardF_decompressOptions_t* dOptPtr);
+
+/* ---------------------------------------------------------------------------------------------
  * (2) batch symbols
  * ------------------------------------------------------------------------------------------- */
 /* Select the CUDA device used by this thread's subsequent calls (default 0). Returns LIZARDB200_OK or error. */

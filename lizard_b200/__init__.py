@@ -135,3 +135,98 @@ def datagen_into(ptr: int, size: int, match_pct: float = 50.0, seed: int = 0, li
     """Same generator, writing into caller memory (e.g. a pinned torch tensor's data_ptr())."""
     if _load_dg().lizb200_datagen(ctypes.c_void_p(ptr), size, match_pct, lit_pct, seed) != 0:
         raise LizardB200Error("datagen failed")
+
+
+# ---- frame layer (LizardF_*) -----------------------------------------------------------------------------------
+class FrameInfo(ctypes.Structure):
+    _fields_ = [("blockSizeID", ctypes.c_int), ("blockMode", ctypes.c_int), ("contentChecksumFlag", ctypes.c_int),
+                ("frameType", ctypes.c_int), ("contentSize", ctypes.c_ulonglong), ("reserved", ctypes.c_uint * 2)]
+
+
+class Preferences(ctypes.Structure):
+    _fields_ = [("frameInfo", FrameInfo), ("compressionLevel", ctypes.c_int), ("autoFlush", ctypes.c_uint),
+                ("reserved", ctypes.c_uint * 4)]
+
+
+def make_prefs(level, block_id=1, independent=True, checksum=False, content_size=0):
+    p = Preferences()
+    p.frameInfo.blockSizeID = block_id
+    p.frameInfo.blockMode = 1 if independent else 0
+    p.frameInfo.contentChecksumFlag = 1 if checksum else 0
+    p.frameInfo.contentSize = content_size
+    p.compressionLevel = level
+    return p
+
+
+def bind_frame_api(L):
+    """Set ctypes signatures of the LizardF_* symbols on a library handle (ours or the compiled reference)."""
+    sz = ctypes.c_size_t
+    L.LizardF_isError.argtypes = [sz]
+    L.LizardF_getErrorName.argtypes = [sz]
+    L.LizardF_getErrorName.restype = ctypes.c_char_p
+    L.LizardF_compressFrameBound.restype = sz
+    L.LizardF_compressFrameBound.argtypes = [sz, ctypes.c_void_p]
+    L.LizardF_compressFrame.restype = sz
+    L.LizardF_compressFrame.argtypes = [ctypes.c_void_p, sz, ctypes.c_void_p, sz, ctypes.c_void_p]
+    L.LizardF_createCompressionContext.restype = sz
+    L.LizardF_createCompressionContext.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint]
+    L.LizardF_freeCompressionContext.argtypes = [ctypes.c_void_p]
+    for name in ("LizardF_compressBegin",):
+        getattr(L, name).restype = sz
+        getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, sz, ctypes.c_void_p]
+    L.LizardF_compressBound.restype = sz
+    L.LizardF_compressBound.argtypes = [sz, ctypes.c_void_p]
+    L.LizardF_compressUpdate.restype = sz
+    L.LizardF_compressUpdate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, sz, ctypes.c_void_p, sz, ctypes.c_void_p]
+    for name in ("LizardF_flush", "LizardF_compressEnd"):
+        getattr(L, name).restype = sz
+        getattr(L, name).argtypes = [ctypes.c_void_p, ctypes.c_void_p, sz, ctypes.c_void_p]
+    L.LizardF_createDecompressionContext.restype = sz
+    L.LizardF_createDecompressionContext.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_uint]
+    L.LizardF_freeDecompressionContext.restype = sz
+    L.LizardF_freeDecompressionContext.argtypes = [ctypes.c_void_p]
+    L.LizardF_decompress.restype = sz
+    L.LizardF_decompress.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(sz), ctypes.c_void_p,
+                                     ctypes.POINTER(sz), ctypes.c_void_p]
+    L.LizardF_getFrameInfo.restype = sz
+    L.LizardF_getFrameInfo.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(sz)]
+    return L
+
+
+def frame_compress(L, data: bytes, prefs) -> bytes:
+    """LizardF_compressFrame on a library handle; raises on a frame error."""
+    cap = L.LizardF_compressFrameBound(len(data), ctypes.byref(prefs))
+    dst = ctypes.create_string_buffer(cap)
+    n = L.LizardF_compressFrame(dst, cap, data, len(data), ctypes.byref(prefs))
+    if L.LizardF_isError(n):
+        raise LizardB200Error("LizardF_compressFrame: " + L.LizardF_getErrorName(n).decode())
+    return dst.raw[:n]
+
+
+def frame_decompress(L, frame: bytes, out_cap: int, chunk: int = 0, dst_chunk: int = 0):
+    """Feed a frame to LizardF_decompress (whole, or in `chunk`-byte pieces). Returns (last result, bytes)."""
+    ctx = ctypes.c_void_p()
+    L.LizardF_createDecompressionContext(ctypes.byref(ctx), 100)
+    out = ctypes.create_string_buffer(max(out_cap, 1))
+    src = ctypes.create_string_buffer(frame, max(len(frame), 1))
+    ip = op = 0
+    res = 1
+    try:
+        while ip < len(frame) or res != 0:
+            n_in = len(frame) - ip if not chunk else min(chunk, len(frame) - ip)
+            n_out = out_cap - op if not dst_chunk else min(dst_chunk, out_cap - op)
+            si = ctypes.c_size_t(n_in)
+            so = ctypes.c_size_t(n_out)
+            res = L.LizardF_decompress(ctx, ctypes.byref(out, op), ctypes.byref(so), ctypes.byref(src, ip),
+                                       ctypes.byref(si), None)
+            if L.LizardF_isError(res):
+                return res, out.raw[:op]
+            ip += si.value
+            op += so.value
+            if si.value == 0 and so.value == 0 and (n_in == 0 or n_out == 0):
+                break
+            if res == 0 and ip >= len(frame):
+                break
+    finally:
+        L.LizardF_freeDecompressionContext(ctx)
+    return res, out.raw[:op]

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cstring>
 #include <cstdio>
+#include <new>
 
 using namespace lzb;
 
@@ -72,13 +73,13 @@ struct Context {
     std::mutex mu;
     bool ready = false, failed = false;
     int device = 0, sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // compute / H2D / D2H
     int dec_grid = 0;
     DeviceBuffer dec_scratch, enc_scratch, counters;
     u32 counter_slot = 0;
     // staging for the host-pointer entry points
     PinnedBuffer pin_in, pin_out, pin_tab;
-    DeviceBuffer d_in, d_out, d_tab;
+    DeviceBuffer d_in, d_out, d_tab, d_pack;
     EncodeConfig enc_cfg;
 };
 Context g_ctx[kMaxDevices];
@@ -118,7 +119,9 @@ int ensure_context(Context& c, int device)
     }
     c.device = device;
     c.sm_count = prop.multiProcessorCount;
-    if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    if ((e = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c.s_out, cudaStreamNonBlocking)) != cudaSuccess) {
         c.failed = true; fail("cudaStreamCreate", e); return LIZARDB200_ERR_CUDA;
     }
     const size_t dec_smem = sizeof(DecWarpShared) * kDecWarps;
@@ -437,3 +440,5 @@ int Lizard_compress_extState(void* state, const char* src, char* dst, int srcSiz
 }
 
 }  // extern "C"
+
+#include "frame.inl"

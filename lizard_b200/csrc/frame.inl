@@ -1,0 +1,770 @@
+// frame.inl -- LizardF_* frame layer (block dispatch) over the batch codec.  Included by api.cu.
+//
+// Reference: lib/lizard_frame.c (header :363-429, block loop :501-590, end mark :641-670, bounds :231-247,
+// :436-451, decoder :756-857 and the state machine :980-1320), format doc/lizard_Frame_format.md.
+// What changes: the per-block loop `while (srcEnd-srcPtr >= blockSize) LizardF_compressBlock(...)`
+// (lizard_frame.c:544-549) becomes ONE batch: H2D, encode kernel, a device-side pack kernel that writes
+// [LE32 size|raw flag][payload] back to back (raw fallback when a block did not fit blockSize-1, :462-466),
+// D2H of the packed body.  The decoder scans the 4-byte size words on the host (serial, cheap) and decodes
+// every complete block present in the call with one kernel launch, straight into the caller's dst.
+//
+// Only LizardF_blockIndependent frames are supported: linked blocks need the streaming dictionary API
+// (Lizard_compress_continue / Lizard_decompress_safe_usingDict), which is out of scope;
+// such requests return LizardF_ERROR_blockMode_invalid.
+
+// ---- XXH32 (public algorithm; used for the header checksum byte and the optional content checksum) ----
+namespace {
+constexpr u32 kX1 = 2654435761u, kX2 = 2246822519u, kX3 = 3266489917u, kX4 = 668265263u, kX5 = 374761393u;
+inline u32 xrotl(u32 v, int r) { return (v << r) | (v >> (32 - r)); }
+inline u32 xround(u32 acc, u32 in) { return xrotl(acc + in * kX2, 13) * kX1; }
+struct Xxh32 {
+    u32 v[4]; u64 total = 0; u8 buf[16]; u32 nbuf = 0; u32 seed = 0;
+    void reset(u32 s) { seed = s; v[0] = s + kX1 + kX2; v[1] = s + kX2; v[2] = s; v[3] = s - kX1; total = 0; nbuf = 0; }
+    void update(const void* data, size_t n) {
+        const u8* p = (const u8*)data; total += n;
+        if (nbuf) { while (nbuf < 16 && n) { buf[nbuf++] = *p++; n--; } if (nbuf == 16) { consume(buf); nbuf = 0; } }
+        while (n >= 16) { consume(p); p += 16; n -= 16; }
+        while (n) { buf[nbuf++] = *p++; n--; }
+    }
+    void consume(const u8* p) { for (int i = 0; i < 4; ++i) v[i] = xround(v[i], rd_le32(p + 4 * i)); }
+    u32 digest() const {
+        u32 h = total >= 16 ? xrotl(v[0], 1) + xrotl(v[1], 7) + xrotl(v[2], 12) + xrotl(v[3], 18) : seed + kX5;
+        h += (u32)total;
+        u32 i = 0;
+        for (; i + 4 <= nbuf; i += 4) h = xrotl(h + rd_le32(buf + i) * kX3, 17) * kX4;
+        for (; i < nbuf; ++i) h = xrotl(h + buf[i] * kX5, 11) * kX1;
+        h ^= h >> 15; h *= kX2; h ^= h >> 13; h *= kX3; h ^= h >> 16;
+        return h;
+    }
+};
+inline u32 xxh32(const void* p, size_t n, u32 seed) { Xxh32 x; x.reset(seed); x.update(p, n); return x.digest(); }
+
+// ---- frame constants / errors (lib/lizard_frame_static.h:56-67) ----
+enum : int { FE_OK = 0, FE_GENERIC, FE_maxBlockSize_invalid, FE_blockMode_invalid, FE_contentChecksumFlag_invalid,
+             FE_compressionLevel_invalid, FE_headerVersion_wrong, FE_blockChecksum_unsupported, FE_reservedFlag_set,
+             FE_allocation_failed, FE_srcSize_tooLarge, FE_dstMaxSize_tooSmall, FE_frameHeader_incomplete,
+             FE_frameType_unknown, FE_frameSize_wrong, FE_srcPtr_wrong, FE_decompressionFailed,
+             FE_headerChecksum_invalid, FE_contentChecksum_invalid, FE_maxCode };
+const char* const kFrameErrorNames[] = { "OK_NoError", "ERROR_GENERIC", "ERROR_maxBlockSize_invalid", "ERROR_blockMode_invalid",
+    "ERROR_contentChecksumFlag_invalid", "ERROR_compressionLevel_invalid", "ERROR_headerVersion_wrong",
+    "ERROR_blockChecksum_unsupported", "ERROR_reservedFlag_set", "ERROR_allocation_failed", "ERROR_srcSize_tooLarge",
+    "ERROR_dstMaxSize_tooSmall", "ERROR_frameHeader_incomplete", "ERROR_frameType_unknown", "ERROR_frameSize_wrong",
+    "ERROR_srcPtr_wrong", "ERROR_decompressionFailed", "ERROR_headerChecksum_invalid", "ERROR_contentChecksum_invalid",
+    "ERROR_maxCode" };
+inline size_t ferr(int e) { return (size_t)-(long)e; }
+constexpr u32 kFrameMagic = 0x184D2206u, kSkippableMagic = 0x184D2A50u, kRawFlag = 0x80000000u;
+constexpr size_t kMinFH = 7, kMaxFH = 15, kBH = 4;
+
+inline size_t frame_block_size(unsigned id)
+{
+    static const size_t sizes[7] = { 128u << 10, 256u << 10, 1u << 20, 4u << 20, 16u << 20, 64u << 20, 256u << 20 };
+    if (id == 0) id = 1;
+    id -= 1;
+    if (id >= 7) return ferr(FE_maxBlockSize_invalid);
+    return sizes[id];
+}
+inline LizardF_blockSizeID_t frame_optimal_bsid(LizardF_blockSizeID_t req, size_t src_size)
+{
+    int prop = LizardF_max128KB;
+    while ((int)req > prop) {
+        if (src_size <= frame_block_size((unsigned)prop)) return (LizardF_blockSizeID_t)prop;
+        prop++;
+    }
+    return req;
+}
+inline void wr_le64(u8* p, u64 v) { for (int i = 0; i < 8; ++i) p[i] = (u8)(v >> (8 * i)); }
+inline u64 rd_le64h(const u8* p) { u64 v = 0; for (int i = 0; i < 8; ++i) v |= (u64)p[i] << (8 * i); return v; }
+
+// ---- device side of the compressor: sizes -> offsets -> packed body ----
+struct PackArgs {
+    const u8* comp_base; size_t comp_stride;     // encoder output of unit i at comp_base + i*comp_stride
+    const int* result;                           // encoder result per unit (0 = store raw)
+    const u8* src_base; u32 block_size; size_t src_size;
+    u64* out_off;                                // [n+1] offsets of the packed records; out_off[n] = total
+    u8* out; u32 n;
+    int level;                                   // for the 1-byte-block quirk below
+};
+
+// Size of block i's record payload.  Quirk kept for byte-exactness: for a 1-byte block the reference calls
+// Lizard_compress_extState with capacity 0 (lizard_frame.c:459), whose bound check wraps around
+// (lizard_compress.c:238, oend < start) and it emits the 6-byte raw inner block [level][0x80][01 00 00][byte].
+__device__ __forceinline__ u32 frame_record_payload(const PackArgs& a, u32 i, u32 len)
+{
+    if (len == 1) return 6;
+    return a.result[i] > 0 ? (u32)a.result[i] : len;
+}
+
+__global__ void __launch_bounds__(1024) lizard_frame_scan_kernel(PackArgs a)
+{
+    __shared__ u64 part[1024];
+    const u32 t = threadIdx.x, per = (a.n + 1023) / 1024;
+    const u32 lo = t * per, hi = min(a.n, lo + per);
+    u64 sum = 0;
+    for (u32 i = lo; i < hi; ++i) {
+        const size_t left = a.src_size - (size_t)i * a.block_size;
+        const u32 len = (u32)(left < a.block_size ? left : a.block_size);
+        sum += 4 + (u64)frame_record_payload(a, i, len);
+    }
+    part[t] = sum;
+    __syncthreads();
+    for (u32 o = 1; o < 1024; o <<= 1) { u64 v = t >= o ? part[t - o] : 0; __syncthreads(); part[t] += v; __syncthreads(); }
+    u64 run = part[t] - sum;
+    for (u32 i = lo; i < hi; ++i) {
+        const size_t left = a.src_size - (size_t)i * a.block_size;
+        const u32 len = (u32)(left < a.block_size ? left : a.block_size);
+        a.out_off[i] = run;
+        run += 4 + (u64)frame_record_payload(a, i, len);
+    }
+    if (t == 1023) a.out_off[a.n] = part[1023];
+}
+
+// byte-exact copy with 4-byte stores once dst is aligned (src may have any alignment)
+__device__ __forceinline__ void cta_copy(u8* dst, const u8* src, u32 n)
+{
+    const u32 t = threadIdx.x, nt = blockDim.x;
+    u32 head = (u32)((4 - ((size_t)dst & 3)) & 3);
+    if (head > n) head = n;
+    if (t < head) dst[t] = src[t];
+    dst += head; src += head; n -= head;
+    const u32 words = n >> 2;
+    const size_t sa = (size_t)src;
+    const u32* sq = (const u32*)(sa & ~(size_t)3);
+    const u32 sh = (u32)(sa & 3) * 8;
+    u32* dq = (u32*)dst;
+    for (u32 i = t; i < words; i += nt) dq[i] = sh ? __funnelshift_r(sq[i], sq[i + 1], sh) : sq[i];
+    const u32 tail = n & 3;
+    if (t < tail) dst[words * 4 + t] = src[words * 4 + t];
+}
+
+__global__ void __launch_bounds__(256) lizard_frame_pack_kernel(PackArgs a)
+{
+    const u32 i = blockIdx.x;
+    const size_t left = a.src_size - (size_t)i * a.block_size;
+    const u32 len = (u32)(left < a.block_size ? left : a.block_size);
+    const int r = a.result[i];
+    u8* o = a.out + a.out_off[i];
+    if (len == 1) {
+        if (threadIdx.x == 0) {
+            o[0] = 6; o[1] = 0; o[2] = 0; o[3] = 0;
+            o[4] = (u8)a.level; o[5] = (u8)kFlagRaw; o[6] = 1; o[7] = 0; o[8] = 0; o[9] = a.src_base[(size_t)i * a.block_size];
+        }
+        return;
+    }
+    const u32 word = r > 0 ? (u32)r : (len | 0x80000000u);
+    if (threadIdx.x < 4) o[threadIdx.x] = (u8)(word >> (8 * threadIdx.x));
+    if (r > 0) cta_copy(o + 4, a.comp_base + (size_t)i * a.comp_stride, (u32)r);
+    else cta_copy(o + 4, a.src_base + (size_t)i * a.block_size, len);
+}
+
+// Units per pipeline stage: host->device copy of chunk k+1, kernels of chunk k and device->host copy of
+// chunk k-1 run concurrently on three streams (PCIe is full duplex, the copy engines are separate).
+constexpr size_t kFrameChunkBytes = 64u << 20;
+
+struct ChunkEvents {
+    std::vector<cudaEvent_t> in, done;
+    cudaError_t make(size_t n) {
+        in.resize(n); done.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            cudaError_t e = cudaEventCreateWithFlags(&in[i], cudaEventDisableTiming); if (e != cudaSuccess) return e;
+            e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming); if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    ~ChunkEvents() { for (auto e : in) cudaEventDestroy(e); for (auto e : done) cudaEventDestroy(e); }
+};
+
+// Compress src[0..n) as independent blocks of block_size into the frame body at `dst` (records only).
+// Returns bytes written or a frame error.  Host pointers.
+size_t frame_compress_blocks(Context& c, u8* dst, size_t dst_cap, const u8* src, size_t n, size_t block_size, int level)
+{
+    if (n == 0) return 0;
+    const size_t nblk = (n + block_size - 1) / block_size;
+    size_t per_chunk = kFrameChunkBytes / block_size; if (per_chunk < 1) per_chunk = 1;
+    const size_t nchunks = (nblk + per_chunk - 1) / per_chunk;
+    const size_t stride = (block_size + 15) / 16 * 16;
+    const size_t tab_bytes = nblk * (8 + 4 + 8 + 4);
+    const size_t host_tab = tab_bytes + nchunks * 8 + 64;
+    const size_t dev_tab = tab_bytes + nblk * 4 + (nblk + nchunks + 1) * 8 + 64;
+    if (c.pin_tab.reserve(host_tab) != cudaSuccess || c.d_tab.reserve(dev_tab) != cudaSuccess ||
+        c.d_in.reserve(n + 64) != cudaSuccess || c.d_out.reserve(nblk * stride + 64) != cudaSuccess ||
+        c.d_pack.reserve(n + nblk * 16 + 64) != cudaSuccess) return ferr(FE_allocation_failed);
+    u64* t_in_off = (u64*)c.pin_tab.p; u64* t_out_off = t_in_off + nblk;
+    u32* t_in_len = (u32*)(t_out_off + nblk); u32* t_out_cap = t_in_len + nblk;
+    volatile u64* h_totals = (volatile u64*)(((size_t)(t_out_cap + nblk) + 7) & ~(size_t)7);
+    for (size_t i = 0; i < nblk; ++i) {
+        const size_t left = n - i * block_size;
+        const u32 len = (u32)(left < block_size ? left : block_size);
+        t_in_off[i] = i * block_size; t_out_off[i] = i * stride; t_in_len[i] = len;
+        t_out_cap[i] = len - 1;                    // lizard_frame.c:459: capacity srcSize-1, else stored raw
+    }
+    u8* dtab = (u8*)c.d_tab.p;
+    const u64* d_in_off = (const u64*)dtab; const u64* d_out_off = d_in_off + nblk;
+    const u32* d_in_len = (const u32*)(d_out_off + nblk); const u32* d_out_cap = d_in_len + nblk;
+    int* d_res = (int*)(d_out_cap + nblk);
+    u64* d_pack_off = (u64*)(((size_t)(d_res + nblk) + 7) & ~(size_t)7);
+    ChunkEvents ev;
+    if (ev.make(nchunks) != cudaSuccess) return ferr(FE_allocation_failed);
+    if (cudaMemcpyAsync(dtab, c.pin_tab.p, tab_bytes, cudaMemcpyHostToDevice, c.s_in) != cudaSuccess) return ferr(FE_GENERIC);
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t first = k * per_chunk, off = first * block_size;
+        const size_t bytes = (k + 1 == nchunks) ? n - off : per_chunk * block_size;
+        if (cudaMemcpyAsync((u8*)c.d_in.p + off, src + off, bytes, cudaMemcpyHostToDevice, c.s_in) != cudaSuccess) return ferr(FE_GENERIC);
+        cudaEventRecord(ev.in[k], c.s_in);
+    }
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t first = k * per_chunk, off = first * block_size;
+        const size_t cnt = (k + 1 == nchunks) ? nblk - first : per_chunk;
+        const size_t bytes = (k + 1 == nchunks) ? n - off : per_chunk * block_size;
+        cudaStreamWaitEvent(c.stream, ev.in[k], 0);
+        if (launch_encode(c, c.d_in.p, d_in_off + first, d_in_len + first, c.d_out.p, d_out_off + first, d_out_cap + first,
+                          d_res + first, (u32)cnt, level, c.stream) != LIZARDB200_OK) return ferr(FE_GENERIC);
+        PackArgs a;
+        a.comp_base = (const u8*)c.d_out.p + first * stride; a.comp_stride = stride; a.result = d_res + first;
+        a.src_base = (const u8*)c.d_in.p + off; a.block_size = (u32)block_size; a.src_size = bytes;
+        a.out_off = d_pack_off + first + k; a.out = (u8*)c.d_pack.p + off + first * 8; a.n = (u32)cnt; a.level = level;
+        lizard_frame_scan_kernel<<<1, 1024, 0, c.stream>>>(a);
+        lizard_frame_pack_kernel<<<(unsigned)cnt, 256, 0, c.stream>>>(a);
+        g_launches += 2;
+        if (cudaMemcpyAsync((void*)&h_totals[k], a.out_off + cnt, 8, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) return ferr(FE_GENERIC);
+        cudaEventRecord(ev.done[k], c.stream);
+    }
+    size_t written = 0;
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t first = k * per_chunk, off = first * block_size;
+        if (cudaEventSynchronize(ev.done[k]) != cudaSuccess) { fail("frame compress", cudaGetLastError()); cudaDeviceSynchronize(); return ferr(FE_GENERIC); }
+        const size_t total = (size_t)h_totals[k];
+        if (written + total > dst_cap) { cudaDeviceSynchronize(); return ferr(FE_dstMaxSize_tooSmall); }
+        if (cudaMemcpyAsync(dst + written, (u8*)c.d_pack.p + off + first * 8, total, cudaMemcpyDeviceToHost, c.s_out) != cudaSuccess) return ferr(FE_GENERIC);
+        written += total;
+    }
+    if (cudaStreamSynchronize(c.s_out) != cudaSuccess) return ferr(FE_GENERIC);
+    return written;
+}
+
+struct FrameBlockRef { size_t src_pos; u32 csize; size_t dst_pos; };
+
+// Decode `blocks` (compressed independent blocks inside src, ascending) into dst, each with capacity max_block.
+// sizes_out[i] = decoded size or negative.  Host pointers.  Pipelined like the compressor.
+int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::vector<FrameBlockRef>& blocks,
+                        u8* dst, size_t dst_span, u32 max_block, std::vector<int>& sizes_out)
+{
+    const size_t n = blocks.size();
+    sizes_out.assign(n, -1);
+    if (n == 0) return 0;
+    size_t per_chunk = kFrameChunkBytes / max_block; if (per_chunk < 1) per_chunk = 1;
+    const size_t nchunks = (n + per_chunk - 1) / per_chunk;
+    const size_t tab_bytes = n * (8 + 4 + 8 + 4);
+    if (c.pin_tab.reserve(tab_bytes + n * 4 + 64) != cudaSuccess || c.d_tab.reserve(tab_bytes + n * 4 + 64) != cudaSuccess ||
+        c.d_in.reserve(src_span + 64) != cudaSuccess || c.d_out.reserve(dst_span + 64) != cudaSuccess) return -1;
+    u64* t_in_off = (u64*)c.pin_tab.p; u64* t_out_off = t_in_off + n;
+    u32* t_in_len = (u32*)(t_out_off + n); u32* t_out_cap = t_in_len + n; volatile int* t_res = (volatile int*)(t_out_cap + n);
+    for (size_t i = 0; i < n; ++i) {
+        t_in_off[i] = blocks[i].src_pos; t_out_off[i] = blocks[i].dst_pos;
+        t_in_len[i] = blocks[i].csize; t_out_cap[i] = max_block;
+    }
+    u8* dtab = (u8*)c.d_tab.p;
+    const u64* d_in_off = (const u64*)dtab; const u64* d_out_off = d_in_off + n;
+    const u32* d_in_len = (const u32*)(d_out_off + n); const u32* d_out_cap = d_in_len + n; int* d_res = (int*)(d_out_cap + n);
+    ChunkEvents ev;
+    if (ev.make(nchunks) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(dtab, c.pin_tab.p, tab_bytes, cudaMemcpyHostToDevice, c.s_in) != cudaSuccess) return -1;
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t first = k * per_chunk, last = (k + 1 == nchunks ? n : first + per_chunk) - 1;
+        const size_t lo = blocks[first].src_pos, hi = blocks[last].src_pos + blocks[last].csize;
+        if (cudaMemcpyAsync((u8*)c.d_in.p + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, c.s_in) != cudaSuccess) return -1;
+        cudaEventRecord(ev.in[k], c.s_in);
+    }
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t first = k * per_chunk, cnt = (k + 1 == nchunks ? n : first + per_chunk) - first;
+        cudaStreamWaitEvent(c.stream, ev.in[k], 0);
+        if (launch_decode(c, c.d_in.p, d_in_off + first, d_in_len + first, c.d_out.p, d_out_off + first, d_out_cap + first,
+                          d_res + first, (u32)cnt, c.stream) != LIZARDB200_OK) return -1;
+        if (cudaMemcpyAsync((void*)(t_res + first), d_res + first, cnt * 4, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) return -1;
+        cudaEventRecord(ev.done[k], c.stream);
+    }
+    for (size_t k = 0; k < nchunks; ++k) {
+        const size_t first = k * per_chunk, last = (k + 1 == nchunks ? n : first + per_chunk) - 1;
+        if (cudaEventSynchronize(ev.done[k]) != cudaSuccess) { fail("frame decode", cudaGetLastError()); cudaDeviceSynchronize(); return -1; }
+        // copy back exactly what was produced: contiguous up to the end of the last good block of the chunk
+        size_t lo = blocks[first].dst_pos, hi = lo;
+        for (size_t i = first; i <= last; ++i) { sizes_out[i] = t_res[i]; if (t_res[i] > 0) hi = blocks[i].dst_pos + (size_t)t_res[i]; }
+        if (hi > lo && cudaMemcpyAsync(dst + lo, (u8*)c.d_out.p + lo, hi - lo, cudaMemcpyDeviceToHost, c.s_out) != cudaSuccess) return -1;
+    }
+    if (cudaStreamSynchronize(c.s_out) != cudaSuccess) return -1;
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+struct LizardF_cctx_s {
+    LizardF_preferences_t prefs;
+    unsigned version; unsigned stage;       // 0: idle, 1: header written
+    size_t block_size;
+    std::vector<u8> tmp;                    // partial block waiting for more input (lizard_frame.c tmpIn)
+    u64 total_in;
+    Xxh32 xxh;
+};
+struct LizardF_dctx_s {
+    LizardF_frameInfo_t info;
+    unsigned version;
+    int stage;                              // see DS_* below
+    u64 remaining;                          // frameRemainingSize
+    size_t max_block;
+    const u8* src_expect;
+    std::vector<u8> tmp_in; size_t tmp_in_size, tmp_in_target;
+    std::vector<u8> tmp_out; size_t tmp_out_size, tmp_out_start;
+    Xxh32 xxh;
+    u8 header[16];
+};
+namespace {
+enum { DS_getHeader = 0, DS_storeHeader, DS_getCBlockSize, DS_storeCBlockSize, DS_copyDirect, DS_getCBlock,
+       DS_storeCBlock, DS_flushOut, DS_getSuffix, DS_storeSuffix, DS_getSFrameSize, DS_storeSFrameSize, DS_skipSkippable };
+Context* frame_context()
+{
+    Context& c = g_ctx[g_device];
+    return &c;
+}
+}  // namespace
+
+extern "C" {
+
+unsigned LizardF_isError(size_t code) { return code > (size_t)-(long)FE_maxCode; }
+const char* LizardF_getErrorName(size_t code)
+{
+    return LizardF_isError(code) ? kFrameErrorNames[-(int)(long)code] : "Unspecified error code";
+}
+
+size_t LizardF_compressBound(size_t srcSize, const LizardF_preferences_t* prefsPtr)
+{   // lib/lizard_frame.c:436-451
+    LizardF_preferences_t nul; memset(&nul, 0, sizeof nul);
+    nul.frameInfo.contentChecksumFlag = LizardF_contentChecksumEnabled;
+    const LizardF_preferences_t* p = prefsPtr ? prefsPtr : &nul;
+    const size_t bs = frame_block_size((unsigned)p->frameInfo.blockSizeID);
+    const unsigned nb = (unsigned)(srcSize / bs) + 1;
+    const size_t last = p->autoFlush ? srcSize % bs : bs;
+    return 4 * (size_t)nb + bs * (nb - 1) + last + 4 + (size_t)p->frameInfo.contentChecksumFlag * 4;
+}
+
+size_t LizardF_compressFrameBound(size_t srcSize, const LizardF_preferences_t* prefsPtr)
+{   // lib/lizard_frame.c:231-247
+    LizardF_preferences_t p;
+    if (prefsPtr) p = *prefsPtr; else memset(&p, 0, sizeof p);
+    p.frameInfo.blockSizeID = frame_optimal_bsid(p.frameInfo.blockSizeID, srcSize);
+    p.autoFlush = 1;
+    return kMaxFH + LizardF_compressBound(srcSize, &p);
+}
+
+size_t LizardF_createCompressionContext(LizardF_compressionContext_t* out, unsigned version)
+{
+    LizardF_cctx_s* c = new (std::nothrow) LizardF_cctx_s();
+    if (!c) return ferr(FE_allocation_failed);
+    memset(&c->prefs, 0, sizeof c->prefs);
+    c->version = version; c->stage = 0; c->block_size = 0; c->total_in = 0;
+    *out = c;
+    return 0;
+}
+size_t LizardF_freeCompressionContext(LizardF_compressionContext_t c) { delete c; return 0; }
+
+size_t LizardF_compressBegin(LizardF_compressionContext_t c, void* dstBuffer, size_t dstMax, const LizardF_preferences_t* prefsPtr)
+{   // lib/lizard_frame.c:363-429
+    u8* const d0 = (u8*)dstBuffer; u8* d = d0;
+    if (dstMax < kMaxFH) return ferr(FE_dstMaxSize_tooSmall);
+    if (c->stage != 0) return ferr(FE_GENERIC);
+    if (prefsPtr) c->prefs = *prefsPtr; else memset(&c->prefs, 0, sizeof c->prefs);
+    if (c->prefs.frameInfo.blockSizeID == 0) c->prefs.frameInfo.blockSizeID = LizardF_max128KB;
+    c->block_size = frame_block_size((unsigned)c->prefs.frameInfo.blockSizeID);
+    if (LizardF_isError(c->block_size)) return c->block_size;
+    if (c->prefs.frameInfo.blockMode != LizardF_blockIndependent) return ferr(FE_blockMode_invalid);
+    {   // Lizard_verifyCompressionLevel, then the GPU level gate
+        int lvl = c->prefs.compressionLevel;
+        if (lvl > (int)kMaxLevel) lvl = kMaxLevel;
+        if (lvl < (int)kMinLevel) lvl = kDefaultLevel;
+        if (level_params(lvl).parser == kParserUnsupported) return ferr(FE_compressionLevel_invalid);
+    }
+    c->tmp.clear(); c->total_in = 0; c->xxh.reset(0);
+    wr_le32(d, kFrameMagic); d += 4;
+    u8* hs = d;
+    *d++ = (u8)((1u << 6) + (((unsigned)c->prefs.frameInfo.blockMode & 1) << 5)
+               + (((unsigned)c->prefs.frameInfo.contentChecksumFlag & 1) << 2) + ((c->prefs.frameInfo.contentSize > 0) << 3));
+    *d++ = (u8)(((unsigned)c->prefs.frameInfo.blockSizeID & 7) << 4);
+    if (c->prefs.frameInfo.contentSize) { wr_le64(d, c->prefs.frameInfo.contentSize); d += 8; }
+    *d = (u8)(xxh32(hs, (size_t)(d - hs), 0) >> 8); d++;
+    c->stage = 1;
+    return (size_t)(d - d0);
+}
+
+static size_t frame_flush_tmp(LizardF_cctx_s* c, u8* dst, size_t cap)
+{
+    if (c->tmp.empty()) return 0;
+    Context& g = *frame_context();
+    int lvl = c->prefs.compressionLevel;
+    if (lvl > (int)kMaxLevel) lvl = kMaxLevel;
+    if (lvl < (int)kMinLevel) lvl = kDefaultLevel;
+    size_t r = frame_compress_blocks(g, dst, cap, c->tmp.data(), c->tmp.size(), c->block_size, lvl);
+    if (!LizardF_isError(r)) c->tmp.clear();
+    return r;
+}
+
+size_t LizardF_compressUpdate(LizardF_compressionContext_t c, void* dstBuffer, size_t dstMax, const void* srcBuffer, size_t srcSize,
+                              const LizardF_compressOptions_t*)
+{   // lib/lizard_frame.c:501-590 (independent blocks)
+    if (c->stage != 1) return ferr(FE_GENERIC);
+    if (dstMax < LizardF_compressBound(srcSize, &c->prefs)) return ferr(FE_dstMaxSize_tooSmall);
+    Context& g = *frame_context();
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (ensure_context(g, g_device) != LIZARDB200_OK) return ferr(FE_GENERIC);
+    int lvl = c->prefs.compressionLevel;
+    if (lvl > (int)kMaxLevel) lvl = kMaxLevel;
+    if (lvl < (int)kMinLevel) lvl = kDefaultLevel;
+    const u8* sp = (const u8*)srcBuffer; const u8* const se = sp + srcSize;
+    u8* const d0 = (u8*)dstBuffer; u8* d = d0; u8* const de = d0 + dstMax;
+    const size_t bs = c->block_size;
+    if (!c->tmp.empty()) {                                   // complete the pending partial block first
+        size_t need = bs - c->tmp.size();
+        if (need > srcSize) { c->tmp.insert(c->tmp.end(), sp, se); sp = se; }
+        else {
+            c->tmp.insert(c->tmp.end(), sp, sp + need); sp += need;
+            size_t r = frame_flush_tmp(c, d, (size_t)(de - d));
+            if (LizardF_isError(r)) return r;
+            d += r;
+        }
+    }
+    size_t whole = ((size_t)(se - sp) / bs) * bs;
+    if (c->prefs.autoFlush) whole = (size_t)(se - sp);       // autoFlush also emits the trailing partial block
+    if (whole) {
+        size_t r = frame_compress_blocks(g, d, (size_t)(de - d), sp, whole, bs, lvl);
+        if (LizardF_isError(r)) return r;
+        d += r; sp += whole;
+    }
+    if (sp < se) c->tmp.assign(sp, se);
+    if (c->prefs.frameInfo.contentChecksumFlag == LizardF_contentChecksumEnabled) c->xxh.update(srcBuffer, srcSize);
+    c->total_in += srcSize;
+    return (size_t)(d - d0);
+}
+
+size_t LizardF_flush(LizardF_compressionContext_t c, void* dstBuffer, size_t dstMax, const LizardF_compressOptions_t*)
+{   // lib/lizard_frame.c:601-629
+    if (c->tmp.empty()) return 0;
+    if (c->stage != 1) return ferr(FE_GENERIC);
+    if (dstMax < c->tmp.size() + 8) return ferr(FE_dstMaxSize_tooSmall);
+    Context& g = *frame_context();
+    std::lock_guard<std::mutex> lock(g.mu);
+    if (ensure_context(g, g_device) != LIZARDB200_OK) return ferr(FE_GENERIC);
+    return frame_flush_tmp(c, (u8*)dstBuffer, dstMax);
+}
+
+size_t LizardF_compressEnd(LizardF_compressionContext_t c, void* dstBuffer, size_t dstMax, const LizardF_compressOptions_t* o)
+{   // lib/lizard_frame.c:641-670
+    u8* const d0 = (u8*)dstBuffer; u8* d = d0;
+    size_t r = LizardF_flush(c, dstBuffer, dstMax, o);
+    if (LizardF_isError(r)) return r;
+    d += r;
+    wr_le32(d, 0); d += 4;
+    if (c->prefs.frameInfo.contentChecksumFlag == LizardF_contentChecksumEnabled) { wr_le32(d, c->xxh.digest()); d += 4; }
+    c->stage = 0;
+    if (c->prefs.frameInfo.contentSize && c->prefs.frameInfo.contentSize != c->total_in) return ferr(FE_frameSize_wrong);
+    return (size_t)(d - d0);
+}
+
+size_t LizardF_compressFrame(void* dstBuffer, size_t dstMax, const void* srcBuffer, size_t srcSize, const LizardF_preferences_t* prefsPtr)
+{   // lib/lizard_frame.c:260-312
+    LizardF_cctx_s ctx;
+    memset(&ctx.prefs, 0, sizeof ctx.prefs);
+    ctx.version = LIZARDF_VERSION; ctx.stage = 0; ctx.block_size = 0; ctx.total_in = 0;
+    LizardF_preferences_t p;
+    if (prefsPtr) p = *prefsPtr; else memset(&p, 0, sizeof p);
+    if (p.frameInfo.contentSize != 0) p.frameInfo.contentSize = (u64)srcSize;
+    p.frameInfo.blockSizeID = frame_optimal_bsid(p.frameInfo.blockSizeID, srcSize);
+    p.autoFlush = 1;
+    if (srcSize <= frame_block_size((unsigned)p.frameInfo.blockSizeID)) p.frameInfo.blockMode = LizardF_blockIndependent;
+    if (dstMax < LizardF_compressFrameBound(srcSize, &p)) return ferr(FE_dstMaxSize_tooSmall);
+    u8* const d0 = (u8*)dstBuffer; u8* d = d0; u8* const de = d0 + dstMax;
+    size_t r = LizardF_compressBegin(&ctx, d, dstMax, &p);
+    if (LizardF_isError(r)) return r;
+    d += r;
+    r = LizardF_compressUpdate(&ctx, d, (size_t)(de - d), srcBuffer, srcSize, nullptr);
+    if (LizardF_isError(r)) return r;
+    d += r;
+    r = LizardF_compressEnd(&ctx, d, (size_t)(de - d), nullptr);
+    if (LizardF_isError(r)) return r;
+    d += r;
+    return (size_t)(d - d0);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+size_t LizardF_createDecompressionContext(LizardF_decompressionContext_t* out, unsigned version)
+{
+    LizardF_dctx_s* d = new (std::nothrow) LizardF_dctx_s();
+    if (!d) return ferr(FE_GENERIC);
+    memset(&d->info, 0, sizeof d->info);
+    d->version = version; d->stage = DS_getHeader; d->remaining = 0; d->max_block = 0; d->src_expect = nullptr;
+    d->tmp_in_size = d->tmp_in_target = d->tmp_out_size = d->tmp_out_start = 0;
+    *out = d;
+    return 0;
+}
+size_t LizardF_freeDecompressionContext(LizardF_decompressionContext_t d)
+{
+    size_t r = 0;
+    if (d) { r = (size_t)d->stage; delete d; }
+    return r;
+}
+
+static size_t frame_decode_header(LizardF_dctx_s* d, const u8* p, size_t n)
+{   // lib/lizard_frame.c:756-857
+    if (n < kMinFH) return ferr(FE_frameHeader_incomplete);
+    memset(&d->info, 0, sizeof d->info);
+    if ((rd_le32(p) & 0xFFFFFFF0u) == kSkippableMagic) {
+        d->info.frameType = LizardF_skippableFrame;
+        if (p == d->header) { d->tmp_in_size = n; d->tmp_in_target = 8; d->stage = DS_storeSFrameSize; return n; }
+        d->stage = DS_getSFrameSize; return 4;
+    }
+    if (rd_le32(p) != kFrameMagic) return ferr(FE_frameType_unknown);
+    d->info.frameType = LizardF_frame;
+    const u8 FLG = p[4];
+    const unsigned version = (FLG >> 6) & 3, block_mode = (FLG >> 5) & 1, block_cksum = (FLG >> 4) & 1,
+                   csize_flag = (FLG >> 3) & 1, ccksum = (FLG >> 2) & 1;
+    const size_t fh = csize_flag ? kMaxFH : kMinFH;
+    if (n < fh) {
+        if (p != d->header) memcpy(d->header, p, n);
+        d->tmp_in_size = n; d->tmp_in_target = fh; d->stage = DS_storeHeader;
+        return n;
+    }
+    const u8 BD = p[5];
+    const unsigned bsid = (BD >> 4) & 7;
+    if (version != 1) return ferr(FE_headerVersion_wrong);
+    if (block_cksum) return ferr(FE_blockChecksum_unsupported);
+    if (FLG & 3) return ferr(FE_reservedFlag_set);
+    if (BD & 0x80) return ferr(FE_reservedFlag_set);
+    if (bsid < 1) return ferr(FE_maxBlockSize_invalid);
+    if (BD & 0x0F) return ferr(FE_reservedFlag_set);
+    if ((u8)(xxh32(p + 4, fh - 5, 0) >> 8) != p[fh - 1]) return ferr(FE_headerChecksum_invalid);
+    d->info.blockMode = (LizardF_blockMode_t)block_mode;
+    d->info.contentChecksumFlag = (LizardF_contentChecksum_t)ccksum;
+    d->info.blockSizeID = (LizardF_blockSizeID_t)bsid;
+    d->max_block = frame_block_size(bsid);
+    d->remaining = 0;
+    if (csize_flag) d->remaining = d->info.contentSize = rd_le64h(p + 6);
+    if (ccksum) d->xxh.reset(0);
+    if (block_mode != LizardF_blockIndependent) return ferr(FE_blockMode_invalid);      // linked blocks: out of scope
+    d->tmp_in.resize(d->max_block + 16);
+    d->tmp_out.resize(d->max_block + 64);
+    d->tmp_in_size = d->tmp_in_target = 0; d->tmp_out_size = d->tmp_out_start = 0;
+    d->stage = DS_getCBlockSize;
+    return fh;
+}
+
+size_t LizardF_decompress(LizardF_decompressionContext_t d, void* dstBuffer, size_t* dstSizePtr,
+                          const void* srcBuffer, size_t* srcSizePtr, const LizardF_decompressOptions_t*)
+{   // lib/lizard_frame.c:980-1320, independent blocks; whole runs of complete blocks are decoded in one launch
+    const u8* const s0 = (const u8*)srcBuffer; const u8* const se = s0 + *srcSizePtr; const u8* sp = s0;
+    u8* const d0 = (u8*)dstBuffer; u8* const de = d0 + *dstSizePtr; u8* dp = d0;
+    const u8* sel = nullptr;
+    bool again = true;
+    size_t hint = 1;
+    *srcSizePtr = 0; *dstSizePtr = 0;
+    if (d->src_expect && s0 != d->src_expect) return ferr(FE_srcPtr_wrong);
+    Context& g = *frame_context();
+    std::lock_guard<std::mutex> lock(g.mu);
+
+    while (again) {
+        switch (d->stage) {
+        case DS_getHeader:
+            if ((size_t)(se - sp) >= kMaxFH) {
+                size_t h = frame_decode_header(d, sp, (size_t)(se - sp));
+                if (LizardF_isError(h)) return h;
+                sp += h;
+                break;
+            }
+            d->tmp_in_size = 0; d->tmp_in_target = kMinFH; d->stage = DS_storeHeader;
+            /* fallthrough */
+        case DS_storeHeader: {
+            size_t n = d->tmp_in_target - d->tmp_in_size;
+            if (n > (size_t)(se - sp)) n = (size_t)(se - sp);
+            memcpy(d->header + d->tmp_in_size, sp, n);
+            d->tmp_in_size += n; sp += n;
+            if (d->tmp_in_size < d->tmp_in_target) { hint = (d->tmp_in_target - d->tmp_in_size) + kBH; again = false; break; }
+            size_t h = frame_decode_header(d, d->header, d->tmp_in_target);
+            if (LizardF_isError(h)) return h;
+            break; }
+        case DS_getCBlockSize:
+            if ((size_t)(se - sp) >= kBH) { sel = sp; sp += kBH; }
+            else { d->tmp_in_size = 0; d->stage = DS_storeCBlockSize; }
+            if (d->stage == DS_storeCBlockSize)
+        case DS_storeCBlockSize: {
+                size_t n = kBH - d->tmp_in_size;
+                if (n > (size_t)(se - sp)) n = (size_t)(se - sp);
+                memcpy(d->tmp_in.data() + d->tmp_in_size, sp, n);
+                sp += n; d->tmp_in_size += n;
+                if (d->tmp_in_size < kBH) { hint = kBH - d->tmp_in_size; again = false; break; }
+                sel = d->tmp_in.data();
+            }
+            {   const u32 word = rd_le32(sel);
+                const size_t csz = word & 0x7FFFFFFFu;
+                if (csz == 0) { d->stage = DS_getSuffix; break; }
+                if (csz > d->max_block) return ferr(FE_GENERIC);
+                d->tmp_in_target = csz;
+                if (word & kRawFlag) { d->stage = DS_copyDirect; break; }
+                d->stage = DS_getCBlock;
+                if (dp == de) { hint = csz + kBH; again = false; }
+                break; }
+        case DS_copyDirect: {
+            size_t n = d->tmp_in_target;
+            if ((size_t)(se - sp) < n) n = (size_t)(se - sp);
+            if ((size_t)(de - dp) < n) n = (size_t)(de - dp);
+            memcpy(dp, sp, n);
+            if (d->info.contentChecksumFlag) d->xxh.update(sp, n);
+            if (d->info.contentSize) d->remaining -= n;
+            sp += n; dp += n;
+            if (n == d->tmp_in_target) { d->stage = DS_getCBlockSize; break; }
+            d->tmp_in_target -= n; hint = d->tmp_in_target + kBH; again = false;
+            break; }
+        case DS_getCBlock: {
+            if ((size_t)(se - sp) < d->tmp_in_target) { d->tmp_in_size = 0; d->stage = DS_storeCBlock; break; }
+            // ---- batch: this block and every following complete compressed block that has room in dst ----
+            if (ensure_context(g, g_device) != LIZARDB200_OK) return ferr(FE_GENERIC);
+            std::vector<FrameBlockRef> blocks;
+            const u8* scan = sp; size_t csz = d->tmp_in_target; u8* out = dp;
+            const u8* span_begin = sp;
+            if ((size_t)(de - out) >= d->max_block) {
+                for (;;) {
+                    blocks.push_back({ (size_t)(scan - span_begin), (u32)csz, (size_t)(out - dp) });
+                    scan += csz; out += d->max_block;
+                    if ((size_t)(se - scan) < kBH) break;                      // next size word not here yet
+                    const u32 w = rd_le32(scan);
+                    const size_t nx = w & 0x7FFFFFFFu;
+                    if (nx == 0 || (w & kRawFlag) || nx > d->max_block || (size_t)(se - scan - kBH) < nx) break;
+                    if ((size_t)(de - out) < d->max_block) break;              // that one needs the tmp-out path
+                    scan += kBH; csz = nx;                                     // take it into this batch
+                }
+            }
+            if (blocks.empty()) {                                          // not enough room in dst: decode via tmp_out
+                std::vector<FrameBlockRef> one{ { 0, (u32)d->tmp_in_target, 0 } };
+                std::vector<int> sz;
+                if (frame_decode_blocks(g, sp, d->tmp_in_target, one, d->tmp_out.data(), d->max_block, (u32)d->max_block, sz) != 0 || sz[0] < 0)
+                    return ferr(FE_decompressionFailed);
+                sp += d->tmp_in_target;
+                if (d->info.contentChecksumFlag) d->xxh.update(d->tmp_out.data(), (size_t)sz[0]);
+                if (d->info.contentSize) d->remaining -= (u64)sz[0];
+                d->tmp_out_size = (size_t)sz[0]; d->tmp_out_start = 0; d->stage = DS_flushOut;
+                break;
+            }
+            // blocks are decoded at max_block spacing on the device, then compacted into dst in order
+            std::vector<int> sz;
+            std::vector<u8>& stage_buf = d->tmp_out;
+            const size_t span = (size_t)(scan - span_begin);
+            const size_t out_span = blocks.size() * d->max_block;
+            (void)stage_buf;
+            if (frame_decode_blocks(g, span_begin, span, blocks, dp, out_span, (u32)d->max_block, sz) != 0) return ferr(FE_GENERIC);
+            // full blocks land exactly in place; a short block (the last of a frame) only shifts what follows it
+            u8* w = dp;
+            for (size_t i = 0; i < blocks.size(); ++i) {
+                if (sz[i] < 0) return ferr(FE_GENERIC);
+                u8* from = dp + blocks[i].dst_pos;
+                if (from != w) memmove(w, from, (size_t)sz[i]);
+                if (d->info.contentChecksumFlag) d->xxh.update(w, (size_t)sz[i]);
+                if (d->info.contentSize) d->remaining -= (u64)sz[i];
+                w += sz[i];
+            }
+            dp = w; sp = scan;
+            d->stage = DS_getCBlockSize;
+            break; }
+        case DS_storeCBlock: {
+            size_t n = d->tmp_in_target - d->tmp_in_size;
+            if (n > (size_t)(se - sp)) n = (size_t)(se - sp);
+            memcpy(d->tmp_in.data() + d->tmp_in_size, sp, n);
+            d->tmp_in_size += n; sp += n;
+            if (d->tmp_in_size < d->tmp_in_target) { hint = (d->tmp_in_target - d->tmp_in_size) + kBH; again = false; break; }
+            if (ensure_context(g, g_device) != LIZARDB200_OK) return ferr(FE_GENERIC);
+            std::vector<FrameBlockRef> one{ { 0, (u32)d->tmp_in_target, 0 } };
+            std::vector<int> sz;
+            const bool direct = (size_t)(de - dp) >= d->max_block;
+            u8* target = direct ? dp : d->tmp_out.data();
+            if (frame_decode_blocks(g, d->tmp_in.data(), d->tmp_in_target, one, target, d->max_block, (u32)d->max_block, sz) != 0 || sz[0] < 0)
+                return direct ? ferr(FE_GENERIC) : ferr(FE_decompressionFailed);
+            if (d->info.contentChecksumFlag) d->xxh.update(target, (size_t)sz[0]);
+            if (d->info.contentSize) d->remaining -= (u64)sz[0];
+            if (direct) { dp += sz[0]; d->stage = DS_getCBlockSize; }
+            else { d->tmp_out_size = (size_t)sz[0]; d->tmp_out_start = 0; d->stage = DS_flushOut; }
+            break; }
+        case DS_flushOut: {
+            size_t n = d->tmp_out_size - d->tmp_out_start;
+            if (n > (size_t)(de - dp)) n = (size_t)(de - dp);
+            memcpy(dp, d->tmp_out.data() + d->tmp_out_start, n);
+            d->tmp_out_start += n; dp += n;
+            if (d->tmp_out_start == d->tmp_out_size) { d->stage = DS_getCBlockSize; break; }
+            hint = kBH; again = false;
+            break; }
+        case DS_getSuffix: {
+            const size_t suffix = (size_t)d->info.contentChecksumFlag * 4;
+            if (d->remaining) return ferr(FE_frameSize_wrong);
+            if (suffix == 0) { hint = 0; d->stage = DS_getHeader; again = false; break; }
+            if ((size_t)(se - sp) < 4) { d->tmp_in_size = 0; d->stage = DS_storeSuffix; }
+            else { sel = sp; sp += 4; }
+            }
+            if (d->stage == DS_storeSuffix)
+        case DS_storeSuffix: {
+                size_t n = 4 - d->tmp_in_size;
+                if (n > (size_t)(se - sp)) n = (size_t)(se - sp);
+                memcpy(d->tmp_in.data() + d->tmp_in_size, sp, n);
+                sp += n; d->tmp_in_size += n;
+                if (d->tmp_in_size < 4) { hint = 4 - d->tmp_in_size; again = false; break; }
+                sel = d->tmp_in.data();
+            }
+            {   if (rd_le32(sel) != d->xxh.digest()) return ferr(FE_contentChecksum_invalid);
+                hint = 0; d->stage = DS_getHeader; again = false;
+                break; }
+        case DS_getSFrameSize:
+            if ((size_t)(se - sp) >= 4) { sel = sp; sp += 4; }
+            else { d->tmp_in_size = 4; d->tmp_in_target = 8; d->stage = DS_storeSFrameSize; }
+            if (d->stage == DS_storeSFrameSize)
+        case DS_storeSFrameSize: {
+                size_t n = d->tmp_in_target - d->tmp_in_size;
+                if (n > (size_t)(se - sp)) n = (size_t)(se - sp);
+                memcpy(d->header + d->tmp_in_size, sp, n);
+                sp += n; d->tmp_in_size += n;
+                if (d->tmp_in_size < d->tmp_in_target) { hint = d->tmp_in_target - d->tmp_in_size; again = false; break; }
+                sel = d->header + 4;
+            }
+            {   const size_t sf = rd_le32(sel);
+                d->info.contentSize = sf; d->tmp_in_target = sf; d->stage = DS_skipSkippable;
+                break; }
+        case DS_skipSkippable: {
+            size_t n = d->tmp_in_target;
+            if (n > (size_t)(se - sp)) n = (size_t)(se - sp);
+            sp += n; d->tmp_in_target -= n;
+            again = false; hint = d->tmp_in_target;
+            if (hint) break;
+            d->stage = DS_getHeader;
+            break; }
+        }
+    }
+    d->src_expect = sp < se ? sp : nullptr;
+    *srcSizePtr = (size_t)(sp - s0);
+    *dstSizePtr = (size_t)(dp - d0);
+    return hint;
+}
+
+size_t LizardF_getFrameInfo(LizardF_decompressionContext_t d, LizardF_frameInfo_t* info, const void* srcBuffer, size_t* srcSizePtr)
+{   // lib/lizard_frame.c:870-893
+    if (d->stage > DS_storeHeader) {
+        size_t o = 0, i = 0;
+        *srcSizePtr = 0; *info = d->info;
+        return LizardF_decompress(d, nullptr, &o, nullptr, &i, nullptr);
+    }
+    const u8* p = (const u8*)srcBuffer;
+    size_t hsize;
+    if (*srcSizePtr < 5) { *srcSizePtr = 0; return ferr(FE_frameHeader_incomplete); }
+    if ((rd_le32(p) & 0xFFFFFFF0u) == kSkippableMagic) hsize = 8;
+    else if (rd_le32(p) != kFrameMagic) { *srcSizePtr = 0; return ferr(FE_frameType_unknown); }
+    else hsize = ((p[4] >> 3) & 1) ? kMaxFH : kMinFH;
+    if (*srcSizePtr < hsize) { *srcSizePtr = 0; return ferr(FE_frameHeader_incomplete); }
+    *srcSizePtr = hsize;
+    size_t o = 0;
+    size_t next = LizardF_decompress(d, nullptr, &o, srcBuffer, srcSizePtr, nullptr);
+    if (d->stage <= DS_storeHeader) return ferr(FE_frameHeader_incomplete);
+    *info = d->info;
+    return next;
+}
+
+}  // extern "C"
