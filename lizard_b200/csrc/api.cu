@@ -20,7 +20,7 @@ namespace {
 constexpr int kDecWarps = 8;                 // warps per CTA in the decode kernel
 constexpr int kMaxDevices = 16;
 
-__global__ void __launch_bounds__(kDecWarps * 32)
+__global__ void __launch_bounds__(kDecWarps * 32, 4)
 lizard_decode_units_kernel(DecodeBatch b)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -28,15 +28,19 @@ lizard_decode_units_kernel(DecodeBatch b)
     DecWarpShared* sh = reinterpret_cast<DecWarpShared*>(smem_raw) + warp;
     const size_t gwarp = (size_t)blockIdx.x * kDecWarps + warp;
     u8* scratch = b.scratch + gwarp * kDecScratchPerWarp;
+    if (lane == 0) sh->big_table = reinterpret_cast<u16*>(scratch + 4 * kDecStreamScratch);
+    __syncwarp();
     for (;;) {
         u32 unit = 0;
         if (lane == 0) unit = atomicAdd(b.counter, 1u);
         unit = __shfl_sync(LZB_FULL, unit, 0);
         if (unit >= b.n_units) break;
-        const int r = decode_unit(b.src_base + b.src_off[unit], b.src_len[unit],
-                                  b.dst_base + b.dst_off[unit], b.dst_cap[unit], scratch, sh, lane);
+        progress_wait(b.progress, unit, lane);
+        const int r = decode_unit<WarpLanes>(b.src_base + b.src_off[unit], b.src_len[unit],
+                                             b.dst_base + b.dst_off[unit], b.dst_cap[unit], scratch, sh);
         if (lane == 0) b.result[unit] = r;
         __syncwarp();
+        progress_done(b.progress, unit, lane);
     }
 }
 
@@ -78,7 +82,8 @@ struct Context {
     DeviceBuffer dec_scratch, enc_scratch, counters;
     u32 counter_slot = 0;
     // staging for the host-pointer entry points
-    PinnedBuffer pin_in, pin_out, pin_tab;
+    PinnedBuffer pin_in, pin_out, pin_tab, pin_flags;
+    DeviceBuffer d_progress;
     DeviceBuffer d_in, d_out, d_tab, d_pack;
     EncodeConfig enc_cfg;
 };
@@ -155,10 +160,12 @@ u32* next_counter(Context& c, cudaStream_t s)
 }
 
 int launch_decode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* dSrcLen,
-                  void* dDst, const u64* dDstOff, const u32* dDstCap, int* dResult, u32 n, cudaStream_t s)
+                  void* dDst, const u64* dDstOff, const u32* dDstCap, int* dResult, u32 n, cudaStream_t s,
+                  const Progress* pg = nullptr)
 {
     if (n == 0) return LIZARDB200_OK;
     DecodeBatch b;
+    if (pg) b.progress = *pg; else memset(&b.progress, 0, sizeof b.progress);
     b.src_base = (const u8*)dSrc; b.src_off = dSrcOff; b.src_len = dSrcLen;
     b.dst_base = (u8*)dDst; b.dst_off = dDstOff; b.dst_cap = dDstCap;
     b.result = dResult; b.n_units = n;
@@ -174,12 +181,14 @@ int launch_decode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* d
 }
 
 int launch_encode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* dSrcLen,
-                  void* dDst, const u64* dDstOff, const u32* dDstCap, int* dResult, u32 n, int level, cudaStream_t s)
+                  void* dDst, const u64* dDstOff, const u32* dDstCap, int* dResult, u32 n, int level, cudaStream_t s,
+                  const Progress* pg = nullptr)
 {
     if (n == 0) return LIZARDB200_OK;
     LevelParams lp = level_params(level);
     if (lp.parser == kParserUnsupported) { g_last_error = "compression level not implemented on the GPU"; return LIZARDB200_ERR_LEVEL; }
     EncodeBatch b;
+    if (pg) b.progress = *pg; else memset(&b.progress, 0, sizeof b.progress);
     b.src_base = (const u8*)dSrc; b.src_off = dSrcOff; b.src_len = dSrcLen;
     b.dst_base = (u8*)dDst; b.dst_off = dDstOff; b.dst_cap = dDstCap;
     b.result = dResult; b.n_units = n; b.level = level;

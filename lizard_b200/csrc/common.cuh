@@ -11,7 +11,9 @@
 #define LZ_HD __host__ __device__ __forceinline__
 #define LZ_D  __device__ __forceinline__
 #define LZ_HDM __host__ __device__ __forceinline__
+#define LZ_HD_COLD __host__ __device__ __noinline__      /* once-per-stream serial code: keep it out of the hot loops' register budget */
 #else
+#define LZ_HD_COLD static
 #define LZ_HDM inline
 #define LZ_HD static inline
 #define LZ_D  static inline

@@ -1,4 +1,5 @@
-// decode.cuh -- device-side Lizard block decoder (one warp per independent compressed unit).
+// decode.cuh -- Lizard block decoder written against the lane policy W (lanes.cuh): one warp per
+// independent compressed unit on the device, one lane (or 32 emulated lanes) in the CPU test build.
 //
 // A "unit" is exactly what one Lizard_decompress_safe() call receives: [level byte] followed by
 // inner blocks of <= 128 KiB (reference: lib/lizard_decompress.c:115-264 Lizard_decompress_generic).
@@ -9,17 +10,56 @@
 // Per inner block the warp
 //   1. parses the 5 stream headers (all lanes redundantly; they are ~20 bytes),
 //   2. expands Huffman'd streams into its private scratch (lane-parallel over the 4 bitstreams),
-//   3. runs the token loop: lanes agree on the (uniform) cursor state and split every literal run and
-//      every match copy between them.
-// Accept/reject and the returned error codes follow lib/lizard_decompress_lz4.h:7-163 and
-// lib/lizard_decompress_liz.h:14-220 check for check (see the comments at each test).
+//   3. runs the token loop in BATCHES of W::lanes() tokens: lane i owns token i.  Everything a token needs
+//      except its position in the literals stream is a function of the token byte; the position depends on
+//      the earlier literal-length extension bytes, so those (about half of the tokens on datagen data) are
+//      resolved in a short serial chain of broadcast loads, everything else (cursor positions, output
+//      positions, bounds checks) is prefix sums and ballots.  Then the warp copies the batch's literal runs
+//      and resolves its matches in order.  Any token that fails a check, or uses a multi-byte length
+//      extension, sends the batch down the serial path, which follows the reference statement by statement
+//      so that accept/reject and the returned error codes are identical
+//      (lib/lizard_decompress_lz4.h:7-163, lib/lizard_decompress_liz.h:14-220).
 #pragma once
 #include "common.cuh"
+#include "lanes.cuh"
 #include "entropy_dec.cuh"
 
 namespace lzb {
 
 #define LZB_FULL 0xffffffffu
+
+// Optional streaming hand-shake for the host-pipelined entry points: units become available as their input
+// chunk lands (`ready` = number of leading units whose bytes are in HBM, published by a 4-byte copy queued
+// behind each H2D chunk), and the last unit of every chunk raises a flag in mapped pinned memory so the host
+// can start that chunk's D2H while later units are still being processed.  All null = everything is resident.
+struct Progress {
+    const volatile u32* ready;      // device: units [0, *ready) may be read
+    u32*                done_count; // device: [n_chunks] finished units per chunk
+    volatile u32*       host_done;  // mapped pinned: [n_chunks] set to 1 when a chunk is complete
+    u32                 chunk_units;
+    u32                 n_units;
+};
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ void progress_wait(const Progress& pg, u32 unit, u32 lane)
+{
+    if (pg.ready) {
+        if (lane == 0) { while (*pg.ready <= unit) __nanosleep(400); }
+        __syncwarp();
+        __threadfence();
+    }
+}
+__device__ __forceinline__ void progress_done(const Progress& pg, u32 unit, u32 lane)
+{
+    if (pg.done_count && lane == 0) {
+        __threadfence();
+        const u32 c = unit / pg.chunk_units;
+        const u32 first = c * pg.chunk_units;
+        const u32 cnt = (pg.n_units - first < pg.chunk_units) ? pg.n_units - first : pg.chunk_units;
+        if (atomicAdd(&pg.done_count[c], 1u) == cnt - 1) { __threadfence_system(); pg.host_done[c] = 1u; }
+    }
+}
+#endif
 
 struct DecodeBatch {
     const u8*  src_base;    // compressed bytes of all units
@@ -32,40 +72,40 @@ struct DecodeBatch {
     u32        n_units;
     u8*        scratch;     // n_warps * kDecScratchPerWarp bytes (Huffman-expanded streams)
     u32*       counter;     // work queue head
+    Progress   progress;
 };
 
-enum : u32 { kDecStreamScratch = kBlockSize + 64, kDecScratchPerWarp = 4 * kDecStreamScratch };
+enum : u32 { kDecStreamScratch = kBlockSize + 64, kDecBigTableBytes = 2u << kHufTableLogMax,
+             kDecScratchPerWarp = 4 * kDecStreamScratch + kDecBigTableBytes };
+enum : u32 { kDecSmemTableLog = 11 };    // Lizard's encoder never exceeds 11 (HUF_TABLELOG_DEFAULT); 12 is legal input
 
 struct DecWarpShared {             // per-warp shared memory
-    u16 table[1u << kHufTableLogMax];
+    u16 table[1u << kDecSmemTableLog];
+    u16* big_table;                // 2^12-entry table in the warp's global scratch, used only for tableLog 12
     HufStatsScratch stats;
     u8  weights[256];
     u32 rank[kHufTableLogMax + 1];
     u32 pad[3];
 };
 
-// ---- warp-cooperative byte movers -------------------------------------------------------------
-LZ_D void warp_copy(u8* dst, const u8* src, u32 n, u32 lane)
+// ---- lane-cooperative byte movers --------------------------------------------------------------
+template <class W> LZ_HD void lanes_fill(u8* dst, u8 v, u32 n)
 {
-    for (u32 i = lane; i < n; i += 32) dst[i] = src[i];
-}
-LZ_D void warp_fill(u8* dst, u8 v, u32 n, u32 lane)
-{
-    for (u32 i = lane; i < n; i += 32) dst[i] = v;
+    for (u32 i = W::lane(); i < n; i += W::lanes()) dst[i] = v;
 }
 // LZ77 match: dst[op+i] = dst[op-off+i] with byte-serial semantics.  An overlapping match is a
 // periodic extension of the `off` bytes before op, so every source byte already exists.
-LZ_D void warp_match(u8* dst, u32 op, u32 off, u32 len, u32 lane)
+template <class W> LZ_HD void lanes_match(u8* dst, long op, u32 off, u32 len)
 {
     const u8* s = dst + op - off;
     u8* d = dst + op;
-    if (off >= len) { for (u32 i = lane; i < len; i += 32) d[i] = s[i]; }
-    else if (off != 0) { for (u32 i = lane; i < len; i += 32) d[i] = s[i % off]; }
+    if (off >= len) { for (u32 i = W::lane(); i < len; i += W::lanes()) d[i] = s[i]; }
+    else if (off != 0) { for (u32 i = W::lane(); i < len; i += W::lanes()) d[i] = s[i % off]; }
 }
 
 // ---- Huffman stream expansion -----------------------------------------------------------------
 // single-symbol decode of one of the 4 segments by one lane; true when the bitstream ended exactly
-LZ_D bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u16* table, u32 tl, int* init_err)
+LZ_HD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u16* table, u32 tl, int* init_err)
 {
     BitReader b;
     int e = bits_init(b, src, len);
@@ -83,24 +123,26 @@ LZ_D bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u1
 }
 
 // HUF_decompress for one stream; all lanes return the same value (n or negative)
-LZ_D int warp_huf_decompress(u8* dst, u32 n, const u8* src, u32 c, DecWarpShared* sh, u32 lane)
+template <class W> LZ_HD int huf_decompress_lanes(u8* dst, u32 n, const u8* src, u32 c, DecWarpShared* sh)
 {
+    const u32 lane = W::lane();
     if (n == 0) return kErrDstSmall;
     if (c > n) return kErrCorrupt;
-    if (c == n) { warp_copy(dst, src, n, lane); __syncwarp(); return (int)n; }
-    if (c == 1) { warp_fill(dst, src[0], n, lane); __syncwarp(); return (int)n; }
+    if (c == n) { lanes_copy<W>(dst, src, n); W::sync(); return (int)n; }
+    if (c == 1) { lanes_fill<W>(dst, src[0], n); W::sync(); return (int)n; }
     const u32 algo = huf_select_decoder(n, c);
     int h = 0; u32 tl = 0;
     if (lane == 0) {
         u32 nsym = 0;
         h = huf_read_stats(sh->weights, sh->rank, &nsym, &tl, src, c, &sh->stats);
-        if (h >= 0) huf_fill_dtable(sh->table, sh->weights, sh->rank, nsym, tl);
+        if (h >= 0) huf_fill_dtable(tl <= kDecSmemTableLog ? sh->table : sh->big_table, sh->weights, sh->rank, nsym, tl);
     }
-    h = __shfl_sync(LZB_FULL, h, 0);
-    tl = __shfl_sync(LZB_FULL, tl, 0);
+    h = W::bcast(h);
+    tl = (u32)W::bcast((int)tl);
+    const u16* const table = tl <= kDecSmemTableLog ? sh->table : sh->big_table;
     if (h < 0) return h;
     if ((u32)h >= c) return kErrSrcSize;
-    __syncwarp();
+    W::sync();
     const u8* pay = src + h;
     const u32 pc = c - (u32)h;
     if (pc < 10) return kErrCorrupt;
@@ -108,25 +150,31 @@ LZ_D int warp_huf_decompress(u8* dst, u32 n, const u8* src, u32 c, DecWarpShared
     if (l1 + l2 + l3 + 6 > pc) return kErrCorrupt;
     const u32 l4 = pc - (l1 + l2 + l3 + 6);
     const long seg = (long)((n + 3) / 4);
-    bool ok = true; int ierr = 0;
-    if (lane < 4) {
-        const u8* s = pay + 6 + (lane > 0 ? l1 : 0) + (lane > 1 ? l2 : 0) + (lane > 2 ? l3 : 0);
-        u32 len = lane == 0 ? l1 : lane == 1 ? l2 : lane == 2 ? l3 : l4;
-        long cnt = lane < 3 ? seg : (long)n - 3 * seg;
+    bool ok = true;
+    int ierr[4] = {0, 0, 0, 0};
+    for (u32 k = lane; k < 4; k += W::lanes()) {
+        const u8* s = pay + 6 + (k > 0 ? l1 : 0) + (k > 1 ? l2 : 0) + (k > 2 ? l3 : 0);
+        const u32 len = k == 0 ? l1 : k == 1 ? l2 : k == 2 ? l3 : l4;
+        long cnt = k < 3 ? seg : (long)n - 3 * seg;
         if (cnt < 0) cnt = 0;
-        ok = huf_lane_segment(dst + (long)lane * seg, cnt, s, len, sh->table, tl, &ierr);
+        const bool good = huf_lane_segment(dst + (long)k * seg, cnt, s, len, table, tl, &ierr[k]);
+        ok = ok && good;
     }
     // the reference initialises the four readers before decoding anything and returns the first failure
-    for (int k = 0; k < 4; ++k) { int e = __shfl_sync(LZB_FULL, ierr, k); if (e < 0) return e; }
-    const bool all_ok = __all_sync(LZB_FULL, ok);
-    __syncwarp();
+    for (u32 k = 0; k < 4; ++k) {
+        const u32 owner = k % W::lanes();
+        const int e = (int)W::shfl((u32)ierr[k], owner);
+        if (e < 0) return e;
+    }
+    const bool all_ok = W::ballot(!ok) == 0;
+    W::sync();
     if (all_ok) return (int)n;
     if (!algo) return kErrCorrupt;
     // the reference would have run its double-symbol decoder, which tolerates a few malformed tails
     int r = 0;
-    if (lane == 0) r = huf_decode4_serial(dst, n, pay, pc, sh->table, tl, 1);
-    r = __shfl_sync(LZB_FULL, r, 0);
-    __syncwarp();
+    if (lane == 0) r = huf_decode4_serial(dst, n, pay, pc, table, tl, 1);
+    r = W::bcast(r);
+    W::sync();
     return r;
 }
 
@@ -136,133 +184,373 @@ struct Streams {
     const u8* lits;   u32 nlits;
     const u8* off16;  u32 noff16;
     const u8* off24;  u32 noff24;
-    const u8* src_end;                // end of the whole compressed unit (bound for stray reads)
+    const u8* src_begin;              // the whole compressed unit (bound for stray reads)
+    const u8* src_end;
 };
 
 // byte of a stream that the reference reads without an exact bound: real memory past a raw stream is
 // the rest of the compressed unit; anything further reads as zero here
-LZ_D u32 stray_byte(const u8* p, const Streams& s, const u8* unit_begin)
+LZ_HD u32 stray_byte(const u8* p, const Streams& s)
 {
-    // streams living in scratch never take this path past their end with a meaningful value
-    return (p >= unit_begin && p < s.src_end) ? *p : 0u;
+    return (p >= s.src_begin && p < s.src_end) ? *p : 0u;
 }
 
 // length extension byte(s): b<254 -> b ; 254 -> LE16 ; 255 -> LE24  (lizard_decompress_lz4.h:50-61)
-LZ_D u32 read_ext(const u8* lits, u32 nlits, u32& lp)
+LZ_HD u32 read_ext(const u8* lits, u32 nlits, long& lp)
 {
     u32 v = lits[lp];
     if (v >= 254) {
-        u32 b1 = lp + 1 < nlits ? lits[lp + 1] : 0, b2 = lp + 2 < nlits ? lits[lp + 2] : 0;
+        const u32 b1 = lp + 1 < (long)nlits ? lits[lp + 1] : 0, b2 = lp + 2 < (long)nlits ? lits[lp + 2] : 0;
         if (v == 254) { v = b1 | (b2 << 8); lp += 2; }
-        else { u32 b3 = lp + 3 < nlits ? lits[lp + 3] : 0; v = b1 | (b2 << 8) | (b3 << 16); lp += 3; }
+        else { const u32 b3 = lp + 3 < (long)nlits ? lits[lp + 3] : 0; v = b1 | (b2 << 8) | (b3 << 16); lp += 3; }
     }
     lp++;
     return v;
 }
 
-// fastLZ4 codewords (lib/lizard_decompress_lz4.h:7-163).  `op` is the offset inside the unit's output,
-// `oend` the unit's capacity; matches may reach back to offset 0 of the unit.
-LZ_D int decode_tokens_lz4(const Streams& s, u8* dst, u32 op0, u32 oend, u32 lane)
+// cursor state of one token loop
+struct TokCursor { u32 fp; long lp; long op; u32 p16, p24; u32 last_off; };
+
+// ---- serial path: the reference's loop, one token at a time (all lanes in lock step) ------------------
+// Returns 0 to continue, or the (negative) error code.  Runs at most `count` tokens.
+template <class W> LZ_HD int lz4_serial(const Streams& s, u8* dst, long oend, TokCursor& c, u32 count)
 {
     const long nl = (long)s.nlits;
-    long op = op0;
-    u32 fp = 0, lp = 0;
-    if (oend - op0 == 0) return (s.nflags == 1 && s.flags[0] == 0) ? 0 : -1;
-    while (fp < s.nflags) {
-        const u32 tok = s.flags[fp++];
+    for (u32 t = 0; t < count && c.fp < s.nflags; ++t) {
+        const u32 tok = s.flags[c.fp++];
         u32 len = tok & 15;
         if (len == 15) {
-            if ((long)lp > nl - 5) return -(int)fp - 1;
-            len = read_ext(s.lits, s.nlits, lp) + 15;
+            if (c.lp > nl - 5) return -(int)c.fp - 1;
+            len = read_ext(s.lits, s.nlits, c.lp) + 15;
         }
-        if (op + len > (long)oend - 16 || (long)lp + len > nl - 18) return -(int)fp - 1;
-        warp_copy(dst + op, s.lits + lp, len, lane);
-        op += len; lp += len;
-        const u32 off = rd_le16(s.lits + lp); lp += 2;
-        if ((long)off > op) return -(int)fp - 1;                 // match < lowLimit
+        if (c.op + len > oend - 16 || c.lp + len > nl - 18) return -(int)c.fp - 1;
+        lanes_copy<W>(dst + c.op, s.lits + c.lp, len);
+        c.op += len; c.lp += len;
+        const u32 off = rd_le16(s.lits + c.lp); c.lp += 2;
+        if ((long)off > c.op) return -(int)c.fp - 1;               // match < lowLimit
         u32 ml = tok >> 4;
         if (ml == 15) {
-            if ((long)lp > nl - 5) return -(int)fp - 1;
-            ml = read_ext(s.lits, s.nlits, lp) + 15;
+            if (c.lp > nl - 5) return -(int)c.fp - 1;
+            ml = read_ext(s.lits, s.nlits, c.lp) + 15;
         }
         ml += kMinMatch;
-        if (op + ml > (long)oend - 16) return -(int)fp - 1;
-        __syncwarp();
-        warp_match(dst, (u32)op, off, ml, lane);
-        __syncwarp();
-        op += ml;
+        if (c.op + ml > oend - 16) return -(int)c.fp - 1;
+        W::sync();
+        lanes_match<W>(dst, c.op, off, ml);
+        W::sync();
+        c.op += ml;
     }
-    const long rest = nl - (long)lp;
-    if (rest < 0 || op + rest > (long)oend) return -(int)fp - 1;
-    warp_copy(dst + op, s.lits + lp, (u32)rest, lane);
-    __syncwarp();
-    op += rest;
-    return (int)(op - op0);
+    return 0;
 }
 
-// LIZv1 codewords (lib/lizard_decompress_liz.h:14-220)
-LZ_D int decode_tokens_lizv1(const Streams& s, u8* dst, u32 op0, u32 oend, u32 lane, const u8* unit_begin)
+template <class W> LZ_HD int lizv1_serial(const Streams& s, u8* dst, long oend, TokCursor& c, u32 count)
 {
     const long nl = (long)s.nlits;
-    long op = op0;
-    u32 fp = 0, lp = 0, p16 = 0, p24 = 0;
-    u32 last_off = 0;                                             // LIZARD_INIT_LAST_OFFSET per inner block
-    if (oend - op0 == 0) return (s.nflags == 1 && s.flags[0] == 0) ? 0 : -1;
-    while (fp < s.nflags) {
-        const u32 tok = s.flags[fp++];
+    for (u32 t = 0; t < count && c.fp < s.nflags; ++t) {
+        const u32 tok = s.flags[c.fp++];
         u32 ml;
         if (tok >= 32) {
             u32 len = tok & 7;
             if (len == 7) {
-                if ((long)lp > nl - 1) return -(int)fp - 1;
-                len = read_ext(s.lits, s.nlits, lp) + 7;
+                if (c.lp > nl - 1) return -(int)c.fp - 1;
+                len = read_ext(s.lits, s.nlits, c.lp) + 7;
             }
-            if (op + len > (long)oend - 16 || (long)lp > nl - 16) return -(int)fp - 1;
+            if (c.op + len > oend - 16 || c.lp > nl - 16) return -(int)c.fp - 1;
             {   // the reference copies first and notices an over-long run later; never read past the stream
-                u32 avail = (long)lp < nl ? (u32)(nl - lp) : 0;
-                warp_copy(dst + op, s.lits + lp, len < avail ? len : avail, lane);
+                const u32 avail = c.lp < nl ? (u32)(nl - c.lp) : 0;
+                lanes_copy<W>(dst + c.op, s.lits + c.lp, len < avail ? len : avail);
             }
-            op += len; lp += len;
-            if (p16 > s.noff16) return -(int)fp - 1;
+            c.op += len; c.lp += len;
+            if (c.p16 > s.noff16) return -(int)c.fp - 1;
             if ((tok >> 7) == 0) {                                // new 16-bit offset; bit 7 set = repeat last offset
-                if (p16 + 2 <= s.noff16) last_off = rd_le16(s.off16 + p16);
-                else last_off = stray_byte(s.off16 + p16, s, unit_begin) | (stray_byte(s.off16 + p16 + 1, s, unit_begin) << 8);
-                p16 += 2;
+                if (c.p16 + 2 <= s.noff16) c.last_off = rd_le16(s.off16 + c.p16);
+                else c.last_off = stray_byte(s.off16 + c.p16, s) | (stray_byte(s.off16 + c.p16 + 1, s) << 8);
+                c.p16 += 2;
             }
             ml = (tok >> 3) & 15;
             if (ml == 15) {
-                if ((long)lp > nl - 1) return -(int)fp - 1;
-                ml = read_ext(s.lits, s.nlits, lp) + 15;
+                if (c.lp > nl - 1) return -(int)c.fp - 1;
+                ml = read_ext(s.lits, s.nlits, c.lp) + 15;
             }
         } else if (tok < kLastLongOff) {
-            if ((long)p24 > (long)s.noff24 - 3) return -(int)fp - 1;
+            if ((long)c.p24 > (long)s.noff24 - 3) return -(int)c.fp - 1;
             ml = tok + kMmLongOff;
-            last_off = rd_le24(s.off24 + p24); p24 += 3;
+            c.last_off = rd_le24(s.off24 + c.p24); c.p24 += 3;
         } else {
-            if ((long)lp > nl - 1) return -(int)fp - 1;
-            ml = read_ext(s.lits, s.nlits, lp) + kLastLongOff + kMmLongOff;
-            if ((long)p24 > (long)s.noff24 - 3) return -(int)fp - 1;
-            last_off = rd_le24(s.off24 + p24); p24 += 3;
+            if (c.lp > nl - 1) return -(int)c.fp - 1;
+            ml = read_ext(s.lits, s.nlits, c.lp) + kLastLongOff + kMmLongOff;
+            if ((long)c.p24 > (long)s.noff24 - 3) return -(int)c.fp - 1;
+            c.last_off = rd_le24(s.off24 + c.p24); c.p24 += 3;
         }
-        if ((long)last_off > op) return -(int)fp - 1;             // match < lowLimit
-        if (op + ml > (long)oend - 16) return -(int)fp - 1;
-        __syncwarp();
-        warp_match(dst, (u32)op, last_off, ml, lane);
-        __syncwarp();
-        op += ml;
+        if ((long)c.last_off > c.op) return -(int)c.fp - 1;         // match < lowLimit
+        if (c.op + ml > oend - 16) return -(int)c.fp - 1;
+        W::sync();
+        lanes_match<W>(dst, c.op, c.last_off, ml);
+        W::sync();
+        c.op += ml;
     }
-    const long rest = nl - (long)lp;
-    if (rest < 0 || op + rest > (long)oend) return -(int)fp - 1;
-    warp_copy(dst + op, s.lits + lp, (u32)rest, lane);
-    __syncwarp();
-    op += rest;
-    return (int)(op - op0);
+    return 0;
+}
+
+// ---- 4-bytes-per-lane copy pieces: one pass moves 4*lanes bytes ------------------------------------------
+LZ_HD u32 ld32u(const u8* p)      // unaligned little-endian load; may touch the aligned words around p only
+{
+#if defined(__CUDA_ARCH__)
+    const size_t a = (size_t)p;
+    const u32* q = (const u32*)(a & ~(size_t)3);
+    const u32 sh = (u32)(a & 3) * 8;
+    const u32 lo = q[0];
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, q[1], sh);
+#else
+    return rd_le32(p);
+#endif
+}
+// this lane's 4 bytes (index 4*lane) of a run of n bytes; bytes past n read as 0
+template <class W> LZ_HD u32 load_chunk4(const u8* src, u32 n)
+{
+    const u32 i = 4 * W::lane();
+    if (i + 4 <= n) return ld32u(src + i);
+    u32 v = 0;
+    for (u32 j = 0; j < 4; ++j) if (i + j < n) v |= (u32)src[i + j] << (8 * j);
+    return v;
+}
+template <class W> LZ_HD void store_chunk4(u8* dst, u32 v, u32 n)
+{
+    const u32 i = 4 * W::lane();
+    if (i >= n) return;
+    u8* d = dst + i;
+    if (i + 4 <= n && ((size_t)d & 3) == 0) { *(u32*)d = v; return; }
+    const u32 cnt = n - i < 4 ? n - i : 4;
+    for (u32 j = 0; j < cnt; ++j) d[j] = (u8)(v >> (8 * j));
+}
+// non-overlapping copy (src and dst ranges disjoint, or src entirely before dst with distance >= n)
+template <class W> LZ_HD void lanes_copy4(u8* dst, const u8* src, u32 n)
+{
+    const u32 step = 4 * W::lanes();
+    for (u32 base = 0; base < n; base += step) {
+        const u32 part = n - base < step ? n - base : step;
+        const u32 v = load_chunk4<W>(src + base, part);
+        store_chunk4<W>(dst + base, v, part);
+    }
+}
+
+// ---- batch execution shared by both flavours: copy the literal runs, then resolve the matches in order ----
+template <class W> LZ_HD void run_batch_copies(u8* dst, const u8* lits, u32 nb, u32 lit_src, u32 lit_len,
+                                               u32 opos, u32 off, u32 ml)
+{
+    const u32 step = 4 * W::lanes();
+    // warm the cache for this lane's match source while the literal runs are being moved
+    if (W::lane() < nb && off != 0 && off <= opos + lit_len) W::prefetch(dst + (opos + lit_len - off));
+    // literal runs are independent of everything in this batch: two at a time, loads before stores
+    u32 k = 0;
+    for (; k + 1 < nb; k += 2) {
+        const u32 len0 = W::shfl(lit_len, k), sp0 = W::shfl(lit_src, k), dp0 = W::shfl(opos, k);
+        const u32 len1 = W::shfl(lit_len, k + 1), sp1 = W::shfl(lit_src, k + 1), dp1 = W::shfl(opos, k + 1);
+        const u32 p0 = len0 < step ? len0 : step, p1 = len1 < step ? len1 : step;
+        const u32 v0 = load_chunk4<W>(lits + sp0, p0);
+        const u32 v1 = load_chunk4<W>(lits + sp1, p1);
+        store_chunk4<W>(dst + dp0, v0, p0);
+        store_chunk4<W>(dst + dp1, v1, p1);
+        if (len0 > step) lanes_copy4<W>(dst + dp0 + step, lits + sp0 + step, len0 - step);
+        if (len1 > step) lanes_copy4<W>(dst + dp1 + step, lits + sp1 + step, len1 - step);
+    }
+    if (k < nb) {
+        const u32 len0 = W::shfl(lit_len, k), sp0 = W::shfl(lit_src, k), dp0 = W::shfl(opos, k);
+        lanes_copy4<W>(dst + dp0, lits + sp0, len0);
+    }
+    W::sync();
+    for (k = 0; k < nb; ++k) {
+        const u32 m = W::shfl(ml, k);
+        const u32 o = W::shfl(off, k);
+        const u32 dp = W::shfl(opos + lit_len, k);
+        if (o >= m) lanes_copy4<W>(dst + dp, dst + dp - o, m);      // source entirely before the destination
+        else lanes_match<W>(dst, (long)dp, o, m);
+        W::sync();
+    }
+}
+
+// fastLZ4 codewords (lib/lizard_decompress_lz4.h:7-163).  `op0` is the offset inside the unit's output,
+// `oend` the unit's capacity; matches may reach back to offset 0 of the unit.
+template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op0, u32 oend_u)
+{
+    const long nl = (long)s.nlits, oend = (long)oend_u;
+    const u32 NL = W::lanes(), lane = W::lane();
+    if (oend_u - op0 == 0) return (s.nflags == 1 && s.flags[0] == 0) ? 0 : -1;
+    TokCursor c; c.fp = 0; c.lp = 0; c.op = op0; c.p16 = c.p24 = 0; c.last_off = 0;
+    while (c.fp < s.nflags) {
+        const u32 nb = s.nflags - c.fp < NL ? s.nflags - c.fp : NL;
+        const bool act = lane < nb;
+        if (c.lp + 4096 + 128 * (long)lane < nl) W::prefetch(s.lits + c.lp + 4096 + 128 * (long)lane);
+        const u32 tok = act ? s.flags[c.fp + lane] : 0;
+        const u32 litn = tok & 15, mln = tok >> 4;
+        const bool need = act && litn == 15;
+        // bytes this token occupies in the literals stream, not counting an extended literal run itself
+        const u32 adv = act ? ((need ? 1 : litn) + 2 + (mln == 15 ? 1 : 0)) : 0;
+        u32 tot_adv = 0;
+        const u32 A = W::excl_scan(adv, &tot_adv);
+        // serial chain over the tokens whose literal length is in the stream
+        u32 pending = W::ballot(need), E = 0, myext = 0;
+        bool slow = false;
+        while (pending) {
+            const u32 k = ctz32(pending); pending &= pending - 1;
+            const long pk = c.lp + (long)W::shfl(A, k) + (long)E;
+            if (pk > nl - 5) { slow = true; break; }
+            const u32 b = s.lits[pk];
+            if (b >= 254) { slow = true; break; }
+            if (lane == k) myext = 15 + b;
+            E += 15 + b;
+        }
+        if (!slow) {
+            u32 tot_ext = 0;
+            const u32 Eex = W::excl_scan(myext, &tot_ext);
+            const long tokpos = c.lp + (long)A + (long)Eex;
+            const u32 lit_len = need ? myext : (act ? litn : 0);
+            const long lit_src = tokpos + (need ? 1 : 0);
+            const long off_pos = lit_src + lit_len;
+            bool bad = false;
+            u32 ml = 0, off = 0;
+            if (act) {
+                if (lit_src + (long)lit_len > nl - 18) bad = true;
+                else {
+                    off = rd_le16(s.lits + off_pos);
+                    ml = mln;
+                    if (mln == 15) {
+                        if (off_pos + 2 > nl - 5) bad = true;
+                        else { const u32 b2 = s.lits[off_pos + 2]; if (b2 >= 254) bad = true; else ml = 15 + b2; }
+                    }
+                    ml += kMinMatch;
+                }
+            }
+            u32 tot_out = 0;
+            const u32 O = W::excl_scan((act && !bad) ? lit_len + ml : 0, &tot_out);
+            const long opos = c.op + (long)O;
+            if (act && !bad) {
+                if (opos + (long)lit_len > oend - 16) bad = true;
+                else if ((long)off > opos + (long)lit_len) bad = true;
+                else if (opos + (long)lit_len + (long)ml > oend - 16) bad = true;
+            }
+            if (W::ballot(bad) == 0) {
+                run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml);
+                c.fp += nb; c.lp += (long)tot_adv + (long)tot_ext; c.op += (long)tot_out;
+                continue;
+            }
+        }
+        const int e = lz4_serial<W>(s, dst, oend, c, nb);
+        if (e < 0) return e;
+    }
+    const long rest = nl - c.lp;
+    if (rest < 0 || c.op + rest > oend) return -(int)c.fp - 1;
+    lanes_copy<W>(dst + c.op, s.lits + c.lp, (u32)rest);
+    W::sync();
+    c.op += rest;
+    return (int)(c.op - (long)op0);
+}
+
+// LIZv1 codewords (lib/lizard_decompress_liz.h:14-220)
+template <class W> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 op0, u32 oend_u)
+{
+    const long nl = (long)s.nlits, oend = (long)oend_u;
+    const u32 NL = W::lanes(), lane = W::lane();
+    if (oend_u - op0 == 0) return (s.nflags == 1 && s.flags[0] == 0) ? 0 : -1;
+    TokCursor c; c.fp = 0; c.lp = 0; c.op = op0; c.p16 = c.p24 = 0; c.last_off = 0;
+    while (c.fp < s.nflags) {
+        const u32 nb = s.nflags - c.fp < NL ? s.nflags - c.fp : NL;
+        const bool act = lane < nb;
+        if (c.lp + 4096 + 128 * (long)lane < nl) W::prefetch(s.lits + c.lp + 4096 + 128 * (long)lane);
+        const u32 tok = act ? s.flags[c.fp + lane] : 32;           // inactive lanes: an empty short token
+        const bool shortf = tok >= 32;                              // [r_MMMM_LLL] with a 16-bit or repeated offset
+        const u32 litn = shortf ? (tok & 7) : 0;
+        const u32 mln = shortf ? ((tok >> 3) & 15) : tok;
+        const bool need = act && shortf && litn == 7;
+        const bool mlext = act && ((shortf && mln == 15) || (!shortf && tok == kLastLongOff));
+        const bool new16 = act && shortf && (tok >> 7) == 0;
+        const u32 adv = act ? ((need ? 1 : litn) + (mlext ? 1 : 0)) : 0;
+        u32 tot_adv = 0, tot16 = 0, tot24 = 0;
+        const u32 A = W::excl_scan(adv, &tot_adv);
+        const u32 P16 = W::excl_scan(new16 ? 2u : 0u, &tot16);
+        const u32 P24 = W::excl_scan((act && !shortf) ? 3u : 0u, &tot24);
+        u32 pending = W::ballot(need), E = 0, myext = 0;
+        bool slow = false;
+        while (pending) {
+            const u32 k = ctz32(pending); pending &= pending - 1;
+            const long pk = c.lp + (long)W::shfl(A, k) + (long)E;
+            if (pk > nl - 1) { slow = true; break; }
+            const u32 b = s.lits[pk];
+            if (b >= 254) { slow = true; break; }
+            if (lane == k) myext = 7 + b;
+            E += 7 + b;
+        }
+        if (!slow) {
+            u32 tot_ext = 0;
+            const u32 Eex = W::excl_scan(myext, &tot_ext);
+            const long tokpos = c.lp + (long)A + (long)Eex;
+            const u32 lit_len = need ? myext : (act ? litn : 0);
+            const long lit_src = tokpos + (need ? 1 : 0);
+            const long ext_pos = lit_src + lit_len;                 // where a match-length extension byte would sit
+            bool bad = false;
+            u32 ml = 0, off = 0;
+            if (act) {
+                if (shortf) {
+                    if (lit_src > nl - 16 || lit_src + (long)lit_len > nl) bad = true;
+                    else if (c.p16 + P16 + (new16 ? 2u : 0u) > s.noff16) bad = true;
+                    else {
+                        if (new16) off = rd_le16(s.off16 + c.p16 + P16);
+                        ml = mln;
+                        if (mln == 15) {
+                            if (ext_pos > nl - 1) bad = true;
+                            else { const u32 b2 = s.lits[ext_pos]; if (b2 >= 254) bad = true; else ml = 15 + b2; }
+                        }
+                    }
+                } else {
+                    if (tok == kLastLongOff) {
+                        if (ext_pos > nl - 1) bad = true;
+                        else { const u32 b2 = s.lits[ext_pos]; if (b2 >= 254) bad = true; else ml = b2 + kLastLongOff + kMmLongOff; }
+                    } else ml = tok + kMmLongOff;
+                    if (!bad) {
+                        if ((long)(c.p24 + P24) > (long)s.noff24 - 3) bad = true;
+                        else off = rd_le24(s.off24 + c.p24 + P24);
+                    }
+                }
+            }
+            // repeat-offset tokens take the offset of the closest earlier token that carried one
+            const bool has_off = act && (new16 || !shortf);
+            const u32 carriers = W::ballot(has_off);
+            const u32 before = carriers & ((lane == 0) ? 0u : (0xffffffffu >> (32 - lane)));
+            const u32 src_lane = before ? highbit32(before) : lane;
+            const u32 inherited = W::shfl(off, src_lane);
+            if (act && !has_off) off = before ? inherited : c.last_off;
+            u32 tot_out = 0;
+            const u32 O = W::excl_scan((act && !bad) ? lit_len + ml : 0, &tot_out);
+            const long opos = c.op + (long)O;
+            if (act && !bad) {
+                if (shortf && opos + (long)lit_len > oend - 16) bad = true;
+                else if ((long)off > opos + (long)lit_len) bad = true;
+                else if (opos + (long)lit_len + (long)ml > oend - 16) bad = true;
+            }
+            if (W::ballot(bad) == 0) {
+                run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml);
+                c.fp += nb; c.lp += (long)tot_adv + (long)tot_ext; c.op += (long)tot_out;
+                c.p16 += tot16; c.p24 += tot24;
+                c.last_off = W::shfl(off, nb - 1);
+                continue;
+            }
+        }
+        const int e = lizv1_serial<W>(s, dst, oend, c, nb);
+        if (e < 0) return e;
+    }
+    const long rest = nl - c.lp;
+    if (rest < 0 || c.op + rest > oend) return -(int)c.fp - 1;
+    lanes_copy<W>(dst + c.op, s.lits + c.lp, (u32)rest);
+    W::sync();
+    c.op += rest;
+    return (int)(c.op - (long)op0);
 }
 
 // One stream header.  Returns 1 on success, 0 on failure (Lizard_readStream, lizard_decompress.c:72-112).
 // `ip` is an offset into the unit.
-LZ_D int read_stream(bool huff, const u8* src, long csize, long& ip, u8* scratch, const u8** ptr, u32* len,
-                     DecWarpShared* sh, u32 lane)
+template <class W> LZ_HD int read_stream(bool huff, const u8* src, long csize, long& ip, u8* scratch, const u8** ptr, u32* len,
+                                        DecWarpShared* sh)
 {
     if (!huff) {
         if (ip > csize - 3) return 0;
@@ -274,7 +562,7 @@ LZ_D int read_stream(bool huff, const u8* src, long csize, long& ip, u8* scratch
     if (ip > csize - 6) return 0;
     const u32 n = rd_le24(src + ip), c = rd_le24(src + ip + 3);
     if (n > kBlockSize || ip + (long)c > csize - 6) return 0;
-    const int r = warp_huf_decompress(scratch, n, src + ip + 6, c, sh, lane);
+    const int r = huf_decompress_lanes<W>(scratch, n, src + ip + 6, c, sh);
     if (r < 0 || (u32)r != n) return 0;
     ip += (long)c + 6;
     *ptr = scratch; *len = n;
@@ -282,7 +570,7 @@ LZ_D int read_stream(bool huff, const u8* src, long csize, long& ip, u8* scratch
 }
 
 // Lizard_decompress_safe for one unit; every lane returns the same value.
-LZ_D int decode_unit(const u8* src, u32 csize_u, u8* dst, u32 cap, u8* scratch, DecWarpShared* sh, u32 lane)
+template <class W> LZ_HD int decode_unit(const u8* src, u32 csize_u, u8* dst, u32 cap, u8* scratch, DecWarpShared* sh)
 {
     const long csize = (long)csize_u;
     if (csize < 1) return 0;
@@ -297,8 +585,8 @@ LZ_D int decode_unit(const u8* src, u32 csize_u, u8* dst, u32 cap, u8* scratch, 
             if (ip > csize - 3) return -1;
             const u32 len = rd_le24(src + ip); ip += 3;
             if (ip + (long)len > csize || op + (long)len > (long)cap) return -1;
-            warp_copy(dst + op, src + ip, len, lane);
-            __syncwarp();
+            lanes_copy<W>(dst + op, src + ip, len);
+            W::sync();
             op += len; ip += len;
             continue;
         }
@@ -311,14 +599,13 @@ LZ_D int decode_unit(const u8* src, u32 csize_u, u8* dst, u32 cap, u8* scratch, 
             ip = len_end;
         }
         Streams s;
-        s.src_end = src + csize;
-        if (!read_stream(hdr & kFlagOff16, src, csize, ip, scratch + 3 * kDecStreamScratch, &s.off16, &s.noff16, sh, lane)) return -1;
-        if (!read_stream(hdr & kFlagOff24, src, csize, ip, scratch + 2 * kDecStreamScratch, &s.off24, &s.noff24, sh, lane)) return -1;
-        if (!read_stream(hdr & kFlagFlags, src, csize, ip, scratch + 1 * kDecStreamScratch, &s.flags, &s.nflags, sh, lane)) return -1;
-        if (!read_stream(hdr & kFlagLiterals, src, csize, ip, scratch, &s.lits, &s.nlits, sh, lane)) return -1;
+        s.src_begin = src; s.src_end = src + csize;
+        if (!read_stream<W>(hdr & kFlagOff16, src, csize, ip, scratch + 3 * kDecStreamScratch, &s.off16, &s.noff16, sh)) return -1;
+        if (!read_stream<W>(hdr & kFlagOff24, src, csize, ip, scratch + 2 * kDecStreamScratch, &s.off24, &s.noff24, sh)) return -1;
+        if (!read_stream<W>(hdr & kFlagFlags, src, csize, ip, scratch + 1 * kDecStreamScratch, &s.flags, &s.nflags, sh)) return -1;
+        if (!read_stream<W>(hdr & kFlagLiterals, src, csize, ip, scratch, &s.lits, &s.nlits, sh)) return -1;
         if (ip > csize) return -1;
-        const int res = lizv1 ? decode_tokens_lizv1(s, dst, (u32)op, cap, lane, src)
-                              : decode_tokens_lz4(s, dst, (u32)op, cap, lane);
+        const int res = lizv1 ? decode_tokens_lizv1<W>(s, dst, (u32)op, cap) : decode_tokens_lz4<W>(s, dst, (u32)op, cap);
         if (res <= 0) return res;
         op += res;
     }

@@ -9,6 +9,7 @@
 #pragma once
 #include "common.cuh"
 #include "encode_core.cuh"
+#include "decode.cuh"       // Progress hand-shake
 #include <cuda_runtime.h>
 
 namespace lzb {
@@ -21,6 +22,7 @@ struct EncodeBatch {
     int        level;
     u8*        scratch;   // grid_warps * per_warp_bytes
     u32*       counter;
+    Progress   progress;
 };
 
 struct EncodeConfig {
@@ -49,10 +51,12 @@ lizard_encode_units_kernel(EncodeBatch b, u32 table_in_smem, size_t per_warp_byt
         if (lane == 0) unit = atomicAdd(b.counter, 1u);
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= b.n_units) break;
+        progress_wait(b.progress, unit, lane);
         const int r = encode_unit<WarpLanes>(b.src_base + b.src_off[unit], b.src_len[unit],
                                              b.dst_base + b.dst_off[unit], b.dst_cap[unit], b.level, table, work);
         if (lane == 0) b.result[unit] = r;
         __syncwarp();
+        progress_done(b.progress, unit, lane);
     }
 }
 

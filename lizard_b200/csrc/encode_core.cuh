@@ -16,6 +16,7 @@
 #pragma once
 #include "common.cuh"
 #include "entropy_enc.cuh"
+#include "lanes.cuh"
 #if !defined(__CUDACC__)
 #include <string.h>
 #endif
@@ -69,49 +70,6 @@ LZ_HD u32 count_match(const u8* a, const u8* b, const u8* limit)
     }
     while (a < limit && *a == *b) { a++; b++; }
     return (u32)(a - a0);
-}
-
-// ---- lane policies ----------------------------------------------------------------------------------
-struct HostLanes {
-    static constexpr bool kDevice = false;
-    LZ_HDM static u32 lane() { return 0; }
-    LZ_HDM static u32 lanes() { return 1; }
-    LZ_HDM static void sync() {}
-    LZ_HDM static int bcast(int v) { return v; }
-    LZ_HDM static u32 sum(u32 v) { return v; }
-    LZ_HDM static u32 excl_scan(u32 v, u32* total) { *total = v; return 0; }
-    LZ_HDM static u32 ballot(bool p) { return p ? 1u : 0u; }
-    LZ_HDM static u32 shfl(u32 v, u32) { return v; }
-    LZ_HDM static u32 match_any(u32) { return 1u; }
-};
-#if defined(__CUDACC__)
-struct WarpLanes {
-    static constexpr bool kDevice = true;
-    __device__ __forceinline__ static u32 lane() { return threadIdx.x & 31; }
-    __device__ __forceinline__ static u32 lanes() { return 32; }
-    __device__ __forceinline__ static void sync() { __syncwarp(); }
-    __device__ __forceinline__ static int bcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
-    __device__ __forceinline__ static u32 sum(u32 v)
-    {
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        return v;
-    }
-    __device__ __forceinline__ static u32 excl_scan(u32 v, u32* total)
-    {
-        u32 x = v;
-        for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= (u32)o) x += y; }
-        *total = __shfl_sync(0xffffffffu, x, 31);
-        return x - v;
-    }
-    __device__ __forceinline__ static u32 ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
-    __device__ __forceinline__ static u32 shfl(u32 v, u32 src) { return __shfl_sync(0xffffffffu, v, (int)src); }
-    __device__ __forceinline__ static u32 match_any(u32 v) { return __match_any_sync(0xffffffffu, v); }
-};
-#endif
-
-template <class W> LZ_HD void lanes_copy(u8* dst, const u8* src, u32 n)
-{
-    for (u32 i = W::lane(); i < n; i += W::lanes()) dst[i] = src[i];
 }
 
 // ---- the five output streams of one inner block -------------------------------------------------------
@@ -263,15 +221,6 @@ last_literals:
 }
 
 // ---- lane-parallel building blocks ---------------------------------------------------------------------
-LZ_HD u32 ctz32(u32 v)
-{
-#if defined(__CUDA_ARCH__)
-    return (u32)(__ffs((int)v) - 1);
-#else
-    return (u32)__builtin_ctz(v);
-#endif
-}
-
 // Position of the j-th probe of one fastSmall search relative to its first probe: the stride grows by one
 // every 64 probes (step = searchMatchNb++ >> 6, lizard_parser_fastsmall.h:69-75), so the offsets are
 // 0,1,2,...,65,67,69,... independent of the data.

@@ -218,7 +218,7 @@ struct HufStatsScratch {          // explicit so a device lane can place it wher
     FseCell cells[1u << kHufHeaderFseLog];
 };
 
-LZ_HD int huf_read_stats(u8* weights, u32* rank_count, u32* nsym, u32* table_log,
+LZ_HD_COLD int huf_read_stats(u8* weights, u32* rank_count, u32* nsym, u32* table_log,
                          const u8* src, u32 size, HufStatsScratch* ws)
 {
     if (size == 0) return kErrSrcSize;
@@ -271,7 +271,7 @@ LZ_HD int huf_read_stats(u8* weights, u32* rank_count, u32* nsym, u32* table_log
 
 // Single-symbol decode table: entry = symbol | nbBits << 8, 1 << table_log entries.
 // rank_count[] is consumed (turned into running start positions).
-LZ_HD void huf_fill_dtable(u16* table, const u8* weights, u32* rank_count, u32 nsym, u32 table_log)
+LZ_HD_COLD void huf_fill_dtable(u16* table, const u8* weights, u32* rank_count, u32 nsym, u32 table_log)
 {
     u32 start = 0;
     for (u32 w = 1; w <= table_log; ++w) { u32 cur = start; start += rank_count[w] << (w - 1); rank_count[w] = cur; }
@@ -375,7 +375,7 @@ LZ_HD void hufx2_finish(u8* base, long p, long pend, BitReader& b, const u16* t,
 
 // 4-segment payload after the weight header.  dst must have 8 bytes of slack past n (the
 // reference writes up to 2 bytes past tiny outputs and the pair decoder stores 2 bytes at a time).
-LZ_HD int huf_decode4_serial(u8* dst, u32 n, const u8* src, u32 c, const u16* t, u32 tl, u32 algo)
+LZ_HD_COLD int huf_decode4_serial(u8* dst, u32 n, const u8* src, u32 c, const u16* t, u32 tl, u32 algo)
 {
     if (c < 10) return kErrCorrupt;
     u32 l1 = rd_le16(src), l2 = rd_le16(src + 2), l3 = rd_le16(src + 4);

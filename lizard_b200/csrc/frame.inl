@@ -156,21 +156,50 @@ __global__ void __launch_bounds__(256) lizard_frame_pack_kernel(PackArgs a)
     else cta_copy(o + 4, a.src_base + (size_t)i * a.block_size, len);
 }
 
-// Units per pipeline stage: host->device copy of chunk k+1, kernels of chunk k and device->host copy of
-// chunk k-1 run concurrently on three streams (PCIe is full duplex, the copy engines are separate).
-constexpr size_t kFrameChunkBytes = 64u << 20;
+// Host pipelining: ONE kernel launch covers all units (no per-chunk tail effects); the input is copied in
+// chunks on a second stream, each copy followed by a 1-thread kernel that publishes how many leading units
+// are resident (Progress::ready); the last unit of each chunk raises a flag in pinned host memory, upon
+// which the host packs / copies that chunk back on a third stream.  H2D, kernels and D2H overlap.
+constexpr size_t kFrameChunkBytes = 32u << 20;
 
-struct ChunkEvents {
-    std::vector<cudaEvent_t> in, done;
-    cudaError_t make(size_t n) {
-        in.resize(n); done.resize(n);
-        for (size_t i = 0; i < n; ++i) {
-            cudaError_t e = cudaEventCreateWithFlags(&in[i], cudaEventDisableTiming); if (e != cudaSuccess) return e;
-            e = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming); if (e != cudaSuccess) return e;
+// wait for chunk k's completion flag; false if the compute stream died
+bool wait_chunk(Context& c, volatile u32* flag)
+{
+    unsigned spins = 0;
+    while (*flag == 0) {
+        if ((++spins & 0xFFF) == 0) {
+            cudaError_t q = cudaStreamQuery(c.stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) { fail("frame kernel", q); return false; }
+            if (q == cudaSuccess && *flag == 0) { g_last_error = "frame kernel finished without completing a chunk"; return false; }
         }
-        return cudaSuccess;
     }
-    ~ChunkEvents() { for (auto e : in) cudaEventDestroy(e); for (auto e : done) cudaEventDestroy(e); }
+    return true;
+}
+
+struct StreamProgress {
+    Progress pg; u32* d_ready; volatile u32* h_done; u32* h_ready_vals; size_t nchunks;
+    cudaEvent_t tables_ready = nullptr;
+    ~StreamProgress() { if (tables_ready) cudaEventDestroy(tables_ready); }
+    // d_progress layout: [ready][pad x3][done_count x nchunks]; flags in pinned memory
+    cudaError_t init(Context& c, size_t n_units, size_t per_chunk)
+    {
+        nchunks = (n_units + per_chunk - 1) / per_chunk;
+        cudaError_t e;
+        if ((e = c.d_progress.reserve((4 + nchunks) * 4 + 64)) != cudaSuccess) return e;
+        if ((e = c.pin_flags.reserve(nchunks * 8 + 64)) != cudaSuccess) return e;
+        d_ready = (u32*)c.d_progress.p;
+        h_done = (volatile u32*)c.pin_flags.p;
+        h_ready_vals = (u32*)c.pin_flags.p + nchunks;
+        for (size_t k = 0; k < nchunks; ++k) {
+            h_done[k] = 0;
+            const size_t upto = (k + 1) * per_chunk;
+            h_ready_vals[k] = (u32)(upto < n_units ? upto : n_units);
+        }
+        if ((e = cudaMemsetAsync(c.d_progress.p, 0, (4 + nchunks) * 4, c.stream)) != cudaSuccess) return e;
+        pg.ready = d_ready; pg.done_count = d_ready + 4; pg.host_done = h_done;
+        pg.chunk_units = (u32)per_chunk; pg.n_units = (u32)n_units;
+        return cudaEventCreateWithFlags(&tables_ready, cudaEventDisableTiming);
+    }
 };
 
 // Compress src[0..n) as independent blocks of block_size into the frame body at `dst` (records only).
@@ -180,12 +209,13 @@ size_t frame_compress_blocks(Context& c, u8* dst, size_t dst_cap, const u8* src,
     if (n == 0) return 0;
     const size_t nblk = (n + block_size - 1) / block_size;
     size_t per_chunk = kFrameChunkBytes / block_size; if (per_chunk < 1) per_chunk = 1;
-    const size_t nchunks = (nblk + per_chunk - 1) / per_chunk;
     const size_t stride = (block_size + 15) / 16 * 16;
     const size_t tab_bytes = nblk * (8 + 4 + 8 + 4);
-    const size_t host_tab = tab_bytes + nchunks * 8 + 64;
-    const size_t dev_tab = tab_bytes + nblk * 4 + (nblk + nchunks + 1) * 8 + 64;
-    if (c.pin_tab.reserve(host_tab) != cudaSuccess || c.d_tab.reserve(dev_tab) != cudaSuccess ||
+    StreamProgress sp;
+    if (sp.init(c, nblk, per_chunk) != cudaSuccess) return ferr(FE_allocation_failed);
+    const size_t nchunks = sp.nchunks;
+    if (c.pin_tab.reserve(tab_bytes + nchunks * 8 + 64) != cudaSuccess ||
+        c.d_tab.reserve(tab_bytes + nblk * 4 + (nblk + nchunks + 1) * 8 + 64) != cudaSuccess ||
         c.d_in.reserve(n + 64) != cudaSuccess || c.d_out.reserve(nblk * stride + 64) != cudaSuccess ||
         c.d_pack.reserve(n + nblk * 16 + 64) != cudaSuccess) return ferr(FE_allocation_failed);
     u64* t_in_off = (u64*)c.pin_tab.p; u64* t_out_off = t_in_off + nblk;
@@ -202,49 +232,53 @@ size_t frame_compress_blocks(Context& c, u8* dst, size_t dst_cap, const u8* src,
     const u32* d_in_len = (const u32*)(d_out_off + nblk); const u32* d_out_cap = d_in_len + nblk;
     int* d_res = (int*)(d_out_cap + nblk);
     u64* d_pack_off = (u64*)(((size_t)(d_res + nblk) + 7) & ~(size_t)7);
-    ChunkEvents ev;
-    if (ev.make(nchunks) != cudaSuccess) return ferr(FE_allocation_failed);
+
     if (cudaMemcpyAsync(dtab, c.pin_tab.p, tab_bytes, cudaMemcpyHostToDevice, c.s_in) != cudaSuccess) return ferr(FE_GENERIC);
+    cudaEventRecord(sp.tables_ready, c.s_in);
+    cudaStreamWaitEvent(c.stream, sp.tables_ready, 0);
+    if (launch_encode(c, c.d_in.p, d_in_off, d_in_len, c.d_out.p, d_out_off, d_out_cap, d_res, (u32)nblk, level, c.stream, &sp.pg) != LIZARDB200_OK)
+        return ferr(FE_GENERIC);
     for (size_t k = 0; k < nchunks; ++k) {
         const size_t first = k * per_chunk, off = first * block_size;
         const size_t bytes = (k + 1 == nchunks) ? n - off : per_chunk * block_size;
-        if (cudaMemcpyAsync((u8*)c.d_in.p + off, src + off, bytes, cudaMemcpyHostToDevice, c.s_in) != cudaSuccess) return ferr(FE_GENERIC);
-        cudaEventRecord(ev.in[k], c.s_in);
+        const size_t upto = (k + 1 == nchunks) ? nblk : first + per_chunk;
+        cudaMemcpyAsync((u8*)c.d_in.p + off, src + off, bytes, cudaMemcpyHostToDevice, c.s_in);
+        // publish "units [0, upto) are resident" with a 4-byte copy queued behind the data copy: it runs on the copy
+        // engine, so it cannot be starved by the persistent kernel occupying every SM
+        (void)upto;
+        cudaMemcpyAsync(sp.d_ready, &sp.h_ready_vals[k], 4, cudaMemcpyHostToDevice, c.s_in);
     }
+    size_t written = 0;
+    bool too_small = false, failed = false;
     for (size_t k = 0; k < nchunks; ++k) {
         const size_t first = k * per_chunk, off = first * block_size;
         const size_t cnt = (k + 1 == nchunks) ? nblk - first : per_chunk;
         const size_t bytes = (k + 1 == nchunks) ? n - off : per_chunk * block_size;
-        cudaStreamWaitEvent(c.stream, ev.in[k], 0);
-        if (launch_encode(c, c.d_in.p, d_in_off + first, d_in_len + first, c.d_out.p, d_out_off + first, d_out_cap + first,
-                          d_res + first, (u32)cnt, level, c.stream) != LIZARDB200_OK) return ferr(FE_GENERIC);
+        if (!wait_chunk(c, &sp.h_done[k])) { failed = true; break; }
         PackArgs a;
         a.comp_base = (const u8*)c.d_out.p + first * stride; a.comp_stride = stride; a.result = d_res + first;
         a.src_base = (const u8*)c.d_in.p + off; a.block_size = (u32)block_size; a.src_size = bytes;
         a.out_off = d_pack_off + first + k; a.out = (u8*)c.d_pack.p + off + first * 8; a.n = (u32)cnt; a.level = level;
-        lizard_frame_scan_kernel<<<1, 1024, 0, c.stream>>>(a);
-        lizard_frame_pack_kernel<<<(unsigned)cnt, 256, 0, c.stream>>>(a);
+        lizard_frame_scan_kernel<<<1, 1024, 0, c.s_out>>>(a);
+        lizard_frame_pack_kernel<<<(unsigned)cnt, 256, 0, c.s_out>>>(a);
         g_launches += 2;
-        if (cudaMemcpyAsync((void*)&h_totals[k], a.out_off + cnt, 8, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) return ferr(FE_GENERIC);
-        cudaEventRecord(ev.done[k], c.stream);
-    }
-    size_t written = 0;
-    for (size_t k = 0; k < nchunks; ++k) {
-        const size_t first = k * per_chunk, off = first * block_size;
-        if (cudaEventSynchronize(ev.done[k]) != cudaSuccess) { fail("frame compress", cudaGetLastError()); cudaDeviceSynchronize(); return ferr(FE_GENERIC); }
+        cudaMemcpyAsync((void*)&h_totals[k], a.out_off + cnt, 8, cudaMemcpyDeviceToHost, c.s_out);
+        if (cudaStreamSynchronize(c.s_out) != cudaSuccess) { failed = true; break; }
         const size_t total = (size_t)h_totals[k];
-        if (written + total > dst_cap) { cudaDeviceSynchronize(); return ferr(FE_dstMaxSize_tooSmall); }
-        if (cudaMemcpyAsync(dst + written, (u8*)c.d_pack.p + off + first * 8, total, cudaMemcpyDeviceToHost, c.s_out) != cudaSuccess) return ferr(FE_GENERIC);
+        if (written + total > dst_cap) { too_small = true; break; }
+        cudaMemcpyAsync(dst + written, a.out, total, cudaMemcpyDeviceToHost, c.s_out);
         written += total;
     }
-    if (cudaStreamSynchronize(c.s_out) != cudaSuccess) return ferr(FE_GENERIC);
+    cudaError_t e1 = cudaStreamSynchronize(c.s_out), e2 = cudaStreamSynchronize(c.stream), e3 = cudaStreamSynchronize(c.s_in);
+    if (failed || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { if (!failed) fail("frame compress", e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3); return ferr(FE_GENERIC); }
+    if (too_small) return ferr(FE_dstMaxSize_tooSmall);
     return written;
 }
 
 struct FrameBlockRef { size_t src_pos; u32 csize; size_t dst_pos; };
 
 // Decode `blocks` (compressed independent blocks inside src, ascending) into dst, each with capacity max_block.
-// sizes_out[i] = decoded size or negative.  Host pointers.  Pipelined like the compressor.
+// sizes_out[i] = decoded size or negative.  Host pointers.
 int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::vector<FrameBlockRef>& blocks,
                         u8* dst, size_t dst_span, u32 max_block, std::vector<int>& sizes_out)
 {
@@ -252,10 +286,12 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
     sizes_out.assign(n, -1);
     if (n == 0) return 0;
     size_t per_chunk = kFrameChunkBytes / max_block; if (per_chunk < 1) per_chunk = 1;
-    const size_t nchunks = (n + per_chunk - 1) / per_chunk;
     const size_t tab_bytes = n * (8 + 4 + 8 + 4);
+    StreamProgress sp;
+    if (sp.init(c, n, per_chunk) != cudaSuccess) return -1;
+    const size_t nchunks = sp.nchunks;
     if (c.pin_tab.reserve(tab_bytes + n * 4 + 64) != cudaSuccess || c.d_tab.reserve(tab_bytes + n * 4 + 64) != cudaSuccess ||
-        c.d_in.reserve(src_span + 64) != cudaSuccess || c.d_out.reserve(dst_span + 64) != cudaSuccess) return -1;
+        c.d_in.reserve(src_span + 256) != cudaSuccess || c.d_out.reserve(dst_span + 64) != cudaSuccess) return -1;
     u64* t_in_off = (u64*)c.pin_tab.p; u64* t_out_off = t_in_off + n;
     u32* t_in_len = (u32*)(t_out_off + n); u32* t_out_cap = t_in_len + n; volatile int* t_res = (volatile int*)(t_out_cap + n);
     for (size_t i = 0; i < n; ++i) {
@@ -265,32 +301,35 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
     u8* dtab = (u8*)c.d_tab.p;
     const u64* d_in_off = (const u64*)dtab; const u64* d_out_off = d_in_off + n;
     const u32* d_in_len = (const u32*)(d_out_off + n); const u32* d_out_cap = d_in_len + n; int* d_res = (int*)(d_out_cap + n);
-    ChunkEvents ev;
-    if (ev.make(nchunks) != cudaSuccess) return -1;
     if (cudaMemcpyAsync(dtab, c.pin_tab.p, tab_bytes, cudaMemcpyHostToDevice, c.s_in) != cudaSuccess) return -1;
+    cudaEventRecord(sp.tables_ready, c.s_in);
+    cudaStreamWaitEvent(c.stream, sp.tables_ready, 0);
+    if (launch_decode(c, c.d_in.p, d_in_off, d_in_len, c.d_out.p, d_out_off, d_out_cap, d_res, (u32)n, c.stream, &sp.pg) != LIZARDB200_OK) return -1;
+    {   // input chunks: [first block start, last block end) widened to 128-byte lines so that a cache line shared
+        // with the next chunk's first unit is final the first time an SM touches it
+        size_t copied_to = 0;
+        for (size_t k = 0; k < nchunks; ++k) {
+            const size_t first = k * per_chunk, last = (k + 1 == nchunks ? n : first + per_chunk) - 1;
+            size_t lo = blocks[first].src_pos; if (lo > copied_to) lo = lo & ~(size_t)127; if (lo < copied_to) lo = copied_to;
+            size_t hi = (blocks[last].src_pos + blocks[last].csize + 127) & ~(size_t)127; if (hi > src_span) hi = src_span;
+            if (hi > lo) cudaMemcpyAsync((u8*)c.d_in.p + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, c.s_in);
+            copied_to = hi > copied_to ? hi : copied_to;
+            cudaMemcpyAsync(sp.d_ready, &sp.h_ready_vals[k], 4, cudaMemcpyHostToDevice, c.s_in);
+        }
+    }
+    bool failed = false;
     for (size_t k = 0; k < nchunks; ++k) {
         const size_t first = k * per_chunk, last = (k + 1 == nchunks ? n : first + per_chunk) - 1;
-        const size_t lo = blocks[first].src_pos, hi = blocks[last].src_pos + blocks[last].csize;
-        if (cudaMemcpyAsync((u8*)c.d_in.p + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, c.s_in) != cudaSuccess) return -1;
-        cudaEventRecord(ev.in[k], c.s_in);
-    }
-    for (size_t k = 0; k < nchunks; ++k) {
-        const size_t first = k * per_chunk, cnt = (k + 1 == nchunks ? n : first + per_chunk) - first;
-        cudaStreamWaitEvent(c.stream, ev.in[k], 0);
-        if (launch_decode(c, c.d_in.p, d_in_off + first, d_in_len + first, c.d_out.p, d_out_off + first, d_out_cap + first,
-                          d_res + first, (u32)cnt, c.stream) != LIZARDB200_OK) return -1;
-        if (cudaMemcpyAsync((void*)(t_res + first), d_res + first, cnt * 4, cudaMemcpyDeviceToHost, c.stream) != cudaSuccess) return -1;
-        cudaEventRecord(ev.done[k], c.stream);
-    }
-    for (size_t k = 0; k < nchunks; ++k) {
-        const size_t first = k * per_chunk, last = (k + 1 == nchunks ? n : first + per_chunk) - 1;
-        if (cudaEventSynchronize(ev.done[k]) != cudaSuccess) { fail("frame decode", cudaGetLastError()); cudaDeviceSynchronize(); return -1; }
+        if (!wait_chunk(c, &sp.h_done[k])) { failed = true; break; }
+        cudaMemcpyAsync((void*)(t_res + first), d_res + first, (last - first + 1) * 4, cudaMemcpyDeviceToHost, c.s_out);
+        if (cudaStreamSynchronize(c.s_out) != cudaSuccess) { failed = true; break; }
         // copy back exactly what was produced: contiguous up to the end of the last good block of the chunk
         size_t lo = blocks[first].dst_pos, hi = lo;
         for (size_t i = first; i <= last; ++i) { sizes_out[i] = t_res[i]; if (t_res[i] > 0) hi = blocks[i].dst_pos + (size_t)t_res[i]; }
-        if (hi > lo && cudaMemcpyAsync(dst + lo, (u8*)c.d_out.p + lo, hi - lo, cudaMemcpyDeviceToHost, c.s_out) != cudaSuccess) return -1;
+        if (hi > lo) cudaMemcpyAsync(dst + lo, (u8*)c.d_out.p + lo, hi - lo, cudaMemcpyDeviceToHost, c.s_out);
     }
-    if (cudaStreamSynchronize(c.s_out) != cudaSuccess) return -1;
+    cudaError_t e1 = cudaStreamSynchronize(c.s_out), e2 = cudaStreamSynchronize(c.stream), e3 = cudaStreamSynchronize(c.s_in);
+    if (failed || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return -1;
     return 0;
 }
 

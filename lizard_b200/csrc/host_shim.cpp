@@ -5,6 +5,7 @@
 // path links or loads this file; liblizard_b200.so has no CPU code path.
 #include "entropy_dec.cuh"
 #include "encode_core.cuh"
+#include "decode.cuh"
 #include <stdlib.h>
 
 extern "C" int lzb_host_huf_decompress(unsigned char* dst, unsigned n, const unsigned char* src, unsigned c)
@@ -27,6 +28,19 @@ extern "C" int lzb_host_compress(const unsigned char* src, int n, unsigned char*
     work->huf.seg_count = (lzb::u32 (*)[256])malloc(4 * 256 * sizeof(lzb::u32));
     int r = lzb::encode_unit<lzb::HostLanes>(src, (lzb::u32)n, dst, (lzb::u32)cap, level, table, work);
     free(work->huf.seg_count); free(table); free(work);
+    return r;
+}
+
+// Lizard_decompress_safe through the one-lane instantiation of the device decoder
+extern "C" int lzb_host_decompress(const unsigned char* src, int csize, unsigned char* dst, int cap)
+{
+    if (csize < 1) return 0;
+    if (cap < 0) return -1;
+    unsigned char* scratch = (unsigned char*)malloc(lzb::kDecScratchPerWarp);
+    lzb::DecWarpShared* sh = (lzb::DecWarpShared*)malloc(sizeof(lzb::DecWarpShared));
+    sh->big_table = (lzb::u16*)(scratch + 4 * lzb::kDecStreamScratch);
+    int r = lzb::decode_unit<lzb::HostLanes>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, sh);
+    free(scratch); free(sh);
     return r;
 }
 
@@ -131,6 +145,7 @@ struct EmuLanes {
     {
         unsigned long long t[emu::kLanes]; emu::exchange(v, t); return (lzb::u32)t[src & 31];
     }
+    static void prefetch(const void*) {}
     static lzb::u32 match_any(lzb::u32 v)
     {
         unsigned long long t[emu::kLanes]; emu::exchange(v, t);
@@ -161,5 +176,28 @@ extern "C" int lzb_emu_compress(const unsigned char* src, int n, unsigned char* 
     a.work->huf.seg_count = (lzb::u32 (*)[256])malloc(4 * 256 * sizeof(lzb::u32));
     emu::run(emu_compress_body, &a);
     free(a.work->huf.seg_count); free(a.table); free(a.work);
+    return a.result;
+}
+
+struct EmuDecompressArgs { const unsigned char* src; int csize; unsigned char* dst; int cap; unsigned char* scratch; lzb::DecWarpShared* sh; int result; };
+static void emu_decompress_body(void* p)
+{
+    EmuDecompressArgs* a = (EmuDecompressArgs*)p;
+    int r = lzb::decode_unit<EmuLanes>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh);
+    if (EmuLanes::lane() == 0) a->result = r;
+}
+
+// Lizard_decompress_safe through the 32-lane emulation of the device code path
+extern "C" int lzb_emu_decompress(const unsigned char* src, int csize, unsigned char* dst, int cap)
+{
+    if (csize < 1) return 0;
+    if (cap < 0) return -1;
+    EmuDecompressArgs a;
+    a.src = src; a.csize = csize; a.dst = dst; a.cap = cap; a.result = -1;
+    a.scratch = (unsigned char*)malloc(lzb::kDecScratchPerWarp);
+    a.sh = (lzb::DecWarpShared*)malloc(sizeof(lzb::DecWarpShared));
+    a.sh->big_table = (lzb::u16*)(a.scratch + 4 * lzb::kDecStreamScratch);
+    emu::run(emu_decompress_body, &a);
+    free(a.scratch); free(a.sh);
     return a.result;
 }

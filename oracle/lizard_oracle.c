@@ -313,6 +313,12 @@ size_t oracle_HUF_decompress(void* dstv, size_t n, const void* srcv, size_t c)
  * =================================================================================================== */
 typedef struct { const u8 *flags, *flags_end, *lits, *lits_end, *o16, *o16_end, *o24, *o24_end; } o_dstreams;
 
+/* diagnostic for the tests: smallest match offset seen by the last oracle_Lizard_decompress_safe call of this
+ * thread.  Every Lizard parser enforces offsets >= 8 (LIZARD_*_MIN_OFFSET); below that the reference's 8-byte
+ * granule copies (lizard_common.h:347-377) make its output depend on stale bytes past the write cursor. */
+static __thread unsigned o_min_offset_seen = 0xFFFFFFFFu;
+unsigned oracle_last_min_offset(void) { return o_min_offset_seen; }
+
 static void o_copy8(u8* d, const u8* s) { u64 v; memcpy(&v, s, 8); memcpy(d, &v, 8); }   /* 8-byte granule, as compiled */
 static void o_wild16(u8* d, const u8* s, u8* e) { do { o_copy8(d, s); o_copy8(d + 8, s + 8); d += 16; s += 16; } while (d < e); }
 
@@ -341,6 +347,7 @@ static int o_decode_lz4(o_dstreams* s, u8* dest, int out_size, const u8* low)
         {   u32 off = rd16(s->lits); const u8* m; s->lits += 2;
             m = op - off;
             if (m < low) goto err;
+            if (off < o_min_offset_seen) o_min_offset_seen = off;
             len = tok >> 4;
             if (len == 15) { if (s->lits > iend - 5) goto err; len = o_ext(&s->lits) + 15; }
             len += 4;
@@ -388,6 +395,7 @@ static int o_decode_lizv1(o_dstreams* s, u8* dest, int out_size, const u8* low)
         }
         {   const u8* m = op + last;
             if (m < low) goto err;
+            if ((unsigned)(-last) < o_min_offset_seen && len > 0) o_min_offset_seen = (unsigned)(-last);
             cpy = op + len;
             if (cpy > oend - 16) goto err;
             o_copy8(op, m); o_copy8(op + 8, m + 8);
@@ -425,6 +433,7 @@ int oracle_Lizard_decompress_safe(const char* source, char* dest, int csize, int
     u8* op = (u8*)dest; u8* const oend = op + max_out;
     int out_left = max_out, level, res;
     u8* scratch;
+    o_min_offset_seen = 0xFFFFFFFFu;
     if (csize < 1) return 0;
     level = *ip++;
     if (level < 10 || level > 49) return -1;

@@ -18,6 +18,8 @@ int oracle_Lizard_compressBound(int isize);
  * Levels 10,11,30,31 (fastSmall/fast) and 21,22,41,42 (priceFast); other levels return 0. */
 int oracle_Lizard_compress(const char* src, char* dst, int srcSize, int maxDstSize, int level);
 int oracle_Lizard_decompress_safe(const char* src, char* dst, int compressedSize, int maxDecompressedSize);
+/* smallest match offset met by this thread's last oracle_Lizard_decompress_safe call (0xFFFFFFFF if none) */
+unsigned oracle_last_min_offset(void);
 
 /* Huff0 stage on its own (what Lizard_writeStream / Lizard_readStream call) */
 size_t oracle_HUF_compress(void* dst, size_t dstCapacity, const void* src, size_t srcSize);   /* 0, 1 or size; (size_t)-1 on error */

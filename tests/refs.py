@@ -36,3 +36,29 @@ def ref_decompress(L, comp: bytes, cap: int):
     dst = ctypes.create_string_buffer(max(cap, 1))
     r = L.Lizard_decompress_safe(comp, dst, len(comp), cap)
     return r, (dst.raw[:r] if r > 0 else b"")
+
+
+_ORACLE = None
+
+
+def oracle():
+    """Our plain-C restatement (oracle/liboracle.so); None if not built."""
+    global _ORACLE
+    p = os.path.join(ROOT, "oracle", "liboracle.so")
+    if _ORACLE is None and os.path.exists(p):
+        L = ctypes.CDLL(p)
+        L.oracle_Lizard_compress.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.oracle_Lizard_decompress_safe.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+        L.oracle_last_min_offset.restype = ctypes.c_uint
+        _ORACLE = L
+    return _ORACLE
+
+
+def stream_obeys_min_offset(comp: bytes, cap: int) -> bool:
+    """True when every match of a (successfully decoded) stream has offset >= 8, the rule all Lizard parsers
+    enforce (LIZARD_*_MIN_OFFSET).  Below that the reference's 8-byte granule copies make ITS output depend on
+    stale bytes beyond the write cursor, so byte parity is only defined for streams that obey the rule."""
+    L = oracle()
+    dst = ctypes.create_string_buffer(max(cap, 1) + 64)
+    r = L.oracle_Lizard_decompress_safe(comp, dst, len(comp), cap)
+    return r > 0 and L.oracle_last_min_offset() >= 8

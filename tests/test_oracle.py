@@ -40,6 +40,8 @@ def _shim():
     L.lzb_host_compress.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
     L.lzb_host_huf_decompress.argtypes = [ctypes.c_char_p, ctypes.c_uint, ctypes.c_char_p, ctypes.c_uint]
     L.lzb_emu_compress.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    for f in ("lzb_host_decompress", "lzb_emu_decompress"):
+        getattr(L, f).argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
     return L
 
 
@@ -232,6 +234,54 @@ def test_decompress_parity_valid_and_corrupt(ref, oracle):
             assert r == rr, (level, len(data), len(bad), cap)
             if rr > 0:
                 assert out == ro
+
+
+def _shim_decompress(L, fn, comp, cap):
+    dst = ctypes.create_string_buffer(max(cap, 1) + 64)
+    r = getattr(L, fn)(comp, len(comp), dst, cap)
+    return r, (dst.raw[:r] if r > 0 else b"")
+
+
+def _content_is_defined(ref, comp, cap):
+    # offsets < 8 (never produced by a Lizard encoder) make the reference's output depend on stale dst bytes
+    outs = []
+    for fill in (0x00, 0xA5):
+        dst = ctypes.create_string_buffer(bytes([fill]) * (cap + 64), cap + 64)
+        r = ref.Lizard_decompress_safe(comp, dst, len(comp), cap)
+        outs.append(dst.raw[:max(r, 0)])
+    return outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("fn,count", [("lzb_host_decompress", 90), ("lzb_emu_decompress", 14)])
+def test_device_decoder_code_on_host_matches_reference(ref, shim, fn, count):
+    """The batch token loops (1 lane, and 32 emulated lanes = what the GPU runs): same return codes as the
+    reference on valid and damaged streams, same bytes whenever the reference's own output is well defined."""
+    rnd = random.Random(21)
+    compared = 0
+    for data in _inputs(21, count):
+        level = rnd.choice([10, 21, 41, 30, 17, 24, 45])
+        comp = refs.ref_compress(ref, data, level)
+        cases = [(comp, len(data)), (comp, max(len(data) - 1, 0)), (comp, len(data) + 77)]
+        for _ in range(5):
+            bad = bytearray(comp)
+            if not bad:
+                break
+            mode = rnd.randrange(3)
+            if mode == 0:
+                bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+            elif mode == 1:
+                bad = bad[: rnd.randrange(0, len(bad) + 1)]
+            else:
+                bad[rnd.randrange(min(40, len(bad)))] = rnd.randrange(256)
+            cases.append((bytes(bad), rnd.choice([len(data), max(len(data) - 1, 0), len(data) + 100])))
+        for c, cap in cases:
+            rr, ro = refs.ref_decompress(ref, c, cap)
+            r, o = _shim_decompress(shim, fn, c, cap)
+            assert r == rr, (fn, level, len(data), len(c), cap)
+            if rr > 0 and refs.stream_obeys_min_offset(c, cap):
+                compared += 1
+                assert o == ro, (fn, level, len(data), cap)
+    assert compared > 0
 
 
 def test_huffman_stage_parity(ref, oracle, shim):
