@@ -79,7 +79,10 @@ enum : u32 { kDecStreamScratch = kBlockSize + 64, kDecBigTableBytes = 2u << kHuf
              kDecScratchPerWarp = 4 * kDecStreamScratch + kDecBigTableBytes };
 enum : u32 { kDecSmemTableLog = 11 };    // Lizard's encoder never exceeds 11 (HUF_TABLELOG_DEFAULT); 12 is legal input
 
+struct alignas(16) SeqDesc { u32 a, b, c, d; };   // 16-byte sequence descriptor (see run_batch_copies)
+
 struct DecWarpShared {             // per-warp shared memory
+    SeqDesc desc[64];              // literal-run and match descriptors of the current token batch
     u16 table[1u << kDecSmemTableLog];
     u16* big_table;                // 2^12-entry table in the warp's global scratch, used only for tableLog 12
     HufStatsScratch stats;
@@ -208,6 +211,29 @@ LZ_HD u32 read_ext(const u8* lits, u32 nlits, long& lp)
     return v;
 }
 
+// length-extension field at lits[p]: value v (b<254 | 254,LE16 | 255,LE24) and its size in bytes; false when the
+// stream does not hold the whole field (the serial path then reproduces the reference's behaviour)
+LZ_HD bool ext_field(const u8* lits, long nl, long p, u32* v, u32* size)
+{
+    if (p >= nl) return false;
+    const u32 b = lits[p];
+    if (b < 254) { *v = b; *size = 1; return true; }
+    const u32 sz = b == 254 ? 3u : 4u;
+    if (p + (long)sz > nl) return false;
+    *v = b == 254 ? rd_le16(lits + p + 1) : rd_le24(lits + p + 1);
+    *size = sz;
+    return true;
+}
+
+#if defined(LZB_STATS) && !defined(__CUDA_ARCH__)
+static unsigned long long g_tok_fast = 0, g_tok_slow = 0;
+#define LZB_COUNT_FAST(n) (g_tok_fast += (n))
+#define LZB_COUNT_SLOW(n) (g_tok_slow += (n))
+#else
+#define LZB_COUNT_FAST(n)
+#define LZB_COUNT_SLOW(n)
+#endif
+
 // cursor state of one token loop
 struct TokCursor { u32 fp; long lp; long op; u32 p16, p24; u32 last_off; };
 
@@ -292,87 +318,46 @@ template <class W> LZ_HD int lizv1_serial(const Streams& s, u8* dst, long oend, 
     return 0;
 }
 
-// ---- 4-bytes-per-lane copy pieces: one pass moves 4*lanes bytes ------------------------------------------
-LZ_HD u32 ld32u(const u8* p)      // unaligned little-endian load; may touch the aligned words around p only
-{
-#if defined(__CUDA_ARCH__)
-    const size_t a = (size_t)p;
-    const u32* q = (const u32*)(a & ~(size_t)3);
-    const u32 sh = (u32)(a & 3) * 8;
-    const u32 lo = q[0];
-    if (sh == 0) return lo;
-    return __funnelshift_r(lo, q[1], sh);
-#else
-    return rd_le32(p);
-#endif
-}
-// this lane's 4 bytes (index 4*lane) of a run of n bytes; bytes past n read as 0
-template <class W> LZ_HD u32 load_chunk4(const u8* src, u32 n)
-{
-    const u32 i = 4 * W::lane();
-    if (i + 4 <= n) return ld32u(src + i);
-    u32 v = 0;
-    for (u32 j = 0; j < 4; ++j) if (i + j < n) v |= (u32)src[i + j] << (8 * j);
-    return v;
-}
-template <class W> LZ_HD void store_chunk4(u8* dst, u32 v, u32 n)
-{
-    const u32 i = 4 * W::lane();
-    if (i >= n) return;
-    u8* d = dst + i;
-    if (i + 4 <= n && ((size_t)d & 3) == 0) { *(u32*)d = v; return; }
-    const u32 cnt = n - i < 4 ? n - i : 4;
-    for (u32 j = 0; j < cnt; ++j) d[j] = (u8)(v >> (8 * j));
-}
-// non-overlapping copy (src and dst ranges disjoint, or src entirely before dst with distance >= n)
-template <class W> LZ_HD void lanes_copy4(u8* dst, const u8* src, u32 n)
-{
-    const u32 step = 4 * W::lanes();
-    for (u32 base = 0; base < n; base += step) {
-        const u32 part = n - base < step ? n - base : step;
-        const u32 v = load_chunk4<W>(src + base, part);
-        store_chunk4<W>(dst + base, v, part);
-    }
-}
-
 // ---- batch execution shared by both flavours: copy the literal runs, then resolve the matches in order ----
+// Every lane publishes its sequence as two 16-byte descriptors in the warp's shared memory; the copy loops then
+// read them with uniform (broadcast) loads instead of three shuffles per sequence.
 template <class W> LZ_HD void run_batch_copies(u8* dst, const u8* lits, u32 nb, u32 lit_src, u32 lit_len,
-                                               u32 opos, u32 off, u32 ml)
+                                               u32 opos, u32 off, u32 ml, SeqDesc* desc)
 {
-    const u32 step = 4 * W::lanes();
-    // warm the cache for this lane's match source while the literal runs are being moved
-    if (W::lane() < nb && off != 0 && off <= opos + lit_len) W::prefetch(dst + (opos + lit_len - off));
-    // literal runs are independent of everything in this batch: two at a time, loads before stores
-    u32 k = 0;
-    for (; k + 1 < nb; k += 2) {
-        const u32 len0 = W::shfl(lit_len, k), sp0 = W::shfl(lit_src, k), dp0 = W::shfl(opos, k);
-        const u32 len1 = W::shfl(lit_len, k + 1), sp1 = W::shfl(lit_src, k + 1), dp1 = W::shfl(opos, k + 1);
-        const u32 p0 = len0 < step ? len0 : step, p1 = len1 < step ? len1 : step;
-        const u32 v0 = load_chunk4<W>(lits + sp0, p0);
-        const u32 v1 = load_chunk4<W>(lits + sp1, p1);
-        store_chunk4<W>(dst + dp0, v0, p0);
-        store_chunk4<W>(dst + dp1, v1, p1);
-        if (len0 > step) lanes_copy4<W>(dst + dp0 + step, lits + sp0 + step, len0 - step);
-        if (len1 > step) lanes_copy4<W>(dst + dp1 + step, lits + sp1 + step, len1 - step);
+    const u32 lane = W::lane(), L = W::lanes();
+    if (lane < nb) {
+        SeqDesc dl; dl.a = lit_src; dl.b = opos; dl.c = lit_len; dl.d = 0;
+        SeqDesc dm; dm.a = opos + lit_len; dm.b = off; dm.c = ml; dm.d = 0;
+        desc[lane] = dl; desc[32 + lane] = dm;
     }
-    if (k < nb) {
-        const u32 len0 = W::shfl(lit_len, k), sp0 = W::shfl(lit_src, k), dp0 = W::shfl(opos, k);
-        lanes_copy4<W>(dst + dp0, lits + sp0, len0);
+    // warm the cache for this lane's match source while the literal runs are being moved
+    if (lane < nb && off != 0 && off <= opos + lit_len) W::prefetch(dst + (opos + lit_len - off));
+    W::sync();
+    // literal runs are independent of everything in this batch
+    for (u32 k = 0; k < nb; ++k) {
+        const SeqDesc d = desc[k];
+        lanes_copy_rows<W>(dst + d.b, lits + d.a, d.c);
     }
     W::sync();
-    for (k = 0; k < nb; ++k) {
-        const u32 m = W::shfl(ml, k);
-        const u32 o = W::shfl(off, k);
-        const u32 dp = W::shfl(opos + lit_len, k);
-        if (o >= m) lanes_copy4<W>(dst + dp, dst + dp - o, m);      // source entirely before the destination
-        else lanes_match<W>(dst, (long)dp, o, m);
+    for (u32 k = 0; k < nb; ++k) {
+        const SeqDesc d = desc[32 + k];
+        const u32 m = d.c, o = d.b;
+        u8* const to = dst + d.a;
+        if (o >= m || o >= 4 * L) {
+            // source entirely before the destination of each pass: plain passes, ordered by a barrier
+            for (u32 base = 0; base < m; base += 4 * L) {
+                const u32 part = m - base < 4 * L ? m - base : 4 * L;
+                lanes_copy_rows<W>(to + base, to + base - o, part);
+                if (base + 4 * L < m) W::sync();
+            }
+        } else lanes_match<W>(dst, (long)d.a, o, m);
         W::sync();
     }
 }
 
 // fastLZ4 codewords (lib/lizard_decompress_lz4.h:7-163).  `op0` is the offset inside the unit's output,
 // `oend` the unit's capacity; matches may reach back to offset 0 of the unit.
-template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op0, u32 oend_u)
+template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op0, u32 oend_u, SeqDesc* desc)
 {
     const long nl = (long)s.nlits, oend = (long)oend_u;
     const u32 NL = W::lanes(), lane = W::lane();
@@ -389,24 +374,37 @@ template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op
         const u32 adv = act ? ((need ? 1 : litn) + 2 + (mln == 15 ? 1 : 0)) : 0;
         u32 tot_adv = 0;
         const u32 A = W::excl_scan(adv, &tot_adv);
-        // serial chain over the tokens whose literal length is in the stream
-        u32 pending = W::ballot(need), E = 0, myext = 0;
+        // Serial chain over the tokens that carry a length extension (literal length and/or match length): only
+        // these make a token's position in the literals stream data dependent.  E = bytes not yet counted in A.
+        const bool needm = act && mln == 15;
+        u32 pending = W::ballot(need || needm), E = 0;
+        const u32 needl_mask = W::ballot(need), needm_mask = W::ballot(needm);
+        u32 my_lit = 0, my_lx = 0, my_mlv = 0, my_mx = 0;          // literal length / its field size, ml-ext value / size
         bool slow = false;
         while (pending) {
             const u32 k = ctz32(pending); pending &= pending - 1;
-            const long pk = c.lp + (long)W::shfl(A, k) + (long)E;
-            if (pk > nl - 5) { slow = true; break; }
-            const u32 b = s.lits[pk];
-            if (b >= 254) { slow = true; break; }
-            if (lane == k) myext = 15 + b;
-            E += 15 + b;
+            const long base = c.lp + (long)W::shfl(A, k) + (long)E;     // first stream byte of token k
+            long pm;                                                     // where its match-length field would sit
+            if ((needl_mask >> k) & 1) {
+                u32 v, sz;
+                if (base > nl - 5 || !ext_field(s.lits, nl, base, &v, &sz)) { slow = true; break; }
+                if (lane == k) { my_lit = 15 + v; my_lx = sz; }
+                E += 15 + v + (sz - 1);
+                pm = base + sz + 15 + v + 2;
+            } else pm = base + (long)W::shfl(litn, k) + 2;
+            if ((needm_mask >> k) & 1) {
+                u32 v, sz;
+                if (pm > nl - 5 || !ext_field(s.lits, nl, pm, &v, &sz)) { slow = true; break; }
+                if (lane == k) { my_mlv = v; my_mx = sz; }
+                E += sz - 1;
+            }
         }
         if (!slow) {
             u32 tot_ext = 0;
-            const u32 Eex = W::excl_scan(myext, &tot_ext);
+            const u32 Eex = W::excl_scan((need ? my_lit + (my_lx - 1) : 0u) + (needm ? my_mx - 1 : 0u), &tot_ext);
             const long tokpos = c.lp + (long)A + (long)Eex;
-            const u32 lit_len = need ? myext : (act ? litn : 0);
-            const long lit_src = tokpos + (need ? 1 : 0);
+            const u32 lit_len = need ? my_lit : (act ? litn : 0);
+            const long lit_src = tokpos + (need ? (long)my_lx : 0);
             const long off_pos = lit_src + lit_len;
             bool bad = false;
             u32 ml = 0, off = 0;
@@ -414,12 +412,7 @@ template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op
                 if (lit_src + (long)lit_len > nl - 18) bad = true;
                 else {
                     off = rd_le16(s.lits + off_pos);
-                    ml = mln;
-                    if (mln == 15) {
-                        if (off_pos + 2 > nl - 5) bad = true;
-                        else { const u32 b2 = s.lits[off_pos + 2]; if (b2 >= 254) bad = true; else ml = 15 + b2; }
-                    }
-                    ml += kMinMatch;
+                    ml = (needm ? 15 + my_mlv : mln) + kMinMatch;
                 }
             }
             u32 tot_out = 0;
@@ -431,11 +424,13 @@ template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op
                 else if (opos + (long)lit_len + (long)ml > oend - 16) bad = true;
             }
             if (W::ballot(bad) == 0) {
-                run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml);
+                LZB_COUNT_FAST(W::lane() == 0 ? nb : 0);
+                run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, desc);
                 c.fp += nb; c.lp += (long)tot_adv + (long)tot_ext; c.op += (long)tot_out;
                 continue;
             }
         }
+        LZB_COUNT_SLOW(W::lane() == 0 ? nb : 0);
         const int e = lz4_serial<W>(s, dst, oend, c, nb);
         if (e < 0) return e;
     }
@@ -448,7 +443,7 @@ template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op
 }
 
 // LIZv1 codewords (lib/lizard_decompress_liz.h:14-220)
-template <class W> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 op0, u32 oend_u)
+template <class W> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 op0, u32 oend_u, SeqDesc* desc)
 {
     const long nl = (long)s.nlits, oend = (long)oend_u;
     const u32 NL = W::lanes(), lane = W::lane();
@@ -470,24 +465,34 @@ template <class W> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 
         const u32 A = W::excl_scan(adv, &tot_adv);
         const u32 P16 = W::excl_scan(new16 ? 2u : 0u, &tot16);
         const u32 P24 = W::excl_scan((act && !shortf) ? 3u : 0u, &tot24);
-        u32 pending = W::ballot(need), E = 0, myext = 0;
+        u32 pending = W::ballot(need || mlext), E = 0;
+        const u32 needl_mask = W::ballot(need), needm_mask = W::ballot(mlext);
+        u32 my_lit = 0, my_lx = 0, my_mlv = 0, my_mx = 0;
         bool slow = false;
         while (pending) {
             const u32 k = ctz32(pending); pending &= pending - 1;
-            const long pk = c.lp + (long)W::shfl(A, k) + (long)E;
-            if (pk > nl - 1) { slow = true; break; }
-            const u32 b = s.lits[pk];
-            if (b >= 254) { slow = true; break; }
-            if (lane == k) myext = 7 + b;
-            E += 7 + b;
+            const long base = c.lp + (long)W::shfl(A, k) + (long)E;
+            long pm;
+            if ((needl_mask >> k) & 1) {
+                u32 v, sz;
+                if (base > nl - 1 || !ext_field(s.lits, nl, base, &v, &sz)) { slow = true; break; }
+                if (lane == k) { my_lit = 7 + v; my_lx = sz; }
+                E += 7 + v + (sz - 1);
+                pm = base + sz + 7 + v;
+            } else pm = base + (long)W::shfl(litn, k);
+            if ((needm_mask >> k) & 1) {
+                u32 v, sz;
+                if (pm > nl - 1 || !ext_field(s.lits, nl, pm, &v, &sz)) { slow = true; break; }
+                if (lane == k) { my_mlv = v; my_mx = sz; }
+                E += sz - 1;
+            }
         }
         if (!slow) {
             u32 tot_ext = 0;
-            const u32 Eex = W::excl_scan(myext, &tot_ext);
+            const u32 Eex = W::excl_scan((need ? my_lit + (my_lx - 1) : 0u) + (mlext ? my_mx - 1 : 0u), &tot_ext);
             const long tokpos = c.lp + (long)A + (long)Eex;
-            const u32 lit_len = need ? myext : (act ? litn : 0);
-            const long lit_src = tokpos + (need ? 1 : 0);
-            const long ext_pos = lit_src + lit_len;                 // where a match-length extension byte would sit
+            const u32 lit_len = need ? my_lit : (act ? litn : 0);
+            const long lit_src = tokpos + (need ? (long)my_lx : 0);
             bool bad = false;
             u32 ml = 0, off = 0;
             if (act) {
@@ -496,21 +501,12 @@ template <class W> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 
                     else if (c.p16 + P16 + (new16 ? 2u : 0u) > s.noff16) bad = true;
                     else {
                         if (new16) off = rd_le16(s.off16 + c.p16 + P16);
-                        ml = mln;
-                        if (mln == 15) {
-                            if (ext_pos > nl - 1) bad = true;
-                            else { const u32 b2 = s.lits[ext_pos]; if (b2 >= 254) bad = true; else ml = 15 + b2; }
-                        }
+                        ml = mlext ? 15 + my_mlv : mln;
                     }
                 } else {
-                    if (tok == kLastLongOff) {
-                        if (ext_pos > nl - 1) bad = true;
-                        else { const u32 b2 = s.lits[ext_pos]; if (b2 >= 254) bad = true; else ml = b2 + kLastLongOff + kMmLongOff; }
-                    } else ml = tok + kMmLongOff;
-                    if (!bad) {
-                        if ((long)(c.p24 + P24) > (long)s.noff24 - 3) bad = true;
-                        else off = rd_le24(s.off24 + c.p24 + P24);
-                    }
+                    ml = (tok == kLastLongOff) ? my_mlv + kLastLongOff + kMmLongOff : tok + kMmLongOff;
+                    if ((long)(c.p24 + P24) > (long)s.noff24 - 3) bad = true;
+                    else off = rd_le24(s.off24 + c.p24 + P24);
                 }
             }
             // repeat-offset tokens take the offset of the closest earlier token that carried one
@@ -529,13 +525,15 @@ template <class W> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 
                 else if (opos + (long)lit_len + (long)ml > oend - 16) bad = true;
             }
             if (W::ballot(bad) == 0) {
-                run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml);
+                LZB_COUNT_FAST(W::lane() == 0 ? nb : 0);
+                run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, desc);
                 c.fp += nb; c.lp += (long)tot_adv + (long)tot_ext; c.op += (long)tot_out;
                 c.p16 += tot16; c.p24 += tot24;
                 c.last_off = W::shfl(off, nb - 1);
                 continue;
             }
         }
+        LZB_COUNT_SLOW(W::lane() == 0 ? nb : 0);
         const int e = lizv1_serial<W>(s, dst, oend, c, nb);
         if (e < 0) return e;
     }
@@ -605,7 +603,7 @@ template <class W> LZ_HD int decode_unit(const u8* src, u32 csize_u, u8* dst, u3
         if (!read_stream<W>(hdr & kFlagFlags, src, csize, ip, scratch + 1 * kDecStreamScratch, &s.flags, &s.nflags, sh)) return -1;
         if (!read_stream<W>(hdr & kFlagLiterals, src, csize, ip, scratch, &s.lits, &s.nlits, sh)) return -1;
         if (ip > csize) return -1;
-        const int res = lizv1 ? decode_tokens_lizv1<W>(s, dst, (u32)op, cap) : decode_tokens_lz4<W>(s, dst, (u32)op, cap);
+        const int res = lizv1 ? decode_tokens_lizv1<W>(s, dst, (u32)op, cap, sh->desc) : decode_tokens_lz4<W>(s, dst, (u32)op, cap, sh->desc);
         if (res <= 0) return res;
         op += res;
     }

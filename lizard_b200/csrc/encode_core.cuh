@@ -72,153 +72,195 @@ LZ_HD u32 count_match(const u8* a, const u8* b, const u8* limit)
     return (u32)(a - a0);
 }
 
-// ---- the five output streams of one inner block -------------------------------------------------------
+// ---- sequence list of one inner block ---------------------------------------------------------------------
+// The parsers do not write the token streams while they run: they append one record per sequence and keep
+// exact byte counts of the four streams (the codeword rules below are pure functions of lit/ml/off).  When
+// the block is parsed, write_block() knows every size, takes the reference's raw / does-not-fit decisions
+// without moving a byte, and emit_streams() materialises all sequences lane-parallel, straight into their
+// final place in dst whenever no entropy stage follows.  This keeps the literal copies (the biggest stall
+// source in the first version) off the serial search->extend->record chain.
+struct SeqRec { u32 anchor, lit, ml, off; };       // off == 0: repeat last offset (LIZv1 only)
+
 struct EncStreams {
-    u8* lits;  u8* flags;  u8* off16;  u8* off24;
-    u32 nl, nf, n16, n24;
+    SeqRec* rec;  u32 nseq;
+    u32 nl, nf, n16, n24;                          // exact sizes of literals / flags / off16 / off24 streams
+    u32 tail_anchor, tail_len;                     // last literals
 };
 
 // length extension: b<254 | 254,LE16 | 255,LE24
-LZ_HD void put_ext(u8* lits, u32& nl, u32 v, bool writer)
+LZ_HD u32 ext_bytes(u32 v) { return v >= (1u << 16) ? 4u : (v >= 254 ? 3u : 1u); }
+LZ_HD void put_ext_at(u8* p, u32 v)
 {
-    if (v >= (1u << 16)) { if (writer) { lits[nl] = 255; wr_le24(lits + nl + 1, v); } nl += 4; }
-    else if (v >= 254)   { if (writer) { lits[nl] = 254; wr_le16(lits + nl + 1, v); } nl += 3; }
-    else                 { if (writer) lits[nl] = (u8)v; nl += 1; }
+    if (v >= (1u << 16)) { p[0] = 255; wr_le24(p + 1, v); }
+    else if (v >= 254)   { p[0] = 254; wr_le16(p + 1, v); }
+    else                 p[0] = (u8)v;
 }
 
-// Lizard_encodeSequence_LZ4: literals src[anchor..ip) then a match of `ml` bytes at distance `off`
-template <class W> LZ_HD void emit_lz4(EncStreams& s, const u8* src, u32 anchor, u32 ip, u32 ml, u32 off)
+// Lizard_encodeSequence_LZ4 (lib/lizard_compress_lz4.h:3-71): literals src[anchor..ip) + match(ml, off)
+template <class W> LZ_HD void emit_lz4(EncStreams& s, const u8*, u32 anchor, u32 ip, u32 ml, u32 off)
 {
-    const bool wr = W::lane() == 0;
-    const u32 lit = ip - anchor;
-    u32 tok;
-    if (lit >= 15) { tok = 15; put_ext(s.lits, s.nl, lit - 15, wr); } else tok = lit;
-    lanes_copy<W>(s.lits + s.nl, src + anchor, lit);
-    s.nl += lit;
-    if (wr) wr_le16(s.lits + s.nl, off);
-    s.nl += 2;
-    const u32 m = ml - kMinMatch;
-    if (m >= 15) { tok += 15u << 4; put_ext(s.lits, s.nl, m - 15, wr); } else tok += m << 4;
-    if (wr) s.flags[s.nf] = (u8)tok;
-    s.nf++;
+    const u32 lit = ip - anchor, m = ml - kMinMatch;
+    s.nl += (lit >= 15 ? ext_bytes(lit - 15) : 0) + lit + 2 + (m >= 15 ? ext_bytes(m - 15) : 0);
+    s.nf += 1;
+    if (W::lane() == 0) { SeqRec r; r.anchor = anchor; r.lit = lit; r.ml = ml; r.off = off; s.rec[s.nseq] = r; }
+    s.nseq++;
 }
 
-// Lizard_encodeSequence_LIZv1.  off == 0 means "repeat last offset".  Updates last_off.
-template <class W> LZ_HD void emit_lizv1(EncStreams& s, const u8* src, u32 anchor, u32 ip, u32 ml, u32 off, u32& last_off)
+// Lizard_encodeSequence_LIZv1 (lib/lizard_compress_liz.h:43-165).  off == 0 means "repeat last offset".
+template <class W> LZ_HD void emit_lizv1(EncStreams& s, const u8*, u32 anchor, u32 ip, u32 ml, u32 off, u32& last_off)
 {
-    const bool wr = W::lane() == 0;
     const u32 lit = ip - anchor;
-    u32 tok = 0;
-    if (lit > 0 || off < kMax16BitOffset) {
-        if (lit >= 7) { tok = 7; put_ext(s.lits, s.nl, lit - 7, wr); } else tok = lit;
-        lanes_copy<W>(s.lits + s.nl, src + anchor, lit);
-        s.nl += lit;
-        if (off >= kMax16BitOffset) {          // literals before a 24-bit-offset match ride on a zero-length repeat token
-            tok += 1u << 7;
-            if (wr) s.flags[s.nf] = (u8)tok;
-            s.nf++;
-            tok = 0;
-        }
+    const bool far = off >= kMax16BitOffset;
+    if (lit > 0 || !far) {
+        s.nl += (lit >= 7 ? ext_bytes(lit - 7) : 0) + lit;
+        if (far) s.nf += 1;                                   // carrier token for the literals
     }
-    if (off >= kMax16BitOffset) {
-        if (ml - kMmLongOff >= kLastLongOff) { tok = kLastLongOff; put_ext(s.lits, s.nl, ml - kMmLongOff - kLastLongOff, wr); }
-        else tok = ml - kMmLongOff;
-        if (wr) wr_le24(s.off24 + s.n24, off);
+    if (far) {
+        if (ml - kMmLongOff >= kLastLongOff) s.nl += ext_bytes(ml - kMmLongOff - kLastLongOff);
         s.n24 += 3;
         last_off = off;
     } else {
-        if (off == 0) tok += 1u << 7;
-        else { last_off = off; if (wr) wr_le16(s.off16 + s.n16, off); s.n16 += 2; }
-        if (ml >= 15) { tok += 15u << 3; put_ext(s.lits, s.nl, ml - 15, wr); } else tok += ml << 3;
+        if (off != 0) { last_off = off; s.n16 += 2; }
+        if (ml >= 15) s.nl += ext_bytes(ml - 15);
     }
-    if (wr) s.flags[s.nf] = (u8)tok;
-    s.nf++;
+    s.nf += 1;
+    if (W::lane() == 0) { SeqRec r; r.anchor = anchor; r.lit = lit; r.ml = ml; r.off = off; s.rec[s.nseq] = r; }
+    s.nseq++;
 }
 
-template <class W> LZ_HD void emit_last_literals(EncStreams& s, const u8* src, u32 anchor, u32 end)
+template <class W> LZ_HD void emit_last_literals(EncStreams& s, const u8*, u32 anchor, u32 end)
 {
-    lanes_copy<W>(s.lits + s.nl, src + anchor, end - anchor);
+    s.tail_anchor = anchor; s.tail_len = end - anchor;
     s.nl += end - anchor;
 }
+
+// Materialise the recorded sequences: lane i of each batch owns sequence base+i, prefix sums give its place
+// in every stream, it writes its own token / extension / offset bytes, and the warp copies the batch's
+// literal runs (two runs in flight).  Byte layout per sequence: see the two emitters cited above.
+template <class W> LZ_HD void emit_streams(const EncStreams& s, const u8* src, bool lizv1, u8* dl, u8* df, u8* d16, u8* d24)
+{
+    const u32 NL = W::lanes(), lane = W::lane();
+    u32 pl = 0, pf = 0, p16 = 0, p24 = 0;
+    W::sync();                                                  // records were written by lane 0
+    for (u32 base = 0; base < s.nseq; base += NL) {
+        const u32 nb = s.nseq - base < NL ? s.nseq - base : NL;
+        const bool act = lane < nb;
+        SeqRec r; r.anchor = 0; r.lit = 0; r.ml = 0; r.off = 0;
+        if (act) r = s.rec[base + lane];
+        u32 e1 = 0, e2 = 0, lbytes = 0, fbytes = 0, b16 = 0, b24 = 0, t0 = 0, t1 = 0;
+        bool first = false, far = false;
+        if (act) {
+            if (!lizv1) {
+                const u32 m = r.ml - kMinMatch;
+                e1 = r.lit >= 15 ? ext_bytes(r.lit - 15) : 0;
+                e2 = m >= 15 ? ext_bytes(m - 15) : 0;
+                lbytes = e1 + r.lit + 2 + e2; fbytes = 1;
+                t0 = (r.lit >= 15 ? 15u : r.lit) | ((m >= 15 ? 15u : m) << 4);
+            } else {
+                far = r.off >= kMax16BitOffset;
+                first = r.lit > 0 || !far;
+                if (first) { e1 = r.lit >= 7 ? ext_bytes(r.lit - 7) : 0; t0 = r.lit >= 7 ? 7u : r.lit; }
+                if (far) {
+                    const u32 m = r.ml - kMmLongOff;
+                    e2 = m >= kLastLongOff ? ext_bytes(m - kLastLongOff) : 0;
+                    t1 = m >= kLastLongOff ? (u32)kLastLongOff : m;
+                    b24 = 3; fbytes = first ? 2 : 1;
+                    if (first) t0 += 1u << 7;
+                } else {
+                    e2 = r.ml >= 15 ? ext_bytes(r.ml - 15) : 0;
+                    t0 += (r.off == 0 ? (1u << 7) : 0u) + ((r.ml >= 15 ? 15u : r.ml) << 3);
+                    b16 = r.off != 0 ? 2 : 0; fbytes = 1;
+                }
+                lbytes = (first ? e1 + r.lit : 0) + e2;
+            }
+        }
+        u32 tl = 0, tf = 0, t16 = 0, t24 = 0;
+        const u32 Pl = pl + W::excl_scan(lbytes, &tl);
+        const u32 Pf = pf + W::excl_scan(fbytes, &tf);
+        const u32 P16 = p16 + W::excl_scan(b16, &t16);
+        const u32 P24 = p24 + W::excl_scan(b24, &t24);
+        const u32 lit_dst = Pl + e1;
+        if (act) {
+            if (!lizv1) {
+                df[Pf] = (u8)t0;
+                if (e1) put_ext_at(dl + Pl, r.lit - 15);
+                wr_le16(dl + lit_dst + r.lit, r.off);
+                if (e2) put_ext_at(dl + lit_dst + r.lit + 2, r.ml - kMinMatch - 15);
+            } else {
+                if (first && e1) put_ext_at(dl + Pl, r.lit - 7);
+                const u32 ext_at = first ? lit_dst + r.lit : Pl;
+                if (far) {
+                    if (first) { df[Pf] = (u8)t0; df[Pf + 1] = (u8)t1; } else df[Pf] = (u8)t1;
+                    if (e2) put_ext_at(dl + ext_at, r.ml - kMmLongOff - kLastLongOff);
+                    wr_le24(d24 + P24, r.off);
+                } else {
+                    df[Pf] = (u8)t0;
+                    if (e2) put_ext_at(dl + ext_at, r.ml - 15);
+                    if (b16) wr_le16(d16 + P16, r.off);
+                }
+            }
+        }
+        // literal runs of the batch
+        const u32 cp_len = (act && (!lizv1 || first)) ? r.lit : 0;
+        for (u32 k = 0; k < nb; ++k) {
+            const u32 len0 = W::shfl(cp_len, k), a0 = W::shfl(r.anchor, k), d0 = W::shfl(lit_dst, k);
+            lanes_copy_rows<W>(dl + d0, src + a0, len0);
+        }
+        pl += tl; pf += tf; p16 += t16; p24 += t24;
+    }
+    lanes_copy_rows<W>(dl + pl, src + s.tail_anchor, s.tail_len);
+    W::sync();
+}
+
+// ---- hash table ------------------------------------------------------------------------------------------------
+// The reference keeps 32-bit absolute indices (position + 2^24, 0 = never written).  For units of at most one
+// inner block (<= 128 KiB, i.e. every independent frame block) a position needs 17 bits, so the shared-memory
+// form packs an entry as 16 low bits + 1 bit in a bitmap (all ones = empty): 8.5 KiB instead of 16 KiB at
+// level 10, 34 KiB instead of 64 KiB at levels 21/41 -- the table size is what bounds resident warps per SM.
+// Larger units (several dependent inner blocks) use plain 32-bit entries in global memory.
+struct HashTable {
+    u32* t32;            // plain form (global memory), or null
+    u16* lo;             // packed form
+    u32* hi;
+    LZ_HDM u32 get(u32 h) const
+    {
+        if (t32) return t32[h];
+        const u32 p = (u32)lo[h] | (((hi[h >> 5] >> (h & 31)) & 1u) << 16);
+        return p == 0x1FFFFu ? 0u : p + kDictSize;
+    }
+    LZ_HDM void set(u32 h, u32 abs_index) const
+    {
+        if (t32) { t32[h] = abs_index; return; }
+        const u32 p = abs_index - kDictSize;
+        lo[h] = (u16)p;
+        const u32 bit = 1u << (h & 31);
+#if defined(__CUDA_ARCH__)
+        if (p >> 16) atomicOr(&hi[h >> 5], bit); else atomicAnd(&hi[h >> 5], ~bit);
+#else
+        if (p >> 16) hi[h >> 5] |= bit; else hi[h >> 5] &= ~bit;
+#endif
+    }
+};
+template <class W> LZ_HD void hash_clear(const HashTable& T, u32 hash_log)
+{
+    const u32 n = 1u << hash_log;
+    if (T.t32) { for (u32 i = W::lane(); i < n; i += W::lanes()) T.t32[i] = 0; }
+    else {
+        u32* lo32 = reinterpret_cast<u32*>(T.lo);
+        for (u32 i = W::lane(); i < n / 2; i += W::lanes()) lo32[i] = 0xFFFFFFFFu;
+        for (u32 i = W::lane(); i < n / 32; i += W::lanes()) T.hi[i] = 0xFFFFFFFFu;
+    }
+    W::sync();
+}
+LZ_HD size_t hash_packed_bytes(u32 hash_log) { return ((size_t)2 << hash_log) + ((size_t)4 << hash_log) / 32; }
 
 // ---- parser state shared by the inner blocks of one unit -----------------------------------------------
 struct ParseCtx {
     const u8* src;        // unit start (position 0); table entries are position + kDictSize, 0 = empty
-    u32*      table;
+    HashTable T;
     u32       hash_log;
     u32       window_log;
 };
-
-// Lizard_compress_fastSmall / Lizard_compress_fast on src[b0..b1)
-template <class W> LZ_HD void parse_fast(const ParseCtx& c, u32 b0, u32 b1, EncStreams& s)
-{
-    const u8* const src = c.src;
-    u32* const table = c.table;
-    const u32 hl = c.hash_log;
-    const bool wr = W::lane() == 0;
-    const u32 max_dist = (1u << c.window_log) - 1;
-    const u32 bias = kDictSize;
-    const u32 low_limit = (bias + max_dist >= b0 + bias) ? bias : b0 + bias - max_dist;
-    u32 anchor = b0, ip = b0;
-    u32 ml = 0, mpos = 0;
-    if (b1 - b0 < kMinInputForLz) goto last_literals;
-    {
-        const u32 mflimit = b1 - kMfLimit;
-        const u8* const matchlimit = src + b1 - kLastLiterals;
-        if (wr) table[hash5(ld64(src + ip), hl)] = ip + bias;
-        W::sync();
-        ip++;
-        for (;;) {
-            {   // search forward with growing stride
-                u32 fwd = ip, step = 1, tries = 1u << kSkipTrigger;
-                for (;;) {
-                    ip = fwd;
-                    fwd += step;
-                    step = tries++ >> kSkipTrigger;
-                    if (fwd > mflimit) goto last_literals;
-                    const u32 h = hash5(ld64(src + ip), hl);
-                    const u32 cand = table[h];
-                    W::sync();
-                    if (wr) table[h] = ip + bias;
-                    W::sync();
-                    const u32 cur = ip + bias;
-                    if (cand < low_limit || cand >= cur || cand + max_dist < cur) continue;
-                    if (cur - cand < kMinOffset) continue;
-                    mpos = cand - bias;
-                    if (ld32(src + mpos) != ld32(src + ip)) continue;
-                    ml = count_match(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
-                    while (ip > anchor && mpos > 0 && src[ip - 1] == src[mpos - 1]) { ip--; mpos--; ml++; }
-                    break;
-                }
-            }
-            for (;;) {   // _next_match
-                emit_lz4<W>(s, src, anchor, ip, ml + kMinMatch, ip - mpos);
-                ip += ml + kMinMatch;
-                anchor = ip;
-                if (ip > mflimit) goto last_literals;
-                if (wr) table[hash5(ld64(src + ip - 2), hl)] = ip - 2 + bias;
-                W::sync();
-                const u32 h = hash5(ld64(src + ip), hl);
-                const u32 cand = table[h];
-                W::sync();
-                if (wr) table[h] = ip + bias;
-                W::sync();
-                const u32 cur = ip + bias;
-                if (cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset) {
-                    mpos = cand - bias;
-                    if (ld32(src + mpos) == ld32(src + ip)) {
-                        ml = count_match(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
-                        continue;
-                    }
-                }
-                break;
-            }
-            ip++;
-        }
-    }
-last_literals:
-    emit_last_literals<W>(s, src, anchor, b1);
-}
 
 // ---- lane-parallel building blocks ---------------------------------------------------------------------
 // Position of the j-th probe of one fastSmall search relative to its first probe: the stride grows by one
@@ -283,7 +325,7 @@ template <class W> LZ_HD u32 extend_back_par(const u8* src, u32 ip, u32 mpos, u3
 template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, EncStreams& s)
 {
     const u8* const src = c.src;
-    u32* const table = c.table;
+    const HashTable T = c.T;
     const u32 hl = c.hash_log;
     const u32 lane = W::lane(), NL = W::lanes();
     const bool wr = lane == 0;
@@ -296,26 +338,33 @@ template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, 
     {
         const u32 mflimit = b1 - kMfLimit;
         const u8* const matchlimit = src + b1 - kLastLiterals;
-        if (wr) table[hash5(ld64(src + ip), hl)] = ip + bias;
+        if (wr) T.set(hash5(ld64(src + ip), hl), ip + bias);
         W::sync();
         ip++;
         for (;;) {
             {   // ---- search: batches of NL probes ----
                 const u32 ip0 = ip;
                 u32 j0 = 0;
+                u64 v_ahead = 0; bool have_ahead = false;                      // next batch's bytes, requested one batch early
                 for (;;) {
                     const u32 j = j0 + lane;
                     const u32 P = ip0 + probe_offset(j);
                     const bool valid = ip0 + probe_offset(j + 1) <= mflimit;   // else this probe ends the block
                     u64 v = 0; u32 h = 0x80000000u | lane;                     // unique key: matches nobody
-                    if (valid) { v = ld64(src + P); h = hash5(v, hl); }
+                    if (valid) { v = have_ahead ? v_ahead : ld64(src + P); h = hash5(v, hl); }
+                    {   // the probe positions of the next batch are known already: start their loads now so that the
+                        // memory latency overlaps this batch's bucket / candidate work (wasted only when a match ends the search)
+                        const u32 jn = j + NL;
+                        have_ahead = ip0 + probe_offset(jn + 1) <= mflimit;
+                        v_ahead = have_ahead ? ld64(src + ip0 + probe_offset(jn)) : 0;
+                    }
                     const u32 peers = W::match_any(h);
                     const u32 below = peers & ((1u << lane) - 1);
                     const u32 pl = below ? highbit32(below) : lane;
                     const u32 prevP = W::shfl(P, pl);
                     const u32 cur = P + bias;
                     u32 cand = 0;
-                    if (valid) cand = below ? prevP + bias : table[h];
+                    if (valid) cand = below ? prevP + bias : T.get(h);
                     bool hit = false;
                     if (valid && cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset)
                         hit = ld32(src + (cand - bias)) == (u32)v;
@@ -331,7 +380,7 @@ template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, 
                     W::sync();
                     if ((commit >> lane) & 1) {
                         const u32 grp = peers & commit;
-                        if (highbit32(grp) == lane) table[h] = cur;
+                        if (highbit32(grp) == lane) T.set(h, cur);
                     }
                     W::sync();
                     if (matched) { ip = W::shfl(P, w_lane); mpos = W::shfl(cand, w_lane) - bias; break; }
@@ -347,13 +396,13 @@ template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, 
                 ip += ml + kMinMatch;
                 anchor = ip;
                 if (ip > mflimit) goto last_literals;
-                if (wr) table[hash5(ld64(src + ip - 2), hl)] = ip - 2 + bias;
+                if (wr) T.set(hash5(ld64(src + ip - 2), hl), ip - 2 + bias);
                 W::sync();
                 const u64 v = ld64(src + ip);
                 const u32 h = hash5(v, hl);
-                const u32 cand = table[h];
+                const u32 cand = T.get(h);
                 W::sync();
-                if (wr) table[h] = ip + bias;
+                if (wr) T.set(h, ip + bias);
                 W::sync();
                 const u32 cur = ip + bias;
                 if (cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset) {
@@ -372,109 +421,6 @@ last_literals:
     emit_last_literals<W>(s, src, anchor, b1);
 }
 
-// conditional table update of the priceFast family (lizard_parser_pricefast.h:170-171)
-LZ_HD void pf_update(u32* slot, u32 cur, bool wr)
-{
-    const u32 old = *slot;
-    if (old >= cur || cur >= old + kMinOffset) { if (wr) *slot = cur; }
-}
-
-// Lizard_compress_priceFast on src[b0..b1)
-template <class W> LZ_HD void parse_price_fast(const ParseCtx& c, u32 b0, u32 b1, EncStreams& s, u32 min_match_long)
-{
-    const u8* const src = c.src;
-    u32* const table = c.table;
-    const u32 hl = c.hash_log;
-    const bool wr = W::lane() == 0;
-    const u32 bias = kDictSize;
-    const u32 max_dist = (1u << c.window_log) - 1;
-    u32 anchor = b0, ip = b0 + 1;
-    u32 last_off = 0;
-    if (b1 - b0 >= kMfLimit) {     // iend - MFLIMIT must not wrap
-    const u32 mflimit = b1 - kMfLimit;
-    const u8* const matchlimit = src + b1 - kLastLiterals;
-    while (ip < mflimit) {
-        u32 ml = 0, ref = 0;
-        {   // Lizard_FindMatchFast
-            const u32 cur = ip + bias;
-            const u32 low = (bias + max_dist >= cur) ? bias : cur - max_dist;
-            u32* slot = &table[hash5(ld64(src + ip), hl)];
-            const u32 cand = *slot;
-            bool found = false;
-            if (last_off >= kMinOffset && cur - last_off >= low && last_off <= ip) {
-                const u32 m = ip - last_off;
-                if (ld32(src + m) == ld32(src + ip)) {
-                    ml = count_match(src + ip + kMinMatch, src + m + kMinMatch, matchlimit) + kMinMatch;
-                    ref = m; found = true;
-                }
-            }
-            if (!found && cand < cur && cand >= low) {
-                const u32 m = cand - bias;
-                if (ip - m >= kMinOffset && ld32(src + m) == ld32(src + ip)) {
-                    const u32 mlt = count_match(src + ip + kMinMatch, src + m + kMinMatch, matchlimit) + kMinMatch;
-                    if (mlt >= min_match_long || ip - m < kMax16BitOffset) { ml = mlt; ref = m; }
-                }
-            }
-            W::sync();
-            pf_update(slot, cur, wr);
-            W::sync();
-        }
-        if (!ml) { ip++; continue; }
-
-        u32 ml2 = 0, start2 = 0, ref2 = 0;
-        bool encode_now = false;
-        if (ip - ref == last_off) { ref = ip; encode_now = true; }   // repeat offset: encoded as distance 0
-        else { while (ip > anchor && ref > 0 && src[ip - 1] == src[ref - 1]) { ip--; ref--; ml++; } }
-
-        for (;;) {
-            if (!encode_now) {     // _Search: look ahead at the tail of the current match
-                while (true) {
-                    if (ip + ml >= mflimit) break;
-                    start2 = ip + ml - 2;
-                    {   // Lizard_FindMatchFaster
-                        const u32 cur2 = start2 + bias;
-                        const u32 low2 = (bias + max_dist >= cur2) ? bias : cur2 - max_dist;
-                        u32* slot2 = &table[hash5(ld64(src + start2), hl)];
-                        const u32 cand2 = *slot2;
-                        ml2 = 0;
-                        if (cand2 < cur2 && cand2 >= low2) {
-                            const u32 m = cand2 - bias;
-                            if (start2 - m >= kMinOffset && ld32(src + m) == ld32(src + start2)) {
-                                const u32 mlt = count_match(src + start2 + kMinMatch, src + m + kMinMatch, matchlimit) + kMinMatch;
-                                if (mlt >= min_match_long || start2 - m < kMax16BitOffset) { ml2 = mlt; ref2 = m; }
-                            }
-                        }
-                        W::sync();
-                        pf_update(slot2, cur2, wr);
-                        W::sync();
-                    }
-                    if (!ml2) break;
-                    while (start2 > ip && ref2 > 0 && src[start2 - 1] == src[ref2 - 1]) { start2--; ref2--; ml2++; }
-                    if (ml2 <= ml) { ml2 = 0; break; }
-                    if (start2 <= ip) { ip = start2; ref = ref2; ml = ml2; ml2 = 0; break; }
-                    if (start2 - ip < 3) { ip = start2; ref = ref2; ml = ml2; ml2 = 0; continue; }
-                    if (start2 < ip + ml) {
-                        const u32 corr = ml - (start2 - ip);
-                        start2 += corr; ref2 += corr; ml2 -= corr;
-                        if (ml2 < 3) ml2 = 0;
-                        if (ml2 < min_match_long && start2 - ref2 >= kMax16BitOffset) ml2 = 0;
-                    }
-                    break;
-                }
-            }
-            // _Encode
-            emit_lizv1<W>(s, src, anchor, ip, ml, ip - ref, last_off);
-            ip += ml;
-            anchor = ip;
-            if (!ml2) break;
-            ip = start2; ref = ref2; ml = ml2; ml2 = 0;
-            encode_now = false;
-        }
-    }
-    }
-    emit_last_literals<W>(s, src, anchor, b1);
-}
-
 // Lizard_compress_priceFast with the no-match run probed W::lanes() consecutive positions at a time.
 // Per position the reference (lizard_parser_pricefast.h:158-173) tests the repeat offset first, then the
 // bucket's candidate, then conditionally refreshes the bucket.  last_off is constant during a no-match run,
@@ -484,7 +430,7 @@ template <class W> LZ_HD void parse_price_fast(const ParseCtx& c, u32 b0, u32 b1
 template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u32 b1, EncStreams& s, u32 min_match_long)
 {
     const u8* const src = c.src;
-    u32* const table = c.table;
+    const HashTable T = c.T;
     const u32 hl = c.hash_log;
     const u32 lane = W::lane(), NL = W::lanes();
     const bool wr = lane == 0;
@@ -492,6 +438,7 @@ template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u3
     const u32 max_dist = (1u << c.window_log) - 1;
     u32 anchor = b0, ip = b0 + 1;
     u32 last_off = 0;
+    u64 v_ahead = 0; u32 ahead_pos = 0xffffffffu;              // per lane: bytes at position ahead_pos, if loaded
     if (b1 - b0 >= kMfLimit) {
     const u32 mflimit = b1 - kMfLimit;
     const u8* const matchlimit = src + b1 - kLastLiterals;
@@ -503,10 +450,15 @@ template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u3
             const u32 cur = P + bias;
             const u32 low = (bias + max_dist >= cur) ? bias : cur - max_dist;
             u64 v = 0; u32 h = 0x80000000u | lane;
-            if (valid) { v = ld64(src + P); h = hash5(v, hl); }
+            if (valid) { v = (ahead_pos == P) ? v_ahead : ld64(src + P); h = hash5(v, hl); }
+            {   // request the bytes of the following NL positions one batch early (used if this batch finds nothing)
+                const u32 Pn = P + NL;
+                ahead_pos = Pn < mflimit ? Pn : 0xffffffffu;
+                v_ahead = Pn < mflimit ? ld64(src + Pn) : 0;
+            }
             const u32 peers = W::match_any(h);
             u32 below = peers & ((1u << lane) - 1);
-            u32 seen = valid ? table[h] : 0;
+            u32 seen = valid ? T.get(h) : 0;
             while (below) {                                   // replay earlier same-bucket lanes, in order
                 const u32 bl = ctz32(below); below &= below - 1;
                 const u32 pb = ip + bl + bias;
@@ -532,7 +484,7 @@ template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u3
             W::sync();
             if ((commit >> lane) & 1) {
                 const u32 grp = peers & commit;
-                if (highbit32(grp) == lane) table[h] = newval;
+                if (highbit32(grp) == lane) T.set(h, newval);
             }
             W::sync();
             if (w_lane == 32) { ip += NL; continue; }
@@ -556,8 +508,8 @@ template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u3
                         const u32 cur2 = start2 + bias;
                         const u32 low2 = (bias + max_dist >= cur2) ? bias : cur2 - max_dist;
                         const u64 v2 = ld64(src + start2);
-                        u32* slot2 = &table[hash5(v2, hl)];
-                        const u32 cand2 = *slot2;
+                        const u32 h2 = hash5(v2, hl);
+                        const u32 cand2 = T.get(h2);
                         ml2 = 0;
                         bool ok = false; u32 m = 0;
                         if (cand2 < cur2 && cand2 >= low2) {
@@ -565,7 +517,7 @@ template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u3
                             ok = start2 - m >= kMinOffset && ld32(src + m) == (u32)v2;
                         }
                         W::sync();
-                        pf_update(slot2, cur2, wr);
+                        if (wr && (cand2 >= cur2 || cur2 >= cand2 + kMinOffset)) T.set(h2, cur2);   // lizard_parser_pricefast.h:190
                         W::sync();
                         if (ok) {
                             const u32 mlt = count_match_par<W>(src + start2 + kMinMatch, src + m + kMinMatch, matchlimit) + kMinMatch;
@@ -707,7 +659,7 @@ template <class W> LZ_HD int write_stream(bool use_huff, const u8* p, u32 n, u8*
                     const u32 m = k < 3 ? seg : n - 3 * seg;
                     huf_pack_segment<W>(hw->pack, p + k * seg, m, hw->ws.codes);
                     const u32 sb = (u32)W::bcast((int)hw->plan.seg_bytes[k]);
-                    lanes_copy<W>(dst + o, (const u8*)hw->pack, sb);
+                    lanes_copy_rows<W>(dst + o, (const u8*)hw->pack, sb);
                     W::sync();
                     o += sb;
                 }
@@ -718,75 +670,102 @@ template <class W> LZ_HD int write_stream(bool use_huff, const u8* p, u32 n, u8*
     }
     if (op + 3 + (long)n > oend) return -1;
     if (wr) wr_le24(dst + op, n);
-    lanes_copy<W>(dst + op + 3, p, n);
+    lanes_copy_rows<W>(dst + op + 3, p, n);
     op += 3 + (long)n;
     return 0;
 }
 
-// Lizard_writeBlock: 0 ok, 1 output error
-template <class W> LZ_HD int write_block(const EncStreams& s, const u8* in, u32 in_size, u8* dst, long& op, long oend,
-                                        bool huffman, EncHufWork* hw)
+// Lizard_writeBlock (lib/lizard_compress.c:186-250): 0 ok, 1 output error.  `in` is the inner block's first byte.
+// All sizes are known from the sequence list, so the reference's decisions (raw block, stream does not fit,
+// gain too small) are taken in its order before bytes move; only entropy-coded levels build flags/literals in
+// scratch first.
+template <class W> LZ_HD int write_block(const EncStreams& s, const u8* src, const u8* in, u32 in_size, u8* dst, long& op, long oend,
+                                        bool huffman, bool lizv1, u8* scratch_lits, u8* scratch_flags, EncHufWork* hw)
 {
     const bool wr = W::lane() == 0;
     const long start = op;
     const u32 sum = s.nf + s.nl + s.n16 + s.n24;
     bool raw = (s.nl < kWildCopy) || (sum + 5 * 3 + 1 > in_size);
     if (!raw) {
-        u32 hdr = 0;
-        int r;
-        op += 1;
-        r = write_stream<W>(false, s.lits, 0, dst, op, oend, hw);       if (r < 0) return 1;   // (empty) lengths stream
-        r = write_stream<W>(false, s.off16, s.n16, dst, op, oend, hw);  if (r < 0) return 1;
-        r = write_stream<W>(false, s.off24, s.n24, dst, op, oend, hw);  if (r < 0) return 1;
-        r = write_stream<W>(huffman, s.flags, s.nf, dst, op, oend, hw); if (r < 0) return 1;  hdr += (u32)r * kFlagFlags;
-        r = write_stream<W>(huffman, s.lits, s.nl, dst, op, oend, hw);  if (r < 0) return 1;  hdr += (u32)r * kFlagLiterals;
-        if (wr) dst[start] = (u8)hdr;
-        const u32 out = (u32)(op - start);
-        if (out + out / 32 + 512 > in_size) raw = true;
-        else return 0;
+        long o = start + 1;
+        if (o + 3 > oend) return 1;                                   // (empty) lengths stream
+        const long o_len = o; o += 3;
+        if (o + 3 + (long)s.n16 > oend) return 1;
+        const long o16 = o; o += 3 + (long)s.n16;
+        if (o + 3 + (long)s.n24 > oend) return 1;
+        const long o24 = o; o += 3 + (long)s.n24;
+        const bool entropy = huffman && (s.nf > 1024 || s.nl > 1024);
+        if (!entropy) {
+            if (o + 3 + (long)s.nf > oend) return 1;
+            const long of = o; o += 3 + (long)s.nf;
+            if (o + 3 + (long)s.nl > oend) return 1;
+            const long ol = o; o += 3 + (long)s.nl;
+            const u32 out = (u32)(o - start);
+            if (out + out / 32 + 512 > in_size) raw = true;
+            else {
+                if (wr) {
+                    dst[start] = 0;
+                    wr_le24(dst + o_len, 0); wr_le24(dst + o16, s.n16); wr_le24(dst + o24, s.n24);
+                    wr_le24(dst + of, s.nf); wr_le24(dst + ol, s.nl);
+                }
+                emit_streams<W>(s, src, lizv1, dst + ol + 3, dst + of + 3, dst + o16 + 3, dst + o24 + 3);
+                op = o;
+                return 0;
+            }
+        } else {
+            if (wr) { wr_le24(dst + o_len, 0); wr_le24(dst + o16, s.n16); wr_le24(dst + o24, s.n24); }
+            emit_streams<W>(s, src, lizv1, scratch_lits, scratch_flags, dst + o16 + 3, dst + o24 + 3);
+            op = o;
+            u32 hdr = 0;
+            int r = write_stream<W>(huffman, scratch_flags, s.nf, dst, op, oend, hw); if (r < 0) return 1;  hdr += (u32)r * kFlagFlags;
+            r = write_stream<W>(huffman, scratch_lits, s.nl, dst, op, oend, hw);       if (r < 0) return 1;  hdr += (u32)r * kFlagLiterals;
+            if (wr) dst[start] = (u8)hdr;
+            const u32 out = (u32)(op - start);
+            if (out + out / 32 + 512 > in_size) raw = true;
+            else return 0;
+        }
     }
     if ((u32)(oend - start) < in_size + 4 || oend - start < 0) return 1;
-    W::sync();      // the abandoned stream bytes (written by lane 0) must not land after the raw copy
+    W::sync();      // abandoned stream bytes (written by other lanes) must not land after the raw copy
     if (wr) { dst[start] = (u8)kFlagRaw; wr_le24(dst + start + 1, in_size); }
-    lanes_copy<W>(dst + start + 4, in, in_size);
+    lanes_copy_rows<W>(dst + start + 4, in, in_size);
     op = start + 4 + (long)in_size;
     return 0;
 }
 
 struct EncWork {                 // per-warp global scratch
-    u8 lits[kBlockSizePad];
+    SeqRec seq[kBlockSize / kMinMatch + 8];   // a sequence consumes >= 4 input bytes
+    u8 lits[kBlockSizePad];      // flags / literals streams, only when an entropy stage follows
     u8 flags[kBlockSizePad];
-    u8 off16[kBlockSizePad];
-    u8 off24[kBlockSizePad];
     EncHufWork huf;
 };
 
 // Lizard_compress_extState with a clean table: returns compressed size or 0
 template <class W> LZ_HD int encode_unit(const u8* src, u32 src_size, u8* dst, u32 cap, int level,
-                                        u32* table, EncWork* work)
+                                        const HashTable& T, EncWork* work)
 {
     const LevelParams lp = level_params(level);
     if (lp.parser == kParserUnsupported) return 0;
     if (src_size > kMaxInputSize) return 0;
-    for (u32 i = W::lane(); i < (1u << lp.hashLog); i += W::lanes()) table[i] = 0;
-    W::sync();
+    hash_clear<W>(T, lp.hashLog);
     const bool wr = W::lane() == 0;
     long op = 0;
     const long oend = (long)cap;
     if (cap < 1) return 0;                          // the reference would write the level byte regardless
     if (wr) dst[0] = (u8)level;
     op = 1;
-    ParseCtx pc; pc.src = src; pc.table = table; pc.hash_log = lp.hashLog; pc.window_log = lp.windowLog;
+    ParseCtx pc; pc.src = src; pc.T = T; pc.hash_log = lp.hashLog; pc.window_log = lp.windowLog;
     u32 pos = 0;
     while (pos < src_size) {
         const u32 part = src_size - pos < kBlockSize ? src_size - pos : kBlockSize;
         EncStreams s;
-        s.lits = work->lits; s.flags = work->flags; s.off16 = work->off16; s.off24 = work->off24;
-        s.nl = s.nf = s.n16 = s.n24 = 0;
+        s.rec = work->seq; s.nseq = 0;
+        s.nl = s.nf = s.n16 = s.n24 = 0; s.tail_anchor = pos; s.tail_len = 0;
         if (lp.parser == kParserPriceFast) parse_price_fast_par<W>(pc, pos, pos + part, s, lp.minMatchLongOff);
         else parse_fast_par<W>(pc, pos, pos + part, s);
         W::sync();
-        if (write_block<W>(s, src + pos, part, dst, op, oend, lp.huffman != 0, &work->huf)) return 0;
+        if (write_block<W>(s, src, src + pos, part, dst, op, oend, lp.huffman != 0, lp.lizv1 != 0,
+                           work->lits, work->flags, &work->huf)) return 0;
         W::sync();
         pos += part;
     }

@@ -16,6 +16,16 @@ extern "C" int lzb_host_huf_decompress(unsigned char* dst, unsigned n, const uns
     return r;
 }
 
+// same choice as the device kernel: packed 17-bit entries when the unit is a single inner block and the table
+// would live in shared memory, plain 32-bit entries otherwise (the buffer is big enough for either form)
+static lzb::HashTable make_table(lzb::u32* buf, int n, lzb::u32 hash_log)
+{
+    lzb::HashTable T;
+    if ((lzb::u32)n <= lzb::kBlockSize && hash_log <= 14) { T.t32 = nullptr; T.lo = (lzb::u16*)buf; T.hi = buf + ((size_t)1 << hash_log) / 2; }
+    else { T.t32 = buf; T.lo = nullptr; T.hi = nullptr; }
+    return T;
+}
+
 extern "C" int lzb_host_compress(const unsigned char* src, int n, unsigned char* dst, int cap, int level)
 {
     if (n < 0 || cap < 0) return 0;
@@ -26,7 +36,8 @@ extern "C" int lzb_host_compress(const unsigned char* src, int n, unsigned char*
     lzb::u32* table = (lzb::u32*)malloc(sizeof(lzb::u32) << lp.hashLog);
     lzb::EncWork* work = (lzb::EncWork*)malloc(sizeof(lzb::EncWork));
     work->huf.seg_count = (lzb::u32 (*)[256])malloc(4 * 256 * sizeof(lzb::u32));
-    int r = lzb::encode_unit<lzb::HostLanes>(src, (lzb::u32)n, dst, (lzb::u32)cap, level, table, work);
+    lzb::HashTable T = make_table(table, n, lp.hashLog);
+    int r = lzb::encode_unit<lzb::HostLanes>(src, (lzb::u32)n, dst, (lzb::u32)cap, level, T, work);
     free(work->huf.seg_count); free(table); free(work);
     return r;
 }
@@ -42,6 +53,15 @@ extern "C" int lzb_host_decompress(const unsigned char* src, int csize, unsigned
     int r = lzb::decode_unit<lzb::HostLanes>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, sh);
     free(scratch); free(sh);
     return r;
+}
+
+extern "C" void lzb_host_token_stats(unsigned long long* fast, unsigned long long* slow)
+{
+#if defined(LZB_STATS)
+    *fast = lzb::g_tok_fast; *slow = lzb::g_tok_slow;
+#else
+    *fast = 0; *slow = 0;
+#endif
 }
 
 // =====================================================================================================
@@ -153,11 +173,11 @@ struct EmuLanes {
     }
 };
 
-struct EmuCompressArgs { const unsigned char* src; int n; unsigned char* dst; int cap; int level; lzb::u32* table; lzb::EncWork* work; int result; };
+struct EmuCompressArgs { const unsigned char* src; int n; unsigned char* dst; int cap; int level; lzb::HashTable T; lzb::EncWork* work; int result; };
 static void emu_compress_body(void* p)
 {
     EmuCompressArgs* a = (EmuCompressArgs*)p;
-    int r = lzb::encode_unit<EmuLanes>(a->src, (lzb::u32)a->n, a->dst, (lzb::u32)a->cap, a->level, a->table, a->work);
+    int r = lzb::encode_unit<EmuLanes>(a->src, (lzb::u32)a->n, a->dst, (lzb::u32)a->cap, a->level, a->T, a->work);
     if (EmuLanes::lane() == 0) a->result = r;
 }
 
@@ -171,11 +191,12 @@ extern "C" int lzb_emu_compress(const unsigned char* src, int n, unsigned char* 
     if (lp.parser == lzb::kParserUnsupported) return 0;
     EmuCompressArgs a;
     a.src = src; a.n = n; a.dst = dst; a.cap = cap; a.level = level; a.result = 0;
-    a.table = (lzb::u32*)malloc(sizeof(lzb::u32) << lp.hashLog);
+    lzb::u32* table = (lzb::u32*)malloc(sizeof(lzb::u32) << lp.hashLog);
+    a.T = make_table(table, n, lp.hashLog);
     a.work = (lzb::EncWork*)malloc(sizeof(lzb::EncWork));
     a.work->huf.seg_count = (lzb::u32 (*)[256])malloc(4 * 256 * sizeof(lzb::u32));
     emu::run(emu_compress_body, &a);
-    free(a.work->huf.seg_count); free(a.table); free(a.work);
+    free(a.work->huf.seg_count); free(table); free(a.work);
     return a.result;
 }
 

@@ -50,6 +50,71 @@ template <class W> LZ_HD void lanes_copy(u8* dst, const u8* src, u32 n)
     for (u32 i = W::lane(); i < n; i += W::lanes()) dst[i] = src[i];
 }
 
+// ---- byte-per-lane copy, four rows of lanes per pass --------------------------------------------------------
+// One pass moves up to 4*lanes bytes: lane l handles bytes l, l+L, l+2L, l+3L.  All loads are issued before the
+// stores, so a pass exposes one memory latency; every load/store instruction of the warp touches one contiguous
+// run of bytes (1-2 sectors).  No alignment requirements, which matters because literal runs and matches start
+// at arbitrary byte positions.  The source must not overlap the bytes written by the same pass.
+template <class W> LZ_HD void lanes_copy_rows(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
+{
+    const u32 l = W::lane(), L = W::lanes();
+    for (u32 base = 0; base < n; base += 4 * L) {
+        const u32 i0 = base + l, i1 = i0 + L, i2 = i1 + L, i3 = i2 + L;
+        u8 b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        if (i0 < n) b0 = src[i0];
+        if (i1 < n) b1 = src[i1];
+        if (i2 < n) b2 = src[i2];
+        if (i3 < n) b3 = src[i3];
+        if (i0 < n) dst[i0] = b0;
+        if (i1 < n) dst[i1] = b1;
+        if (i2 < n) dst[i2] = b2;
+        if (i3 < n) dst[i3] = b3;
+    }
+}
+
+// ---- 4-bytes-per-lane copy pieces: one pass moves 4*lanes bytes ------------------------------------------
+LZ_HD u32 ld32u(const u8* p)      // unaligned little-endian load; may touch the aligned words around p only
+{
+#if defined(__CUDA_ARCH__)
+    const size_t a = (size_t)p;
+    const u32* q = (const u32*)(a & ~(size_t)3);
+    const u32 sh = (u32)(a & 3) * 8;
+    const u32 lo = q[0];
+    if (sh == 0) return lo;
+    return __funnelshift_r(lo, q[1], sh);
+#else
+    return rd_le32(p);
+#endif
+}
+// this lane's 4 bytes (index 4*lane) of a run of n bytes; bytes past n read as 0
+template <class W> LZ_HD u32 load_chunk4(const u8* src, u32 n)
+{
+    const u32 i = 4 * W::lane();
+    if (i + 4 <= n) return ld32u(src + i);
+    u32 v = 0;
+    for (u32 j = 0; j < 4; ++j) if (i + j < n) v |= (u32)src[i + j] << (8 * j);
+    return v;
+}
+template <class W> LZ_HD void store_chunk4(u8* dst, u32 v, u32 n)
+{
+    const u32 i = 4 * W::lane();
+    if (i >= n) return;
+    u8* d = dst + i;
+    if (i + 4 <= n && ((size_t)d & 3) == 0) { *(u32*)d = v; return; }
+    const u32 cnt = n - i < 4 ? n - i : 4;
+    for (u32 j = 0; j < cnt; ++j) d[j] = (u8)(v >> (8 * j));
+}
+// non-overlapping copy (src and dst ranges disjoint, or src entirely before dst with distance >= n)
+template <class W> LZ_HD void lanes_copy4(u8* dst, const u8* src, u32 n)
+{
+    const u32 step = 4 * W::lanes();
+    for (u32 base = 0; base < n; base += step) {
+        const u32 part = n - base < step ? n - base : step;
+        const u32 v = load_chunk4<W>(src + base, part);
+        store_chunk4<W>(dst + base, v, part);
+    }
+}
+
 LZ_HD u32 ctz32(u32 v)
 {
 #if defined(__CUDA_ARCH__)

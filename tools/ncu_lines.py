@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Aggregate an ncu report's per-instruction stall samples by source line.
+
+usage: ncu_lines.py <report.ncu-rep> <kernel-name-substring> <library.so> [top]
+Needs the library compiled with -lineinfo.  Works without a GPU (ncu -i, cuobjdump, nvdisasm)."""
+import collections
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+rep, kern, lib = sys.argv[1:4]
+top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+dis = subprocess.run(["nvdisasm", "--print-line-info", "--print-code", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")
+start = [i for i, l in enumerate(dis) if l.startswith("\t.section\t.text.") and kern in l][0]
+off2line, cur = {}, None
+for l in dis[start + 1:]:
+    if l.startswith("\t.section"):
+        break
+    m = re.search(r'//## File "([^"]+)", line (\d+)', l)
+    if m:
+        cur = (m.group(1), int(m.group(2)))
+        continue
+    m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(\S.*?);", l)
+    if m:
+        off2line[int(m.group(1), 16)] = cur
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr = rows[1]
+iS, iI, iA = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Address")
+base = int(rows[2][iA], 16)
+samp, inst = collections.Counter(), collections.Counter()
+for r in rows[2:]:
+    if len(r) <= iI:
+        continue
+    k = off2line.get(int(r[iA], 16) - base)
+    samp[k] += int(r[iS] or 0)
+    inst[k] += int(r[iI] or 0)
+ts, ti = sum(samp.values()), sum(inst.values())
+print("kernel %s: %d stall samples, %d warp instructions" % (kern, ts, ti))
+cache = {}
+for k, v in samp.most_common(top):
+    text = ""
+    if k and os.path.exists(k[0]):
+        cache.setdefault(k[0], open(k[0]).read().split("\n"))
+        text = cache[k[0]][k[1] - 1].strip()[:100]
+    print("%5.1f%% samples %5.1f%% inst  %s:%s  %s" % (100.0 * v / ts, 100.0 * inst[k] / ti, os.path.basename(k[0]) if k else None, k[1] if k else "", text))
