@@ -333,16 +333,31 @@ template <class W> LZ_HD void run_batch_copies(u8* dst, const u8* lits, u32 nb, 
     // warm the cache for this lane's match source while the literal runs are being moved
     if (lane < nb && off != 0 && off <= opos + lit_len) W::prefetch(dst + (opos + lit_len - off));
     W::sync();
-    // literal runs are independent of everything in this batch
-    for (u32 k = 0; k < nb; ++k) {
-        const SeqDesc d = desc[k];
-        lanes_copy_rows<W>(dst + d.b, lits + d.a, d.c);
+    // literal runs are independent of everything in this batch: two at a time
+    {
+        u32 k = 0;
+        for (; k + 1 < nb; k += 2) {
+            const SeqDesc d0 = desc[k], d1 = desc[k + 1];
+            lanes_copy_rows2<W>(dst + d0.b, lits + d0.a, d0.c, dst + d1.b, lits + d1.a, d1.c);
+        }
+        if (k < nb) { const SeqDesc d0 = desc[k]; lanes_copy_rows<W>(dst + d0.b, lits + d0.a, d0.c); }
     }
     W::sync();
-    for (u32 k = 0; k < nb; ++k) {
+    // matches in order; two neighbours go together when the second one does not read what the first one writes
+    for (u32 k = 0; k < nb; ) {
         const SeqDesc d = desc[32 + k];
         const u32 m = d.c, o = d.b;
         u8* const to = dst + d.a;
+        if (k + 1 < nb && o >= m) {
+            const SeqDesc e = desc[32 + k + 1];
+            // e's source [e.a - e.b, e.a - e.b + e.c) must end at or before d's destination start, and not overlap itself
+            if (e.b >= e.c && e.a - e.b + e.c <= d.a) {
+                lanes_copy_rows2<W>(to, to - o, m, dst + e.a, dst + e.a - e.b, e.c);
+                W::sync();
+                k += 2;
+                continue;
+            }
+        }
         if (o >= m || o >= 4 * L) {
             // source entirely before the destination of each pass: plain passes, ordered by a barrier
             for (u32 base = 0; base < m; base += 4 * L) {
@@ -352,6 +367,7 @@ template <class W> LZ_HD void run_batch_copies(u8* dst, const u8* lits, u32 nb, 
             }
         } else lanes_match<W>(dst, (long)d.a, o, m);
         W::sync();
+        k += 1;
     }
 }
 

@@ -29,10 +29,7 @@ LZ_HD u32 ld32(const u8* p)
 #if defined(__CUDA_ARCH__)
     const size_t a = (size_t)p;
     const u32* q = (const u32*)(a & ~(size_t)3);
-    const u32 sh = (u32)(a & 3) * 8;
-    const u32 lo = q[0];
-    if (sh == 0) return lo;
-    return __funnelshift_r(lo, q[1], sh);
+    return __funnelshift_r(q[0], q[1], (u32)(a & 3) * 8);      // two aligned words, shift 0 returns the first
 #else
     u32 v; memcpy(&v, p, 4); return v;
 #endif
@@ -41,13 +38,25 @@ LZ_HD u64 ld64(const u8* p)
 {
 #if defined(__CUDA_ARCH__)
     const size_t a = (size_t)p;
-    const u64* q = (const u64*)(a & ~(size_t)7);
-    const u32 sh = (u32)(a & 7) * 8;
-    const u64 lo = q[0];
-    if (sh == 0) return lo;
-    return (lo >> sh) | (q[1] << (64 - sh));
+    const u32* q = (const u32*)(a & ~(size_t)3);
+    const u32 sh = (u32)(a & 3) * 8;
+    const u32 w0 = q[0], w1 = q[1], w2 = q[2];
+    return (u64)__funnelshift_r(w0, w1, sh) | ((u64)__funnelshift_r(w1, w2, sh) << 32);
 #else
     u64 v; memcpy(&v, p, 8); return v;
+#endif
+}
+// the 5 bytes at p as a 40-bit little-endian value: all the hash needs, and its low word is the 4-byte match test
+LZ_HD u64 ld5(const u8* p)
+{
+#if defined(__CUDA_ARCH__)
+    const size_t a = (size_t)p;
+    const u32* q = (const u32*)(a & ~(size_t)3);
+    const u32 sh = (u32)(a & 3) * 8;
+    const u32 w0 = q[0], w1 = q[1];
+    return (u64)__funnelshift_r(w0, w1, sh) | ((u64)((w1 >> sh) & 0xFFu) << 32);
+#else
+    u64 v; memcpy(&v, p, 8); return v & 0xFFFFFFFFFFull;
 #endif
 }
 
@@ -338,7 +347,7 @@ template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, 
     {
         const u32 mflimit = b1 - kMfLimit;
         const u8* const matchlimit = src + b1 - kLastLiterals;
-        if (wr) T.set(hash5(ld64(src + ip), hl), ip + bias);
+        if (wr) T.set(hash5(ld5(src + ip), hl), ip + bias);
         W::sync();
         ip++;
         for (;;) {
@@ -351,12 +360,12 @@ template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, 
                     const u32 P = ip0 + probe_offset(j);
                     const bool valid = ip0 + probe_offset(j + 1) <= mflimit;   // else this probe ends the block
                     u64 v = 0; u32 h = 0x80000000u | lane;                     // unique key: matches nobody
-                    if (valid) { v = have_ahead ? v_ahead : ld64(src + P); h = hash5(v, hl); }
+                    if (valid) { v = have_ahead ? v_ahead : ld5(src + P); h = hash5(v, hl); }
                     {   // the probe positions of the next batch are known already: start their loads now so that the
                         // memory latency overlaps this batch's bucket / candidate work (wasted only when a match ends the search)
                         const u32 jn = j + NL;
                         have_ahead = ip0 + probe_offset(jn + 1) <= mflimit;
-                        v_ahead = have_ahead ? ld64(src + ip0 + probe_offset(jn)) : 0;
+                        v_ahead = have_ahead ? ld5(src + ip0 + probe_offset(jn)) : 0;
                     }
                     const u32 peers = W::match_any(h);
                     const u32 below = peers & ((1u << lane) - 1);
@@ -396,9 +405,9 @@ template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, 
                 ip += ml + kMinMatch;
                 anchor = ip;
                 if (ip > mflimit) goto last_literals;
-                if (wr) T.set(hash5(ld64(src + ip - 2), hl), ip - 2 + bias);
+                if (wr) T.set(hash5(ld5(src + ip - 2), hl), ip - 2 + bias);
                 W::sync();
-                const u64 v = ld64(src + ip);
+                const u64 v = ld5(src + ip);
                 const u32 h = hash5(v, hl);
                 const u32 cand = T.get(h);
                 W::sync();
@@ -450,11 +459,11 @@ template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u3
             const u32 cur = P + bias;
             const u32 low = (bias + max_dist >= cur) ? bias : cur - max_dist;
             u64 v = 0; u32 h = 0x80000000u | lane;
-            if (valid) { v = (ahead_pos == P) ? v_ahead : ld64(src + P); h = hash5(v, hl); }
+            if (valid) { v = (ahead_pos == P) ? v_ahead : ld5(src + P); h = hash5(v, hl); }
             {   // request the bytes of the following NL positions one batch early (used if this batch finds nothing)
                 const u32 Pn = P + NL;
                 ahead_pos = Pn < mflimit ? Pn : 0xffffffffu;
-                v_ahead = Pn < mflimit ? ld64(src + Pn) : 0;
+                v_ahead = Pn < mflimit ? ld5(src + Pn) : 0;
             }
             const u32 peers = W::match_any(h);
             u32 below = peers & ((1u << lane) - 1);
@@ -507,7 +516,7 @@ template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u3
                     {   // Lizard_FindMatchFaster (uniform: one position)
                         const u32 cur2 = start2 + bias;
                         const u32 low2 = (bias + max_dist >= cur2) ? bias : cur2 - max_dist;
-                        const u64 v2 = ld64(src + start2);
+                        const u64 v2 = ld5(src + start2);
                         const u32 h2 = hash5(v2, hl);
                         const u32 cand2 = T.get(h2);
                         ml2 = 0;

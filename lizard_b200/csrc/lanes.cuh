@@ -58,18 +58,48 @@ template <class W> LZ_HD void lanes_copy(u8* dst, const u8* src, u32 n)
 template <class W> LZ_HD void lanes_copy_rows(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
 {
     const u32 l = W::lane(), L = W::lanes();
-    for (u32 base = 0; base < n; base += 4 * L) {
-        const u32 i0 = base + l, i1 = i0 + L, i2 = i1 + L, i3 = i2 + L;
-        u8 b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-        if (i0 < n) b0 = src[i0];
-        if (i1 < n) b1 = src[i1];
-        if (i2 < n) b2 = src[i2];
-        if (i3 < n) b3 = src[i3];
-        if (i0 < n) dst[i0] = b0;
-        if (i1 < n) dst[i1] = b1;
-        if (i2 < n) dst[i2] = b2;
-        if (i3 < n) dst[i3] = b3;
+    const u8* s = src + l; u8* d = dst + l;
+    if (n <= L) { if (l < n) d[0] = s[0]; return; }              // most runs are shorter than one row
+    if (n <= 2 * L) {
+        u8 b0 = s[0], b1 = 0;
+        if (l + L < n) b1 = s[L];
+        d[0] = b0;
+        if (l + L < n) d[L] = b1;
+        return;
     }
+    for (u32 base = 0; base < n; base += 4 * L, s += 4 * L, d += 4 * L) {
+        const u32 r = n - base;                                   // bytes left; row k is live for lane l when l + k*L < r
+        u8 b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+        if (l < r) b0 = s[0];
+        if (l + L < r) b1 = s[L];
+        if (l + 2 * L < r) b2 = s[2 * L];
+        if (l + 3 * L < r) b3 = s[3 * L];
+        if (l < r) d[0] = b0;
+        if (l + L < r) d[L] = b1;
+        if (l + 2 * L < r) d[2 * L] = b2;
+        if (l + 3 * L < r) d[3 * L] = b3;
+    }
+}
+
+// two independent copies: the first rows of both are loaded before anything is stored (one exposed latency)
+template <class W> LZ_HD void lanes_copy_rows2(u8* __restrict__ dA, const u8* __restrict__ sA, u32 nA,
+                                               u8* __restrict__ dB, const u8* __restrict__ sB, u32 nB)
+{
+    const u32 l = W::lane(), L = W::lanes();
+    if (nA <= 2 * L && nB <= 2 * L) {
+        u8 a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+        if (l < nA) a0 = sA[l];
+        if (l + L < nA) a1 = sA[l + L];
+        if (l < nB) b0 = sB[l];
+        if (l + L < nB) b1 = sB[l + L];
+        if (l < nA) dA[l] = a0;
+        if (l + L < nA) dA[l + L] = a1;
+        if (l < nB) dB[l] = b0;
+        if (l + L < nB) dB[l + L] = b1;
+        return;
+    }
+    lanes_copy_rows<W>(dA, sA, nA);
+    lanes_copy_rows<W>(dB, sB, nB);
 }
 
 // ---- 4-bytes-per-lane copy pieces: one pass moves 4*lanes bytes ------------------------------------------
