@@ -260,12 +260,18 @@ def run_ours(args, rank, world, local_rank):
         dctx = ctypes.c_void_p()
         L.LizardF_createDecompressionContext(ctypes.byref(dctx), 100)
 
+        split = [0.0, 0.0]
+
         def e2e_step():
+            t_a = time.perf_counter()
             fs = L.LizardF_compressFrame(h_frame.data_ptr(), cap, h_src.data_ptr(), nbytes, ctypes.byref(prefs))
             if L.LizardF_isError(fs):
                 raise SystemExit("LizardF_compressFrame: " + L.LizardF_getErrorName(fs).decode())
             so, si = ctypes.c_size_t(nbytes), ctypes.c_size_t(fs)
+            t_b = time.perf_counter()
             r = L.LizardF_decompress(dctx, h_back.data_ptr(), ctypes.byref(so), h_frame.data_ptr(), ctypes.byref(si), None)
+            split[0] += t_b - t_a
+            split[1] += time.perf_counter() - t_b
             if r != 0 or so.value != nbytes or si.value != fs:
                 raise SystemExit("LizardF_decompress: result %d, out %d, in %d of %d" % (r, so.value, si.value, fs))
             return fs
@@ -277,6 +283,7 @@ def run_ours(args, rank, world, local_rank):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+        split[0] = split[1] = 0.0
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
@@ -340,7 +347,8 @@ def run_ours(args, rank, world, local_rank):
         line["e2e"] = {"value": round(mb * K / t_e, 1), "unit": "MB/s",
                        "h2d_bytes_per_step": int(nbytes + frame_size), "d2h_bytes_per_step": int(frame_size + nbytes),
                        "api": "LizardF_compressFrame + LizardF_decompress (128 KiB independent blocks), pinned host buffers, "
-                              "wall clock, chunked H2D / kernels / D2H overlap", "frame_bytes": int(frame_size)}
+                              "wall clock, chunked H2D / kernels / D2H overlap", "frame_bytes": int(frame_size),
+                       "compress_ms_rank0": round(split[0] / K * 1e3, 2), "decompress_ms_rank0": round(split[1] / K * 1e3, 2)}
     # ---- CPU side by side (rank 0, N = 1 only): the reference's own code on one host thread, bounded sample ----
     if world == 1:
         try:

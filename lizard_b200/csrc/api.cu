@@ -11,6 +11,8 @@
 #include <atomic>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
+#include <chrono>
 #include <new>
 
 using namespace lzb;
@@ -182,13 +184,14 @@ int launch_decode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* d
 
 int launch_encode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* dSrcLen,
                   void* dDst, const u64* dDstOff, const u32* dDstCap, int* dResult, u32 n, int level, cudaStream_t s,
-                  const Progress* pg = nullptr)
+                  const Progress* pg = nullptr, const FramePack* fp = nullptr)
 {
     if (n == 0) return LIZARDB200_OK;
     LevelParams lp = level_params(level);
     if (lp.parser == kParserUnsupported) { g_last_error = "compression level not implemented on the GPU"; return LIZARDB200_ERR_LEVEL; }
     EncodeBatch b;
     if (pg) b.progress = *pg; else memset(&b.progress, 0, sizeof b.progress);
+    if (fp) b.pack = *fp; else memset(&b.pack, 0, sizeof b.pack);
     b.src_base = (const u8*)dSrc; b.src_off = dSrcOff; b.src_len = dSrcLen;
     b.dst_base = (u8*)dDst; b.dst_off = dDstOff; b.dst_cap = dDstCap;
     b.result = dResult; b.n_units = n; b.level = level;

@@ -19,6 +19,7 @@
 #include "lanes.cuh"
 #if !defined(__CUDACC__)
 #include <string.h>
+#include <stdlib.h>
 #endif
 
 namespace lzb {
@@ -224,49 +225,65 @@ template <class W> LZ_HD void emit_streams(const EncStreams& s, const u8* src, b
 // ---- hash table ------------------------------------------------------------------------------------------------
 // The reference keeps 32-bit absolute indices (position + 2^24, 0 = never written).  For units of at most one
 // inner block (<= 128 KiB, i.e. every independent frame block) a position needs 17 bits, so the shared-memory
-// form packs an entry as 16 low bits + 1 bit in a bitmap (all ones = empty): 8.5 KiB instead of 16 KiB at
+// form packs an entry as position+1 (0 = empty) in 16 low bits + 1 bit in a bitmap: 8.5 KiB instead of 16 KiB at
 // level 10, 34 KiB instead of 64 KiB at levels 21/41 -- the table size is what bounds resident warps per SM.
+// The parsers insert positions in increasing order, so the bitmap is untouched (all zero) until the parse crosses
+// position 65535 and from then on bits are only ever set; `pos_hint` (a position not below anything inserted so
+// far) lets the first half of a block skip the bitmap altogether.
 // Larger units (several dependent inner blocks) use plain 32-bit entries in global memory.
-struct HashTable {
+struct HashTable {       // runtime descriptor handed to encode_unit
     u32* t32;            // plain form (global memory), or null
     u16* lo;             // packed form
     u32* hi;
-    LZ_HDM u32 get(u32 h) const
+};
+struct PlainTable {
+    u32* t32;
+    LZ_HDM explicit PlainTable(const HashTable& d) : t32(d.t32) {}
+    LZ_HDM u32 get(u32 h, u32) const { return t32[h]; }
+    LZ_HDM void set(u32 h, u32 abs_index) const { t32[h] = abs_index; }
+    template <class W> LZ_HDM void clear(u32 hash_log) const
     {
-        if (t32) return t32[h];
-        const u32 p = (u32)lo[h] | (((hi[h >> 5] >> (h & 31)) & 1u) << 16);
-        return p == 0x1FFFFu ? 0u : p + kDictSize;
+        const u32 n = 1u << hash_log;
+        for (u32 i = W::lane(); i < n; i += W::lanes()) t32[i] = 0;
+        W::sync();
+    }
+};
+struct PackedTable {
+    u16* lo; u32* hi;
+    LZ_HDM explicit PackedTable(const HashTable& d) : lo(d.lo), hi(d.hi) {}
+    LZ_HDM u32 get(u32 h, u32 pos_hint) const
+    {
+        u32 p = lo[h];
+        if (pos_hint >= 0xFFFFu) p |= ((hi[h >> 5] >> (h & 31)) & 1u) << 16;
+        return p ? p - 1 + kDictSize : 0u;
     }
     LZ_HDM void set(u32 h, u32 abs_index) const
     {
-        if (t32) { t32[h] = abs_index; return; }
-        const u32 p = abs_index - kDictSize;
+        const u32 p = abs_index - kDictSize + 1;
         lo[h] = (u16)p;
         const u32 bit = 1u << (h & 31);
 #if defined(__CUDA_ARCH__)
-        if (p >> 16) atomicOr(&hi[h >> 5], bit); else atomicAnd(&hi[h >> 5], ~bit);
+        if (p >> 16) { if (!(hi[h >> 5] & bit)) atomicOr(&hi[h >> 5], bit); }
 #else
-        if (p >> 16) hi[h >> 5] |= bit; else hi[h >> 5] &= ~bit;
+        if (p >> 16) hi[h >> 5] |= bit;
+        else if (hi[h >> 5] & bit) abort();        // insertion order assumption violated
 #endif
     }
-};
-template <class W> LZ_HD void hash_clear(const HashTable& T, u32 hash_log)
-{
-    const u32 n = 1u << hash_log;
-    if (T.t32) { for (u32 i = W::lane(); i < n; i += W::lanes()) T.t32[i] = 0; }
-    else {
-        u32* lo32 = reinterpret_cast<u32*>(T.lo);
-        for (u32 i = W::lane(); i < n / 2; i += W::lanes()) lo32[i] = 0xFFFFFFFFu;
-        for (u32 i = W::lane(); i < n / 32; i += W::lanes()) T.hi[i] = 0xFFFFFFFFu;
+    template <class W> LZ_HDM void clear(u32 hash_log) const
+    {
+        const u32 n = 1u << hash_log;
+        u32* lo32 = reinterpret_cast<u32*>(lo);
+        for (u32 i = W::lane(); i < n / 2; i += W::lanes()) lo32[i] = 0;
+        for (u32 i = W::lane(); i < n / 32; i += W::lanes()) hi[i] = 0;
+        W::sync();
     }
-    W::sync();
-}
-LZ_HD size_t hash_packed_bytes(u32 hash_log) { return ((size_t)2 << hash_log) + ((size_t)4 << hash_log) / 32; }
+};
+LZ_HD size_t hash_packed_bytes(u32 hash_log) { return ((size_t)2 << hash_log) + ((size_t)1 << hash_log) / 8; }
 
 // ---- parser state shared by the inner blocks of one unit -----------------------------------------------
-struct ParseCtx {
+template <class TT> struct ParseCtx {
     const u8* src;        // unit start (position 0); table entries are position + kDictSize, 0 = empty
-    HashTable T;
+    TT        T;
     u32       hash_log;
     u32       window_log;
 };
@@ -277,7 +294,7 @@ struct ParseCtx {
 // 0,1,2,...,65,67,69,... independent of the data.
 LZ_HD u32 probe_offset(u32 j)
 {
-    if (j == 0) return 0;
+    if (j <= 65) return j;                       // the common case: the first two batches of a search
     const u32 m = 62 + j;
     if (m < 64) return 1;
     const u32 q = m >> 6;
@@ -331,10 +348,10 @@ template <class W> LZ_HD u32 extend_back_par(const u8* src, u32 ip, u32 mpos, u3
 // matches.  So lanes evaluate probes j0..j0+L-1 together; a lane's candidate is the latest earlier lane of
 // the same batch with the same bucket, else the table; the lowest hitting lane wins and only buckets of
 // lanes up to the winner are committed (last writer per bucket).
-template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, EncStreams& s)
+template <class W, class TT> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u32 b0, u32 b1, EncStreams& s)
 {
     const u8* const src = c.src;
-    const HashTable T = c.T;
+    const TT T = c.T;
     const u32 hl = c.hash_log;
     const u32 lane = W::lane(), NL = W::lanes();
     const bool wr = lane == 0;
@@ -361,8 +378,9 @@ template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, 
                     const bool valid = ip0 + probe_offset(j + 1) <= mflimit;   // else this probe ends the block
                     u64 v = 0; u32 h = 0x80000000u | lane;                     // unique key: matches nobody
                     if (valid) { v = have_ahead ? v_ahead : ld5(src + P); h = hash5(v, hl); }
-                    {   // the probe positions of the next batch are known already: start their loads now so that the
-                        // memory latency overlaps this batch's bucket / candidate work (wasted only when a match ends the search)
+                    have_ahead = false;
+                    if (j0) {   // a search that missed a whole batch tends to go on: request the next batch's bytes now so
+                                // that their latency overlaps this batch's bucket / candidate work
                         const u32 jn = j + NL;
                         have_ahead = ip0 + probe_offset(jn + 1) <= mflimit;
                         v_ahead = have_ahead ? ld5(src + ip0 + probe_offset(jn)) : 0;
@@ -373,7 +391,7 @@ template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, 
                     const u32 prevP = W::shfl(P, pl);
                     const u32 cur = P + bias;
                     u32 cand = 0;
-                    if (valid) cand = below ? prevP + bias : T.get(h);
+                    if (valid) cand = below ? prevP + bias : T.get(h, P);
                     bool hit = false;
                     if (valid && cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset)
                         hit = ld32(src + (cand - bias)) == (u32)v;
@@ -409,7 +427,7 @@ template <class W> LZ_HD void parse_fast_par(const ParseCtx& c, u32 b0, u32 b1, 
                 W::sync();
                 const u64 v = ld5(src + ip);
                 const u32 h = hash5(v, hl);
-                const u32 cand = T.get(h);
+                const u32 cand = T.get(h, ip);
                 W::sync();
                 if (wr) T.set(h, ip + bias);
                 W::sync();
@@ -430,16 +448,173 @@ last_literals:
     emit_last_literals<W>(s, src, anchor, b1);
 }
 
+// ---- window form of the same parser (32-lane warps) ------------------------------------------------------------
+// parse_fast_par spends one batch per sequence plus a serial "next match" step (insert ip-2, probe ip).  Here a
+// window is 32 CONSECUTIVE positions w0..w0+31 whose bytes, hashes, table values and table-candidate comparisons are
+// fetched once, in parallel; the reference's walk over those positions is then replayed with ballots and shuffles
+// only, for as many sequences as end inside the window:
+//   * `committed` = lanes whose position the reference has inserted into the table so far (program order = lane
+//     order, because positions only grow);
+//   * a walk segment starts at lane `s`: either the post-match probe of position ip (has_next; lizard_parser_
+//     fastsmall.h:138-160: insert ip-2, probe ip) followed by a fresh search from ip+1, or a search in progress;
+//   * lane L's bucket content at its turn is the latest lane below it that is committed or lies in [s, L) and
+//     shares the bucket, else the table value read at the start of the window.  An in-window candidate is compared
+//     through a shuffle (its first four bytes are that lane's own bytes), so no memory access is needed;
+//   * the lowest hitting lane ends the segment; lanes [s, hit] become committed; after the match is measured and
+//     recorded, ip-2 is committed and the walk resumes at ip if that is still inside the window.
+// When the walk leaves the window the committed lanes write their buckets (last writer per bucket wins).
+// Consecutive positions hold while a search has made at most 65 probes (probe_offset); a longer miss run falls
+// back to the batch search with its growing stride.
+template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u32 b0, u32 b1, EncStreams& st)
+{
+    const u8* const src = c.src;
+    const TT T = c.T;
+    const u32 hl = c.hash_log;
+    const u32 lane = W::lane(), NL = W::lanes();
+    const u32 max_dist = (1u << c.window_log) - 1;
+    const u32 bias = kDictSize;
+    const u32 low_limit = (bias + max_dist >= b0 + bias) ? bias : b0 + bias - max_dist;
+    const u32 lt_mask = (1u << lane) - 1;
+    u32 anchor = b0;
+    if (b1 - b0 >= kMinInputForLz) {
+        const u32 mflimit = b1 - kMfLimit;
+        const u8* const matchlimit = src + b1 - kLastLiterals;
+        // window state
+        u32 w0 = b0;            // first position
+        u32 committed = 1;      // position b0 is inserted before the first search (lizard_parser_fastsmall.h:51-53)
+        u32 s = 1;              // the first search starts at b0+1
+        bool has_next = false;
+        u32 jbase = 0;          // probe number of lane s + has_next within its search
+        for (;;) {
+            // ---- fetch: everything memory-bound, once per window ----
+            const u32 P = w0 + lane;
+            const bool ld_ok = P <= mflimit;
+            const bool s_valid = P + 1 <= mflimit;                 // as a search probe: else it ends the block
+            u64 v = 0; u32 h = 0x80000000u | lane;                 // unique key: shares a bucket with nobody
+            if (ld_ok) { v = ld5(src + P); h = hash5(v, hl); }
+            const u32 same = W::match_any(h);
+            const u32 below = same & lt_mask;
+            const u32 tv = ld_ok ? T.get(h, P) : 0u;
+            bool hit_t = false;
+            {
+                const u32 cur = P + bias;
+                if (ld_ok && tv >= low_limit && tv < cur && tv + max_dist >= cur && cur - tv >= kMinOffset)
+                    hit_t = ld32(src + (tv - bias)) == (u32)v;
+            }
+            // ---- replay the reference's walk over the window ----
+            u32 slow_ip0 = 0, slow_j0 = 0; bool go_slow = false, finished = false;
+            for (;;) {
+                const u32 ge_s = ~((1u << s) - 1);
+                const u32 m = below & (committed | ge_s);
+                const u32 pl = m ? highbit32(m) : lane;
+                const u32 pv = W::shfl((u32)v, pl);
+                bool hit = m ? (pv == (u32)v && lane - pl >= kMinOffset) : hit_t;
+                const u32 a = s + (has_next ? 1u : 0u);            // first lane acting as a search probe
+                hit = hit && lane >= s && (s_valid || (has_next && lane == s));
+                const u32 hits = W::ballot(hit);
+                const u32 term = W::ballot(lane >= a && !s_valid);
+                const u32 w_lane = hits ? ctz32(hits) : 32;
+                const u32 t_lane = term ? ctz32(term) : 32;
+                if (w_lane < t_lane) {
+                    committed |= ge_s & (w_lane >= 31 ? 0xffffffffu : ((2u << w_lane) - 1));
+                    const u32 cpos = m ? w0 + pl : tv - bias;
+                    u32 ip = w0 + w_lane;
+                    u32 mpos = W::shfl(cpos, w_lane);
+                    u32 ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
+                    if (!(has_next && w_lane == s)) {               // the post-match probe is taken as it is
+                        const u32 back = extend_back_par<W>(src, ip, mpos, anchor);
+                        ip -= back; mpos -= back; ml += back;
+                    }
+                    emit_lz4<W>(st, src, anchor, ip, ml + kMinMatch, ip - mpos);
+                    ip += ml + kMinMatch;
+                    anchor = ip;
+                    if (ip > mflimit) { finished = true; break; }
+                    const u32 lp = ip - w0;
+                    if (lp < NL) { committed |= 1u << (lp - 2); s = lp; has_next = true; jbase = 0; continue; }
+                    break;                                          // next window starts at ip-2
+                }
+                if (t_lane < 32) { committed |= ge_s & ((1u << t_lane) - 1); finished = true; anchor |= 0; break; }
+                // the whole rest of the window missed: the search goes on
+                committed |= ge_s;
+                slow_j0 = jbase + (NL - a);
+                slow_ip0 = w0 + a - jbase;
+                go_slow = true;
+                break;
+            }
+            // ---- leave the window: committed lanes write their buckets, last writer per bucket ----
+            W::sync();
+            if ((committed >> lane) & 1) {
+                const u32 grp = same & committed;
+                if (highbit32(grp) == lane) T.set(h, P + bias);
+            }
+            W::sync();
+            if (finished) break;
+            if (!go_slow) { w0 = anchor - 2; committed = 1; s = 2; has_next = true; jbase = 0; continue; }
+            if (slow_j0 + NL <= 66) { w0 += NL; committed = 0; s = 0; has_next = false; jbase = slow_j0; continue; }
+            // ---- long miss run: batch search with the growing stride (as parse_fast_par) ----
+            {
+                const u32 ip0 = slow_ip0;
+                u32 j0 = slow_j0;
+                u32 ip = 0, mpos = 0; bool ended = false;
+                for (;;) {
+                    const u32 j = j0 + lane;
+                    const u32 Pj = ip0 + probe_offset(j);
+                    const bool valid = ip0 + probe_offset(j + 1) <= mflimit;
+                    u64 vj = 0; u32 hj = 0x80000000u | lane;
+                    if (valid) { vj = ld5(src + Pj); hj = hash5(vj, hl); }
+                    const u32 peers = W::match_any(hj);
+                    const u32 blw = peers & lt_mask;
+                    const u32 plj = blw ? highbit32(blw) : lane;
+                    const u32 prevP = W::shfl(Pj, plj);
+                    const u32 cur = Pj + bias;
+                    u32 cand = 0;
+                    if (valid) cand = blw ? prevP + bias : T.get(hj, Pj);
+                    bool hit = false;
+                    if (valid && cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset)
+                        hit = ld32(src + (cand - bias)) == (u32)vj;
+                    const u32 hits = W::ballot(hit);
+                    const u32 term = W::ballot(!valid);
+                    const u32 w_lane = hits ? ctz32(hits) : 32;
+                    const u32 t_lane = term ? ctz32(term) : 32;
+                    const bool matched = w_lane < t_lane;
+                    u32 commit;
+                    if (matched) commit = (w_lane >= 31) ? 0xffffffffu : ((2u << w_lane) - 1);
+                    else commit = (t_lane >= 32) ? 0xffffffffu : ((1u << t_lane) - 1);
+                    W::sync();
+                    if ((commit >> lane) & 1) {
+                        const u32 grp = peers & commit;
+                        if (highbit32(grp) == lane) T.set(hj, cur);
+                    }
+                    W::sync();
+                    if (matched) { ip = W::shfl(Pj, w_lane); mpos = W::shfl(cand, w_lane) - bias; break; }
+                    if (t_lane < 32) { ended = true; break; }
+                    j0 += NL;
+                }
+                if (ended) break;
+                u32 ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
+                const u32 back = extend_back_par<W>(src, ip, mpos, anchor);
+                ip -= back; mpos -= back; ml += back;
+                emit_lz4<W>(st, src, anchor, ip, ml + kMinMatch, ip - mpos);
+                ip += ml + kMinMatch;
+                anchor = ip;
+                if (ip > mflimit) break;
+                w0 = ip - 2; committed = 1; s = 2; has_next = true; jbase = 0;
+            }
+        }
+    }
+    emit_last_literals<W>(st, src, anchor, b1);
+}
+
 // Lizard_compress_priceFast with the no-match run probed W::lanes() consecutive positions at a time.
 // Per position the reference (lizard_parser_pricefast.h:158-173) tests the repeat offset first, then the
 // bucket's candidate, then conditionally refreshes the bucket.  last_off is constant during a no-match run,
 // positions advance by one, so L lanes evaluate L consecutive positions; the only cross-lane dependency is
 // the bucket value, which each lane reconstructs by replaying the conditional updates of the earlier lanes
 // that share its bucket.  The lowest hitting lane wins; buckets of lanes up to the winner are committed.
-template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u32 b1, EncStreams& s, u32 min_match_long)
+template <class W, class TT> LZ_HD void parse_price_fast_par(const ParseCtx<TT>& c, u32 b0, u32 b1, EncStreams& s, u32 min_match_long)
 {
     const u8* const src = c.src;
-    const HashTable T = c.T;
+    const TT T = c.T;
     const u32 hl = c.hash_log;
     const u32 lane = W::lane(), NL = W::lanes();
     const bool wr = lane == 0;
@@ -467,7 +642,7 @@ template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u3
             }
             const u32 peers = W::match_any(h);
             u32 below = peers & ((1u << lane) - 1);
-            u32 seen = valid ? T.get(h) : 0;
+            u32 seen = valid ? T.get(h, P) : 0;
             while (below) {                                   // replay earlier same-bucket lanes, in order
                 const u32 bl = ctz32(below); below &= below - 1;
                 const u32 pb = ip + bl + bias;
@@ -518,7 +693,7 @@ template <class W> LZ_HD void parse_price_fast_par(const ParseCtx& c, u32 b0, u3
                         const u32 low2 = (bias + max_dist >= cur2) ? bias : cur2 - max_dist;
                         const u64 v2 = ld5(src + start2);
                         const u32 h2 = hash5(v2, hl);
-                        const u32 cand2 = T.get(h2);
+                        const u32 cand2 = T.get(h2, start2);
                         ml2 = 0;
                         bool ok = false; u32 m = 0;
                         if (cand2 < cur2 && cand2 >= low2) {
@@ -750,28 +925,29 @@ struct EncWork {                 // per-warp global scratch
 };
 
 // Lizard_compress_extState with a clean table: returns compressed size or 0
-template <class W> LZ_HD int encode_unit(const u8* src, u32 src_size, u8* dst, u32 cap, int level,
-                                        const HashTable& T, EncWork* work)
+template <class W, class TT> LZ_HD int encode_unit_t(const u8* src, u32 src_size, u8* dst, u32 cap, int level,
+                                                    const TT T, EncWork* work)
 {
     const LevelParams lp = level_params(level);
     if (lp.parser == kParserUnsupported) return 0;
     if (src_size > kMaxInputSize) return 0;
-    hash_clear<W>(T, lp.hashLog);
+    T.template clear<W>(lp.hashLog);
     const bool wr = W::lane() == 0;
     long op = 0;
     const long oend = (long)cap;
     if (cap < 1) return 0;                          // the reference would write the level byte regardless
     if (wr) dst[0] = (u8)level;
     op = 1;
-    ParseCtx pc; pc.src = src; pc.T = T; pc.hash_log = lp.hashLog; pc.window_log = lp.windowLog;
+    ParseCtx<TT> pc = { src, T, lp.hashLog, lp.windowLog };
     u32 pos = 0;
     while (pos < src_size) {
         const u32 part = src_size - pos < kBlockSize ? src_size - pos : kBlockSize;
         EncStreams s;
         s.rec = work->seq; s.nseq = 0;
         s.nl = s.nf = s.n16 = s.n24 = 0; s.tail_anchor = pos; s.tail_len = 0;
-        if (lp.parser == kParserPriceFast) parse_price_fast_par<W>(pc, pos, pos + part, s, lp.minMatchLongOff);
-        else parse_fast_par<W>(pc, pos, pos + part, s);
+        if (lp.parser == kParserPriceFast) parse_price_fast_par<W, TT>(pc, pos, pos + part, s, lp.minMatchLongOff);
+        else if (W::kLanes >= 4) parse_fast_win<W, TT>(pc, pos, pos + part, s);
+        else parse_fast_par<W, TT>(pc, pos, pos + part, s);
         W::sync();
         if (write_block<W>(s, src, src + pos, part, dst, op, oend, lp.huffman != 0, lp.lizv1 != 0,
                            work->lits, work->flags, &work->huf)) return 0;
@@ -779,6 +955,13 @@ template <class W> LZ_HD int encode_unit(const u8* src, u32 src_size, u8* dst, u
         pos += part;
     }
     return (int)op;
+}
+// the packed form only holds positions of a single inner block
+template <class W> LZ_HD int encode_unit(const u8* src, u32 src_size, u8* dst, u32 cap, int level,
+                                        const HashTable& T, EncWork* work)
+{
+    if (T.t32) return encode_unit_t<W, PlainTable>(src, src_size, dst, cap, level, PlainTable(T), work);
+    return encode_unit_t<W, PackedTable>(src, src_size, dst, cap, level, PackedTable(T), work);
 }
 
 }  // namespace lzb

@@ -75,92 +75,26 @@ inline LizardF_blockSizeID_t frame_optimal_bsid(LizardF_blockSizeID_t req, size_
 inline void wr_le64(u8* p, u64 v) { for (int i = 0; i < 8; ++i) p[i] = (u8)(v >> (8 * i)); }
 inline u64 rd_le64h(const u8* p) { u64 v = 0; for (int i = 0; i < 8; ++i) v |= (u64)p[i] << (8 * i); return v; }
 
-// ---- device side of the compressor: sizes -> offsets -> packed body ----
-struct PackArgs {
-    const u8* comp_base; size_t comp_stride;     // encoder output of unit i at comp_base + i*comp_stride
-    const int* result;                           // encoder result per unit (0 = store raw)
-    const u8* src_base; u32 block_size; size_t src_size;
-    u64* out_off;                                // [n+1] offsets of the packed records; out_off[n] = total
-    u8* out; u32 n;
-    int level;                                   // for the 1-byte-block quirk below
-};
-
-// Size of block i's record payload.  Quirk kept for byte-exactness: for a 1-byte block the reference calls
-// Lizard_compress_extState with capacity 0 (lizard_frame.c:459), whose bound check wraps around
-// (lizard_compress.c:238, oend < start) and it emits the 6-byte raw inner block [level][0x80][01 00 00][byte].
-__device__ __forceinline__ u32 frame_record_payload(const PackArgs& a, u32 i, u32 len)
-{
-    if (len == 1) return 6;
-    return a.result[i] > 0 ? (u32)a.result[i] : len;
-}
-
-__global__ void __launch_bounds__(1024) lizard_frame_scan_kernel(PackArgs a)
-{
-    __shared__ u64 part[1024];
-    const u32 t = threadIdx.x, per = (a.n + 1023) / 1024;
-    const u32 lo = t * per, hi = min(a.n, lo + per);
-    u64 sum = 0;
-    for (u32 i = lo; i < hi; ++i) {
-        const size_t left = a.src_size - (size_t)i * a.block_size;
-        const u32 len = (u32)(left < a.block_size ? left : a.block_size);
-        sum += 4 + (u64)frame_record_payload(a, i, len);
-    }
-    part[t] = sum;
-    __syncthreads();
-    for (u32 o = 1; o < 1024; o <<= 1) { u64 v = t >= o ? part[t - o] : 0; __syncthreads(); part[t] += v; __syncthreads(); }
-    u64 run = part[t] - sum;
-    for (u32 i = lo; i < hi; ++i) {
-        const size_t left = a.src_size - (size_t)i * a.block_size;
-        const u32 len = (u32)(left < a.block_size ? left : a.block_size);
-        a.out_off[i] = run;
-        run += 4 + (u64)frame_record_payload(a, i, len);
-    }
-    if (t == 1023) a.out_off[a.n] = part[1023];
-}
-
-// byte-exact copy with 4-byte stores once dst is aligned (src may have any alignment)
-__device__ __forceinline__ void cta_copy(u8* dst, const u8* src, u32 n)
-{
-    const u32 t = threadIdx.x, nt = blockDim.x;
-    u32 head = (u32)((4 - ((size_t)dst & 3)) & 3);
-    if (head > n) head = n;
-    if (t < head) dst[t] = src[t];
-    dst += head; src += head; n -= head;
-    const u32 words = n >> 2;
-    const size_t sa = (size_t)src;
-    const u32* sq = (const u32*)(sa & ~(size_t)3);
-    const u32 sh = (u32)(sa & 3) * 8;
-    u32* dq = (u32*)dst;
-    for (u32 i = t; i < words; i += nt) dq[i] = sh ? __funnelshift_r(sq[i], sq[i + 1], sh) : sq[i];
-    const u32 tail = n & 3;
-    if (t < tail) dst[words * 4 + t] = src[words * 4 + t];
-}
-
-__global__ void __launch_bounds__(256) lizard_frame_pack_kernel(PackArgs a)
-{
-    const u32 i = blockIdx.x;
-    const size_t left = a.src_size - (size_t)i * a.block_size;
-    const u32 len = (u32)(left < a.block_size ? left : a.block_size);
-    const int r = a.result[i];
-    u8* o = a.out + a.out_off[i];
-    if (len == 1) {
-        if (threadIdx.x == 0) {
-            o[0] = 6; o[1] = 0; o[2] = 0; o[3] = 0;
-            o[4] = (u8)a.level; o[5] = (u8)kFlagRaw; o[6] = 1; o[7] = 0; o[8] = 0; o[9] = a.src_base[(size_t)i * a.block_size];
-        }
-        return;
-    }
-    const u32 word = r > 0 ? (u32)r : (len | 0x80000000u);
-    if (threadIdx.x < 4) o[threadIdx.x] = (u8)(word >> (8 * threadIdx.x));
-    if (r > 0) cta_copy(o + 4, a.comp_base + (size_t)i * a.comp_stride, (u32)r);
-    else cta_copy(o + 4, a.src_base + (size_t)i * a.block_size, len);
-}
-
 // Host pipelining: ONE kernel launch covers all units (no per-chunk tail effects); the input is copied in
 // chunks on a second stream, each copy followed by a 1-thread kernel that publishes how many leading units
 // are resident (Progress::ready); the last unit of each chunk raises a flag in pinned host memory, upon
-// which the host packs / copies that chunk back on a third stream.  H2D, kernels and D2H overlap.
+// which the host copies that chunk back on a third stream.  H2D, kernels and D2H overlap.  The compressor's
+// block records are packed by the encode kernel itself (FramePack, encode.cuh): a separate pack kernel could
+// not become resident while the persistent encode grid holds every SM's registers.
 constexpr size_t kFrameChunkBytes = 32u << 20;
+
+// LIZARDB200_TRACE=1: print a host-clock timeline of the pipelined frame paths to stderr (diagnostics only)
+struct Trace {
+    bool on; std::chrono::steady_clock::time_point t0;
+    Trace() { const char* e = getenv("LIZARDB200_TRACE"); on = e && *e == '1'; t0 = std::chrono::steady_clock::now(); }
+    void mark(const char* what, long k = -1) const
+    {
+        if (!on) return;
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (k >= 0) fprintf(stderr, "[lizard_b200 trace] %8.3f ms  %s %ld\n", ms, what, k);
+        else fprintf(stderr, "[lizard_b200 trace] %8.3f ms  %s\n", ms, what);
+    }
+};
 
 // wait for chunk k's completion flag; false if the compute stream died
 bool wait_chunk(Context& c, volatile u32* flag)
@@ -211,65 +145,59 @@ size_t frame_compress_blocks(Context& c, u8* dst, size_t dst_cap, const u8* src,
     size_t per_chunk = kFrameChunkBytes / block_size; if (per_chunk < 1) per_chunk = 1;
     const size_t stride = (block_size + 15) / 16 * 16;
     const size_t tab_bytes = nblk * (8 + 4 + 8 + 4);
+    Trace tr; tr.mark("compress: begin");
     StreamProgress sp;
     if (sp.init(c, nblk, per_chunk) != cudaSuccess) return ferr(FE_allocation_failed);
     const size_t nchunks = sp.nchunks;
     if (c.pin_tab.reserve(tab_bytes + nchunks * 8 + 64) != cudaSuccess ||
-        c.d_tab.reserve(tab_bytes + nblk * 4 + (nblk + nchunks + 1) * 8 + 64) != cudaSuccess ||
+        c.d_tab.reserve(tab_bytes + nblk * 4 + (nblk + 1) * 8 + 64) != cudaSuccess ||
         c.d_in.reserve(n + 64) != cudaSuccess || c.d_out.reserve(nblk * stride + 64) != cudaSuccess ||
         c.d_pack.reserve(n + nblk * 16 + 64) != cudaSuccess) return ferr(FE_allocation_failed);
     u64* t_in_off = (u64*)c.pin_tab.p; u64* t_out_off = t_in_off + nblk;
     u32* t_in_len = (u32*)(t_out_off + nblk); u32* t_out_cap = t_in_len + nblk;
-    volatile u64* h_totals = (volatile u64*)(((size_t)(t_out_cap + nblk) + 7) & ~(size_t)7);
+    volatile u64* h_chunk_end = (volatile u64*)(((size_t)(t_out_cap + nblk) + 7) & ~(size_t)7);
     for (size_t i = 0; i < nblk; ++i) {
         const size_t left = n - i * block_size;
         const u32 len = (u32)(left < block_size ? left : block_size);
         t_in_off[i] = i * block_size; t_out_off[i] = i * stride; t_in_len[i] = len;
         t_out_cap[i] = len - 1;                    // lizard_frame.c:459: capacity srcSize-1, else stored raw
     }
+    for (size_t k = 0; k < nchunks; ++k) h_chunk_end[k] = 0;
     u8* dtab = (u8*)c.d_tab.p;
     const u64* d_in_off = (const u64*)dtab; const u64* d_out_off = d_in_off + nblk;
     const u32* d_in_len = (const u32*)(d_out_off + nblk); const u32* d_out_cap = d_in_len + nblk;
     int* d_res = (int*)(d_out_cap + nblk);
-    u64* d_pack_off = (u64*)(((size_t)(d_res + nblk) + 7) & ~(size_t)7);
+    u64* d_state = (u64*)(((size_t)(d_res + nblk) + 7) & ~(size_t)7);
 
     if (cudaMemcpyAsync(dtab, c.pin_tab.p, tab_bytes, cudaMemcpyHostToDevice, c.s_in) != cudaSuccess) return ferr(FE_GENERIC);
+    if (cudaMemsetAsync(d_state, 0, nblk * 8, c.s_in) != cudaSuccess) return ferr(FE_GENERIC);
     cudaEventRecord(sp.tables_ready, c.s_in);
     cudaStreamWaitEvent(c.stream, sp.tables_ready, 0);
-    if (launch_encode(c, c.d_in.p, d_in_off, d_in_len, c.d_out.p, d_out_off, d_out_cap, d_res, (u32)nblk, level, c.stream, &sp.pg) != LIZARDB200_OK)
+    FramePack fp; fp.out = (u8*)c.d_pack.p; fp.state = d_state; fp.host_chunk_end = h_chunk_end;
+    if (launch_encode(c, c.d_in.p, d_in_off, d_in_len, c.d_out.p, d_out_off, d_out_cap, d_res, (u32)nblk, level, c.stream, &sp.pg, &fp) != LIZARDB200_OK)
         return ferr(FE_GENERIC);
+    tr.mark("compress: kernel launched");
     for (size_t k = 0; k < nchunks; ++k) {
         const size_t first = k * per_chunk, off = first * block_size;
         const size_t bytes = (k + 1 == nchunks) ? n - off : per_chunk * block_size;
-        const size_t upto = (k + 1 == nchunks) ? nblk : first + per_chunk;
         cudaMemcpyAsync((u8*)c.d_in.p + off, src + off, bytes, cudaMemcpyHostToDevice, c.s_in);
         // publish "units [0, upto) are resident" with a 4-byte copy queued behind the data copy: it runs on the copy
         // engine, so it cannot be starved by the persistent kernel occupying every SM
-        (void)upto;
         cudaMemcpyAsync(sp.d_ready, &sp.h_ready_vals[k], 4, cudaMemcpyHostToDevice, c.s_in);
     }
+    tr.mark("compress: H2D queued");
     size_t written = 0;
     bool too_small = false, failed = false;
     for (size_t k = 0; k < nchunks; ++k) {
-        const size_t first = k * per_chunk, off = first * block_size;
-        const size_t cnt = (k + 1 == nchunks) ? nblk - first : per_chunk;
-        const size_t bytes = (k + 1 == nchunks) ? n - off : per_chunk * block_size;
         if (!wait_chunk(c, &sp.h_done[k])) { failed = true; break; }
-        PackArgs a;
-        a.comp_base = (const u8*)c.d_out.p + first * stride; a.comp_stride = stride; a.result = d_res + first;
-        a.src_base = (const u8*)c.d_in.p + off; a.block_size = (u32)block_size; a.src_size = bytes;
-        a.out_off = d_pack_off + first + k; a.out = (u8*)c.d_pack.p + off + first * 8; a.n = (u32)cnt; a.level = level;
-        lizard_frame_scan_kernel<<<1, 1024, 0, c.s_out>>>(a);
-        lizard_frame_pack_kernel<<<(unsigned)cnt, 256, 0, c.s_out>>>(a);
-        g_launches += 2;
-        cudaMemcpyAsync((void*)&h_totals[k], a.out_off + cnt, 8, cudaMemcpyDeviceToHost, c.s_out);
-        if (cudaStreamSynchronize(c.s_out) != cudaSuccess) { failed = true; break; }
-        const size_t total = (size_t)h_totals[k];
-        if (written + total > dst_cap) { too_small = true; break; }
-        cudaMemcpyAsync(dst + written, a.out, total, cudaMemcpyDeviceToHost, c.s_out);
-        written += total;
+        tr.mark("compress: chunk done", (long)k);
+        const size_t end = (size_t)h_chunk_end[k];          // records of chunks 0..k occupy d_pack[0, end)
+        if (end > dst_cap) { too_small = true; break; }
+        if (end > written) cudaMemcpyAsync(dst + written, (u8*)c.d_pack.p + written, end - written, cudaMemcpyDeviceToHost, c.s_out);
+        written = end;
     }
     cudaError_t e1 = cudaStreamSynchronize(c.s_out), e2 = cudaStreamSynchronize(c.stream), e3 = cudaStreamSynchronize(c.s_in);
+    tr.mark("compress: all streams idle");
     if (failed || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { if (!failed) fail("frame compress", e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3); return ferr(FE_GENERIC); }
     if (too_small) return ferr(FE_dstMaxSize_tooSmall);
     return written;
@@ -287,6 +215,7 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
     if (n == 0) return 0;
     size_t per_chunk = kFrameChunkBytes / max_block; if (per_chunk < 1) per_chunk = 1;
     const size_t tab_bytes = n * (8 + 4 + 8 + 4);
+    Trace tr; tr.mark("decode: begin");
     StreamProgress sp;
     if (sp.init(c, n, per_chunk) != cudaSuccess) return -1;
     const size_t nchunks = sp.nchunks;
@@ -317,10 +246,12 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
             cudaMemcpyAsync(sp.d_ready, &sp.h_ready_vals[k], 4, cudaMemcpyHostToDevice, c.s_in);
         }
     }
+    tr.mark("decode: kernel launched, H2D queued");
     bool failed = false;
     for (size_t k = 0; k < nchunks; ++k) {
         const size_t first = k * per_chunk, last = (k + 1 == nchunks ? n : first + per_chunk) - 1;
         if (!wait_chunk(c, &sp.h_done[k])) { failed = true; break; }
+        tr.mark("decode: chunk done", (long)k);
         cudaMemcpyAsync((void*)(t_res + first), d_res + first, (last - first + 1) * 4, cudaMemcpyDeviceToHost, c.s_out);
         if (cudaStreamSynchronize(c.s_out) != cudaSuccess) { failed = true; break; }
         // copy back exactly what was produced: contiguous up to the end of the last good block of the chunk
@@ -329,6 +260,7 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
         if (hi > lo) cudaMemcpyAsync(dst + lo, (u8*)c.d_out.p + lo, hi - lo, cudaMemcpyDeviceToHost, c.s_out);
     }
     cudaError_t e1 = cudaStreamSynchronize(c.s_out), e2 = cudaStreamSynchronize(c.stream), e3 = cudaStreamSynchronize(c.s_in);
+    tr.mark("decode: all streams idle");
     if (failed || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return -1;
     return 0;
 }

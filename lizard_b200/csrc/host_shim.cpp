@@ -144,6 +144,7 @@ static void run(void (*body)(void*), void* arg)
 
 struct EmuLanes {
     static constexpr bool kDevice = false;
+    static constexpr lzb::u32 kLanes = emu::kLanes;
     static lzb::u32 lane() { return (lzb::u32)emu::g->cur; }
     static lzb::u32 lanes() { return emu::kLanes; }
     static void sync() { unsigned long long t[emu::kLanes]; emu::exchange(0, t); }

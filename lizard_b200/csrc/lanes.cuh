@@ -8,6 +8,7 @@ namespace lzb {
 
 struct HostLanes {
     static constexpr bool kDevice = false;
+    static constexpr u32 kLanes = 1;
     LZ_HDM static u32 lane() { return 0; }
     LZ_HDM static u32 lanes() { return 1; }
     LZ_HDM static void sync() {}
@@ -22,6 +23,7 @@ struct HostLanes {
 #if defined(__CUDACC__)
 struct WarpLanes {
     static constexpr bool kDevice = true;
+    static constexpr u32 kLanes = 32;
     __device__ __forceinline__ static u32 lane() { return threadIdx.x & 31; }
     __device__ __forceinline__ static u32 lanes() { return 32; }
     __device__ __forceinline__ static void sync() { __syncwarp(); }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Aggregate an ncu report's per-instruction stall samples by source line.
 
-usage: ncu_lines.py <report.ncu-rep> <kernel-name-substring> <library.so> [top]
+usage: ncu_lines.py <report.ncu-rep> <kernel-name-substring> <library.so> [top] [inst|func]
 Needs the library compiled with -lineinfo.  Works without a GPU (ncu -i, cuobjdump, nvdisasm)."""
 import collections
 import csv
@@ -14,6 +14,7 @@ import tempfile
 
 rep, kern, lib = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+by_inst = len(sys.argv) > 5 and sys.argv[5] == "inst"
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -43,9 +44,38 @@ for r in rows[2:]:
     samp[k] += int(r[iS] or 0)
     inst[k] += int(r[iI] or 0)
 ts, ti = sum(samp.values()), sum(inst.values())
+if len(sys.argv) > 5 and sys.argv[5] == "func":
+    # bucket by enclosing function: the nearest preceding line at column 0 that looks like a definition
+    fcache = {}
+    def func_of(k):
+        if not k or not os.path.exists(k[0]):
+            return str(k)
+        if k[0] not in fcache:
+            starts = []
+            for n, line in enumerate(open(k[0]).read().split("\n"), 1):
+                if re.match(r"(template\s*<[^>]*>\s*)?(LZ_HD_COLD|LZ_HDM|LZ_HD|LZ_D|__device__|__global__|static|inline|struct)\b.*", line):
+                    m = re.search(r"([A-Za-z_0-9:]+)\s*\(", line)
+                    starts.append((n, (m.group(1) if m else line.strip()[:40])))
+            fcache[k[0]] = starts
+        name = "?"
+        for n, nm in fcache[k[0]]:
+            if n <= k[1]:
+                name = nm
+            else:
+                break
+        return os.path.basename(k[0]) + ":" + name
+    fs, fi = collections.Counter(), collections.Counter()
+    for k in set(samp) | set(inst):
+        f = func_of(k)
+        fs[f] += samp[k]; fi[f] += inst[k]
+    print("kernel %s: %d stall samples, %d warp instructions -- by function" % (kern, ts, ti))
+    for f, v in fi.most_common(top):
+        print("%5.1f%% samples %5.1f%% inst  %s" % (100.0 * fs[f] / ts, 100.0 * v / ti, f))
+    sys.exit(0)
 print("kernel %s: %d stall samples, %d warp instructions" % (kern, ts, ti))
 cache = {}
-for k, v in samp.most_common(top):
+for k, v in (inst if by_inst else samp).most_common(top):
+    v = samp[k]
     text = ""
     if k and os.path.exists(k[0]):
         cache.setdefault(k[0], open(k[0]).read().split("\n"))
