@@ -162,6 +162,58 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def bind_near_gpu(torch, local_rank):
+    """Run this process (and therefore place its pinned host buffers, first touch) on the NUMA node the GPU's PCIe
+    root hangs off.  Returns the node number or None when the topology cannot be read."""
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+def pcie_probe(torch, dev, h_buf):
+    """Pinned-memory copy rates of this box's link, GB/s: (H2D alone, D2H alone, both directions at once)."""
+    n = min(h_buf.numel(), 256 << 20)
+    h_a = h_buf[:n]
+    h_b = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_a = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_b = torch.zeros(n, dtype=torch.uint8, device=dev)
+    s2 = torch.cuda.Stream(device=dev)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t
+
+    def both():
+        with torch.cuda.stream(s2):
+            h_b.copy_(d_b, non_blocking=True)
+        d_a.copy_(h_a, non_blocking=True)
+
+    t_h2d = timed(lambda: d_a.copy_(h_a, non_blocking=True))
+    t_d2h = timed(lambda: h_b.copy_(d_b, non_blocking=True))
+    t_both = timed(both)
+    return round(n / t_h2d / 1e9, 1), round(n / t_d2h / 1e9, 1), round(2 * n / t_both / 1e9, 1)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import lizard_b200 as lz
@@ -169,6 +221,7 @@ def run_ours(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device (the codec has no CPU path)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_near_gpu(torch, local_rank)
     L = lz.lib()
     st = L.LizardB200_setDevice(local_rank)
     if st != 0:
@@ -291,6 +344,7 @@ def run_ours(args, rank, world, local_rank):
         e2e = time.perf_counter() - t0
         L.LizardF_freeDecompressionContext(dctx)
     clocks = sampler.stop()
+    link = pcie_probe(torch, dev, h_src) if e2e is not None else None
 
     # ---- max over ranks ----
     times = torch.tensor([t_c, t_d, e2e if e2e is not None else 0.0], dtype=torch.float64, device=dev)
@@ -348,7 +402,9 @@ def run_ours(args, rank, world, local_rank):
                        "h2d_bytes_per_step": int(nbytes + frame_size), "d2h_bytes_per_step": int(frame_size + nbytes),
                        "api": "LizardF_compressFrame + LizardF_decompress (128 KiB independent blocks), pinned host buffers, "
                               "wall clock, chunked H2D / kernels / D2H overlap", "frame_bytes": int(frame_size),
-                       "compress_ms_rank0": round(split[0] / K * 1e3, 2), "decompress_ms_rank0": round(split[1] / K * 1e3, 2)}
+                       "compress_ms_rank0": round(split[0] / K * 1e3, 2), "decompress_ms_rank0": round(split[1] / K * 1e3, 2),
+                       "pcie_GBps_rank0": {"h2d": link[0], "d2h": link[1], "both_directions_total": link[2]},
+                       "host_numa_node_rank0": numa_node}
     # ---- CPU side by side (rank 0, N = 1 only): the reference's own code on one host thread, bounded sample ----
     if world == 1:
         try:
