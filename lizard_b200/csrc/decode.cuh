@@ -333,41 +333,67 @@ template <class W> LZ_HD void run_batch_copies(u8* dst, const u8* lits, u32 nb, 
     // warm the cache for this lane's match source while the literal runs are being moved
     if (lane < nb && off != 0 && off <= opos + lit_len) W::prefetch(dst + (opos + lit_len - off));
     W::sync();
-    // literal runs are independent of everything in this batch: two at a time
+    typedef LaneGroups<W> LG;
+    const u32 sub = lane / LG::kGroup;
+    const bool act = lane < nb;
+    // ---- literal runs are independent of everything in this batch: short ones go one lane group each
+    //      (LG::kRuns at a time), long ones take the whole warp, two at a time
     {
-        u32 k = 0;
-        for (; k + 1 < nb; k += 2) {
-            const SeqDesc d0 = desc[k], d1 = desc[k + 1];
-            lanes_copy_rows2<W>(dst + d0.b, lits + d0.a, d0.c, dst + d1.b, lits + d1.a, d1.c);
+        const bool l_long = act && lit_len > LG::kMaxBytes;
+        const u32 shorts = W::ballot(act && lit_len != 0 && !l_long);
+        u32 longs = W::ballot(l_long);
+        for (u32 k0 = 0; k0 < nb; k0 += LG::kRuns) {
+            if (((shorts >> k0) & ((1u << LG::kRuns) - 1)) == 0) continue;
+            const u32 k = k0 + sub;
+            const SeqDesc d0 = desc[k];
+            const u32 n = (k < nb && d0.c <= LG::kMaxBytes) ? d0.c : 0u;
+            lanes_copy_groups<W>(dst + d0.b, lits + d0.a, n);
         }
-        if (k < nb) { const SeqDesc d0 = desc[k]; lanes_copy_rows<W>(dst + d0.b, lits + d0.a, d0.c); }
+        while (longs) {
+            const u32 k1 = ctz32(longs); longs &= longs - 1;
+            const SeqDesc d0 = desc[k1];
+            if (longs) {
+                const u32 k2 = ctz32(longs); longs &= longs - 1;
+                const SeqDesc d1 = desc[k2];
+                lanes_copy_rows2<W>(dst + d0.b, lits + d0.a, d0.c, dst + d1.b, lits + d1.a, d1.c);
+            } else lanes_copy_rows<W>(dst + d0.b, lits + d0.a, d0.c);
+        }
     }
     W::sync();
-    // matches in order; two neighbours go together when the second one does not read what the first one writes
-    for (u32 k = 0; k < nb; ) {
-        const SeqDesc d = desc[32 + k];
-        const u32 m = d.c, o = d.b;
-        u8* const to = dst + d.a;
-        if (k + 1 < nb && o >= m) {
-            const SeqDesc e = desc[32 + k + 1];
-            // e's source [e.a - e.b, e.a - e.b + e.c) must end at or before d's destination start, and not overlap itself
-            if (e.b >= e.c && e.a - e.b + e.c <= d.a) {
-                lanes_copy_rows2<W>(to, to - o, m, dst + e.a, dst + e.a - e.b, e.c);
-                W::sync();
-                k += 2;
-                continue;
-            }
+    // ---- matches, LG::kRuns sequences per step.  A match is "free" when it is short, does not overlap itself and
+    //      does not read what an earlier match of the same step writes: the free ones go together, one lane group
+    //      each; the others follow one by one in order.  (A match never reads the destination of a later one: its
+    //      source ends before its own destination does.)
+    const u32 mdst = opos + lit_len, msrc = mdst - off;
+    bool clash = false;
+    for (u32 j = 1; j < LG::kRuns; ++j) {
+        const u32 pd = W::shfl(mdst, (lane - j) & (L - 1)), pm = W::shfl(ml, (lane - j) & (L - 1));
+        if ((lane & (LG::kRuns - 1)) >= j && msrc < pd + pm && pd < msrc + ml) clash = true;
+    }
+    const u32 held = W::ballot(act && ml != 0 && !(ml <= LG::kMaxBytes && off >= ml && !clash));
+    for (u32 k0 = 0; k0 < nb; k0 += LG::kRuns) {
+        const u32 step_mask = ((1u << LG::kRuns) - 1) << k0;
+        if ((~held & step_mask) != 0) {
+            const u32 k = k0 + sub;
+            const SeqDesc d = desc[32 + k];
+            const u32 n = (k < nb && !((held >> k) & 1)) ? d.c : 0u;
+            lanes_copy_groups<W>(dst + d.a, dst + d.a - d.b, n);
+            W::sync();
         }
-        if (o >= m || o >= 4 * L) {
-            // source entirely before the destination of each pass: plain passes, ordered by a barrier
-            for (u32 base = 0; base < m; base += 4 * L) {
-                const u32 part = m - base < 4 * L ? m - base : 4 * L;
-                lanes_copy_rows<W>(to + base, to + base - o, part);
-                if (base + 4 * L < m) W::sync();
-            }
-        } else lanes_match<W>(dst, (long)d.a, o, m);
-        W::sync();
-        k += 1;
+        for (u32 rest = held & step_mask; rest; rest &= rest - 1) {
+            const SeqDesc d = desc[32 + ctz32(rest)];
+            const u32 m = d.c, o = d.b;
+            u8* const to = dst + d.a;
+            if (o >= m || o >= 4 * L) {
+                // source entirely before the destination of each pass: plain passes, ordered by a barrier
+                for (u32 base = 0; base < m; base += 4 * L) {
+                    const u32 part = m - base < 4 * L ? m - base : 4 * L;
+                    lanes_copy_rows<W>(to + base, to + base - o, part);
+                    if (base + 4 * L < m) W::sync();
+                }
+            } else lanes_match<W>(dst, (long)d.a, o, m);
+            W::sync();
+        }
     }
 }
 

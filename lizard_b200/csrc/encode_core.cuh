@@ -212,9 +212,24 @@ template <class W> LZ_HD void emit_streams(const EncStreams& s, const u8* src, b
         }
         // literal runs of the batch
         const u32 cp_len = (act && (!lizv1 || first)) ? r.lit : 0;
-        for (u32 k = 0; k < nb; ++k) {
-            const u32 len0 = W::shfl(cp_len, k), a0 = W::shfl(r.anchor, k), d0 = W::shfl(lit_dst, k);
-            lanes_copy_rows<W>(dl + d0, src + a0, len0);
+        {   // short runs go several at a time (one lane group each), long ones take the whole warp
+            typedef LaneGroups<W> LG;
+            const bool is_long = cp_len > LG::kMaxBytes;
+            const u32 shorts = W::ballot(cp_len != 0 && !is_long);
+            u32 longs = W::ballot(is_long);
+            const u32 sub = lane / LG::kGroup;
+            const u32 short_len = is_long ? 0u : cp_len;
+            for (u32 k0 = 0; k0 < nb; k0 += LG::kRuns) {
+                if (((shorts >> k0) & ((1u << LG::kRuns) - 1)) == 0) continue;
+                const u32 k = k0 + sub;
+                const u32 len0 = W::shfl(short_len, k), a0 = W::shfl(r.anchor, k), d0 = W::shfl(lit_dst, k);
+                lanes_copy_groups<W>(dl + d0, src + a0, len0);
+            }
+            for (; longs; longs &= longs - 1) {
+                const u32 k = ctz32(longs);
+                const u32 len0 = W::shfl(cp_len, k), a0 = W::shfl(r.anchor, k), d0 = W::shfl(lit_dst, k);
+                lanes_copy_rows<W>(dl + d0, src + a0, len0);
+            }
         }
         pl += tl; pf += tf; p16 += t16; p24 += t24;
     }

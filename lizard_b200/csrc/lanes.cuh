@@ -104,6 +104,30 @@ template <class W> LZ_HD void lanes_copy_rows2(u8* __restrict__ dA, const u8* __
     lanes_copy_rows<W>(dB, sB, nB);
 }
 
+// ---- several short runs at once: groups of 8 lanes --------------------------------------------------------------
+// Lane group g (lanes 8g..8g+7) copies its own run of at most 4*8 bytes, all groups in the same instructions: the
+// arguments are per lane (equal within a group).  One load phase, one store phase for up to lanes/8 runs.
+template <class W> struct LaneGroups {
+    static constexpr u32 kGroup = W::kLanes >= 8 ? 8 : W::kLanes;     // lanes per run
+    static constexpr u32 kRuns = W::kLanes / kGroup;                   // runs per step
+    static constexpr u32 kMaxBytes = 4 * kGroup;                       // longest run a step can take
+};
+template <class W> LZ_HD void lanes_copy_groups(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
+{
+    constexpr u32 G = LaneGroups<W>::kGroup;
+    const u32 o = W::lane() & (G - 1);
+    const u8* s = src + o; u8* d = dst + o;
+    u8 b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    if (o < n) b0 = s[0];
+    if (o + G < n) b1 = s[G];
+    if (o + 2 * G < n) b2 = s[2 * G];
+    if (o + 3 * G < n) b3 = s[3 * G];
+    if (o < n) d[0] = b0;
+    if (o + G < n) d[G] = b1;
+    if (o + 2 * G < n) d[2 * G] = b2;
+    if (o + 3 * G < n) d[3 * G] = b3;
+}
+
 // ---- 4-bytes-per-lane copy pieces: one pass moves 4*lanes bytes ------------------------------------------
 LZ_HD u32 ld32u(const u8* p)      // unaligned little-endian load; may touch the aligned words around p only
 {
