@@ -349,14 +349,10 @@ template <class W> LZ_HD void run_batch_copies(u8* dst, const u8* lits, u32 nb, 
             const u32 n = (k < nb && d0.c <= LG::kMaxBytes) ? d0.c : 0u;
             lanes_copy_groups<W>(dst + d0.b, lits + d0.a, n);
         }
-        while (longs) {
-            const u32 k1 = ctz32(longs); longs &= longs - 1;
-            const SeqDesc d0 = desc[k1];
-            if (longs) {
-                const u32 k2 = ctz32(longs); longs &= longs - 1;
-                const SeqDesc d1 = desc[k2];
-                lanes_copy_rows2<W>(dst + d0.b, lits + d0.a, d0.c, dst + d1.b, lits + d1.a, d1.c);
-            } else lanes_copy_rows<W>(dst + d0.b, lits + d0.a, d0.c);
+        for (; longs; longs &= longs - 1) {
+            const SeqDesc d0 = desc[ctz32(longs)];
+            if (d0.c >= kWideMinBytes) lanes_copy_wide<W>(dst + d0.b, lits + d0.a, d0.c, false);
+            else lanes_copy_rows<W>(dst + d0.b, lits + d0.a, d0.c);
         }
     }
     W::sync();
@@ -384,7 +380,8 @@ template <class W> LZ_HD void run_batch_copies(u8* dst, const u8* lits, u32 nb, 
             const SeqDesc d = desc[32 + ctz32(rest)];
             const u32 m = d.c, o = d.b;
             u8* const to = dst + d.a;
-            if (o >= m || o >= 4 * L) {
+            if (m >= kWideMinBytes && o >= wide_min_offset<W>()) lanes_copy_wide<W>(to, to - o, m, true);
+            else if (o >= m || o >= 4 * L) {
                 // source entirely before the destination of each pass: plain passes, ordered by a barrier
                 for (u32 base = 0; base < m; base += 4 * L) {
                     const u32 part = m - base < 4 * L ? m - base : 4 * L;

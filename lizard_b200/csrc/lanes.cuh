@@ -3,6 +3,9 @@
 // semantics), and the CPU test-suite adds EmuLanes (32 coroutines, host_shim.cpp) to run the 32-lane code paths.
 #pragma once
 #include "common.cuh"
+#if !defined(__CUDACC__)
+#include <string.h>
+#endif
 
 namespace lzb {
 
@@ -126,6 +129,75 @@ template <class W> LZ_HD void lanes_copy_groups(u8* __restrict__ dst, const u8* 
     if (o + G < n) d[G] = b1;
     if (o + 2 * G < n) d[2 * G] = b2;
     if (o + 3 * G < n) d[3 * G] = b3;
+}
+
+// ---- 16 bytes per lane: long runs -------------------------------------------------------------------------------
+// The destination is brought to a 16-byte boundary with byte stores, then every lane moves one aligned 16-byte
+// store per pass (512 bytes per warp pass).  The source has an arbitrary byte phase against the destination, equal
+// for all lanes: a lane reads the two aligned 16-byte vectors that straddle its chunk and realigns with funnel
+// shifts.  Only vectors that contain at least one byte of the run are read, so no access leaves the pages the run
+// itself occupies.  `fence` = barrier between passes (needed when the source is data an earlier pass wrote, i.e.
+// a match whose offset is at least one pass + one vector, kWideMinOffset).
+struct Vec16 { u32 w[4]; };
+LZ_HD Vec16 ld_vec16(const u8* p)          // p is 16-byte aligned
+{
+#if defined(__CUDA_ARCH__)
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    Vec16 r; r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w; return r;
+#else
+    Vec16 r; memcpy(&r, p, 16); return r;
+#endif
+}
+LZ_HD void st_vec16(u8* p, u32 a, u32 b, u32 c, u32 d)
+{
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+#else
+    const u32 t[4] = { a, b, c, d }; memcpy(p, t, 16);
+#endif
+}
+LZ_HD u32 funnel_r(u32 lo, u32 hi, u32 bits)   // bits in {0, 8, 16, 24}
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, bits);
+#else
+    return bits ? (lo >> bits) | (hi << (32 - bits)) : lo;
+#endif
+}
+enum : u32 { kWideMinBytes = 64 };
+template <class W> LZ_HD u32 wide_min_offset() { return 16 * W::kLanes + 32; }
+template <class W> LZ_HD void lanes_copy_wide(u8* dst, const u8* src, u32 n, bool fence)
+{
+    const u32 l = W::lane(), L = W::lanes();
+    u32 head = (u32)((16 - ((size_t)dst & 15)) & 15);
+    if (head > n) head = n;
+    for (u32 i = l; i < head; i += L) dst[i] = src[i];
+    dst += head; src += head; n -= head;
+    const u32 chunks = n >> 4;
+    const size_t sa = (size_t)src;
+    const u32 delta = (u32)(sa & 15);
+    const u8* q = src - delta;                                  // aligned; chunk c = source bytes [16c+delta, 16c+delta+16)
+    const u32 ws = delta >> 2, bs = (delta & 3) * 8;
+    if (fence) W::sync();
+    for (u32 base = 0; base < chunks; base += L) {
+        const u32 c = base + l;
+        if (c < chunks) {
+            const Vec16 a = ld_vec16(q + 16 * (size_t)c);
+            Vec16 b = a;
+            if (delta) b = ld_vec16(q + 16 * (size_t)c + 16);   // holds byte 16c+16 <= 16c+delta+15 of the run
+            u32 o0, o1, o2, o3;
+            switch (ws) {
+            case 0:  o0 = funnel_r(a.w[0], a.w[1], bs); o1 = funnel_r(a.w[1], a.w[2], bs); o2 = funnel_r(a.w[2], a.w[3], bs); o3 = funnel_r(a.w[3], b.w[0], bs); break;
+            case 1:  o0 = funnel_r(a.w[1], a.w[2], bs); o1 = funnel_r(a.w[2], a.w[3], bs); o2 = funnel_r(a.w[3], b.w[0], bs); o3 = funnel_r(b.w[0], b.w[1], bs); break;
+            case 2:  o0 = funnel_r(a.w[2], a.w[3], bs); o1 = funnel_r(a.w[3], b.w[0], bs); o2 = funnel_r(b.w[0], b.w[1], bs); o3 = funnel_r(b.w[1], b.w[2], bs); break;
+            default: o0 = funnel_r(a.w[3], b.w[0], bs); o1 = funnel_r(b.w[0], b.w[1], bs); o2 = funnel_r(b.w[1], b.w[2], bs); o3 = funnel_r(b.w[2], b.w[3], bs); break;
+            }
+            st_vec16(dst + 16 * (size_t)c, o0, o1, o2, o3);
+        }
+        if (fence && base + L < chunks) W::sync();
+    }
+    if (fence) W::sync();
+    for (u32 i = 16 * chunks + l; i < n; i += L) dst[i] = src[i];
 }
 
 // ---- 4-bytes-per-lane copy pieces: one pass moves 4*lanes bytes ------------------------------------------
