@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include <cmath>
+#include <cstdio>
 
 namespace lzb {
 
@@ -148,22 +149,27 @@ struct EncodeConfig {
 };
 
 constexpr u32 kEncBigTableBytes = 4u << 18;          // plain 32-bit table for hashLog 18 or multi-inner-block units
-constexpr int kEncMaxWarpsPerSM = 24;
+// Residency: registers allow 28 warps per SM (72 registers/thread), shared memory 26 packed level-10 tables
+// (8.5 KiB each).  The grid therefore runs CTAs of 14 warps, two per SM, where 13 warps keep their hash table in
+// shared memory and the 14th uses the plain table in its global scratch (L1/L2-resident, slower): 28 resident
+// warps per SM turn the 8192-block workload into two full waves instead of three ragged ones.
+constexpr int kEncWarpsPerCta = 14, kEncCtasPerSM = 2, kEncMaxWarpsPerSM = kEncWarpsPerCta * kEncCtasPerSM;
 
-__global__ void __launch_bounds__(32, kEncMaxWarpsPerSM)
-lizard_encode_units_kernel(EncodeBatch b, u32 packed_in_smem, size_t per_warp_bytes)
+__global__ void __launch_bounds__(32 * kEncWarpsPerCta, kEncCtasPerSM)
+lizard_encode_units_kernel(EncodeBatch b, u32 smem_tables, u32 table_bytes, u32 hist_bytes, size_t per_warp_bytes)
 {
     extern __shared__ __align__(16) unsigned char enc_smem[];
-    const u32 lane = threadIdx.x & 31;
-    u8* my = b.scratch + (size_t)blockIdx.x * per_warp_bytes;
+    const u32 lane = threadIdx.x & 31, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    u8* my = b.scratch + ((size_t)blockIdx.x * wpc + wic) * per_warp_bytes;
     EncWork* work = reinterpret_cast<EncWork*>(my);
-    // shared layout: [packed hash table if the level's table fits][4 KiB segment histograms, entropy levels only]
+    // shared layout: [smem_tables packed hash tables][per-warp 4 KiB segment histograms, entropy levels only]
     const LevelParams klp = level_params(b.level);
-    const size_t packed_bytes = packed_in_smem ? hash_packed_bytes(klp.hashLog) : 0;
-    u32* seg_hist = reinterpret_cast<u32*>(enc_smem + packed_bytes);
+    const bool packed_ok = wic < smem_tables;
+    u8* tab = enc_smem + (size_t)wic * table_bytes;
+    u32* seg_hist = reinterpret_cast<u32*>(enc_smem + (size_t)smem_tables * table_bytes + (size_t)wic * hist_bytes);
     HashTable packed, plain;
-    packed.t32 = nullptr; packed.lo = reinterpret_cast<u16*>(enc_smem);
-    packed.hi = reinterpret_cast<u32*>(enc_smem + ((size_t)2 << klp.hashLog));
+    packed.t32 = nullptr; packed.lo = reinterpret_cast<u16*>(tab);
+    packed.hi = reinterpret_cast<u32*>(tab + ((size_t)2 << klp.hashLog));
     plain.t32 = reinterpret_cast<u32*>(my + sizeof(EncWork)); plain.lo = nullptr; plain.hi = nullptr;
     if (lane == 0) work->huf.seg_count = reinterpret_cast<u32 (*)[256]>(seg_hist);
     __syncwarp();
@@ -175,7 +181,7 @@ lizard_encode_units_kernel(EncodeBatch b, u32 packed_in_smem, size_t per_warp_by
         progress_wait(b.progress, unit, lane);
         const u32 len = b.src_len[unit];
         // 17-bit packed entries need every position of the unit below 2^17
-        const HashTable& T = (packed_in_smem && len <= kBlockSize) ? packed : plain;
+        const HashTable& T = (packed_ok && len <= kBlockSize) ? packed : plain;
         const int r = encode_unit<WarpLanes>(b.src_base + b.src_off[unit], len,
                                              b.dst_base + b.dst_off[unit], b.dst_cap[unit], b.level, T, work);
         if (lane == 0) b.result[unit] = r;
@@ -193,42 +199,75 @@ inline int encode_context_init(EncodeConfig& c, int sm_count, int)
     c.per_warp_small = enc_align(sizeof(EncWork) + kEncBigTableBytes);
     c.per_warp_big = c.per_warp_small;
     if (cudaFuncSetAttribute(lizard_encode_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             4096 + (int)hash_packed_bytes(14)) != cudaSuccess) return -1;
+                             227 * 1024) != cudaSuccess) return -1;
     c.max_warps = sm_count * kEncMaxWarpsPerSM;
     c.scratch_bytes = (size_t)c.max_warps * c.per_warp_small;
     return 0;
 }
 
+// Launch shape for a level: warps per CTA, how many of them own a shared-memory table, dynamic shared bytes.
+struct EncodeShape { int warps, smem_tables; size_t table_bytes, hist_bytes, smem; int ctas_per_sm; };
+inline EncodeShape encode_shape(const LevelParams& lp)
+{
+    EncodeShape sh;
+    sh.table_bytes = lp.hashLog <= 14 ? hash_packed_bytes(lp.hashLog) : 0;
+    sh.hist_bytes = lp.huffman ? 4096 : 0;
+    const size_t sm_bytes = 228 * 1024, cta_reserved = 1024, cta_max = 227 * 1024;
+    // Three shapes, picked from measurements (profiles/: shape sweep):
+    //   A. 2 CTAs x 14 warps when at least 12 of the 14 get a shared-memory table (level 10/20-style small tables),
+    //      or when there is no shared-memory table at all (hashLog 18: everything global anyway);
+    //   B. one warp per CTA, every warp on a shared-memory table, when that keeps >= 16 warps resident;
+    //   C. 2 CTAs x 8 warps with as many shared-memory tables as fit (large tables: a few fast warps + global ones).
+    auto tabs_for = [&](int warps, int ctas) -> int {
+        const size_t budget = sm_bytes / ctas < cta_max + cta_reserved ? sm_bytes / ctas - cta_reserved : cta_max;
+        const size_t hist = (size_t)warps * sh.hist_bytes;
+        if (hist > budget) return -1;
+        if (!sh.table_bytes) return 0;
+        int t = (int)((budget - hist) / sh.table_bytes);
+        return t > warps ? warps : t;
+    };
+    EncodeShape best = sh;
+    auto set = [&](int warps, int tabs, int ctas) {
+        best.warps = warps; best.smem_tables = tabs; best.ctas_per_sm = ctas;
+        best.smem = (size_t)tabs * sh.table_bytes + (size_t)warps * sh.hist_bytes;
+    };
+    const int tabs14 = tabs_for(kEncWarpsPerCta, kEncCtasPerSM);
+    int solo = 0;                                                   // shape B: resident single-warp CTAs
+    for (int ctas = kEncMaxWarpsPerSM; ctas >= 1; --ctas) if (tabs_for(1, ctas) >= (sh.table_bytes ? 1 : 0)) { solo = ctas; break; }
+    if (!sh.table_bytes || tabs14 >= 12) set(kEncWarpsPerCta, tabs14 < 0 ? 0 : tabs14, kEncCtasPerSM);
+    else if (solo >= 16) set(1, 1, solo);
+    else {
+        int t8 = tabs_for(8, 2);
+        if (t8 >= 1) set(8, t8, 2);
+        else if (solo >= 1) set(1, 1, solo);
+        else set(kEncWarpsPerCta, 0, kEncCtasPerSM);
+    }
+    return best;
+}
+
 inline cudaError_t encode_launch(const EncodeConfig& c, const EncodeBatch& b, cudaStream_t s, int* launches)
 {
     const LevelParams lp = level_params(b.level);
-    const bool in_smem = lp.hashLog <= 14;
-    const size_t smem = (lp.huffman ? 4096 : 0) + (in_smem ? hash_packed_bytes(lp.hashLog) : 0);
+    EncodeShape sh = encode_shape(lp);
+    if (const char* e = getenv("LIZARDB200_ENC_SHAPE")) {           // diagnostics: "warps,tables,ctas"
+        int w = 0, t = 0, k = 0;
+        if (sscanf(e, "%d,%d,%d", &w, &t, &k) == 3 && w >= 1 && w <= kEncWarpsPerCta && t >= 0 && t <= w && k >= 1) {
+            sh.warps = w; sh.smem_tables = sh.table_bytes ? t : 0; sh.ctas_per_sm = k;
+            sh.smem = (size_t)sh.smem_tables * sh.table_bytes + (size_t)w * sh.hist_bytes;
+        }
+    }
     const size_t per_warp = c.per_warp_small;
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lizard_encode_units_kernel, 32, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lizard_encode_units_kernel, 32 * sh.warps, sh.smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > kEncMaxWarpsPerSM) per_sm = kEncMaxWarpsPerSM;
-    {   // All units cost about the same, so the grid runs in waves and a mostly empty last wave is pure loss.
-        // Measured full-wave throughput grows like (warps/SM)^0.75 (profiles/: occupancy sweep), i.e. the time of one
-        // wave like p^0.25: pick the warps/SM that minimises waves x wave-time.
-        int best = per_sm; double best_cost = 1e300;
-        for (int p = per_sm; p >= (per_sm > 12 ? 12 : 1); --p) {
-            const double waves = (double)((b.n_units + (size_t)c.sm_count * p - 1) / ((size_t)c.sm_count * p));
-            const double cost = waves * pow((double)p, 0.25);
-            if (cost < best_cost - 1e-9) { best_cost = cost; best = p; }
-        }
-        per_sm = best;
-    }
-    if (const char* e = getenv("LIZARDB200_ENC_WARPS_PER_SM")) {   // diagnostics: occupancy sweep
-        const int v = atoi(e);
-        if (v >= 1 && v <= kEncMaxWarpsPerSM) per_sm = v;
-    }
-    int grid = c.sm_count * per_sm;
-    if ((u32)grid > b.n_units) grid = (int)b.n_units;
-    if ((size_t)grid * per_warp > c.scratch_bytes) grid = (int)(c.scratch_bytes / per_warp);
-    lizard_encode_units_kernel<<<grid, 32, smem, s>>>(b, in_smem ? 1u : 0u, per_warp);
+    if (per_sm > sh.ctas_per_sm) per_sm = sh.ctas_per_sm;
+    size_t grid = (size_t)c.sm_count * per_sm;
+    const size_t need = (b.n_units + sh.warps - 1) / sh.warps;
+    if (grid > need) grid = need;
+    if (grid * sh.warps * per_warp > c.scratch_bytes) grid = c.scratch_bytes / (per_warp * sh.warps);
+    lizard_encode_units_kernel<<<(unsigned)grid, 32 * sh.warps, sh.smem, s>>>(b, (u32)sh.smem_tables, (u32)sh.table_bytes,
+                                                                            (u32)sh.hist_bytes, per_warp);
     *launches = 1;
     return cudaGetLastError();
 }

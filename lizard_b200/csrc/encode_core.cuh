@@ -508,6 +508,7 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
             const bool s_valid = P + 1 <= mflimit;                 // as a search probe: else it ends the block
             u64 v = 0; u32 h = 0x80000000u | lane;                 // unique key: shares a bucket with nobody
             if (ld_ok) { v = ld5(src + P); h = hash5(v, hl); }
+            if (P + 384 < b1) W::prefetch(src + P + 384);          // the input is walked once, front to back
             const u32 same = W::match_any(h);
             const u32 below = same & lt_mask;
             const u32 tv = ld_ok ? T.get(h, P) : 0u;
@@ -578,6 +579,7 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
                     const bool valid = ip0 + probe_offset(j + 1) <= mflimit;
                     u64 vj = 0; u32 hj = 0x80000000u | lane;
                     if (valid) { vj = ld5(src + Pj); hj = hash5(vj, hl); }
+                    if (Pj + 512 < b1) W::prefetch(src + Pj + 512);
                     const u32 peers = W::match_any(hj);
                     const u32 blw = peers & lt_mask;
                     const u32 plj = blw ? highbit32(blw) : lane;
