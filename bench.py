@@ -31,6 +31,7 @@ BS = 1 << 17
 # clean-state compressed totals of `datagen -g1G -P50` (seed 0), 8192 x 128 KiB, cap = BS-1
 KNOWN_TOTALS_1G = {10: 670259129, 21: 616060194, 41: 385653946}
 ALGO_BYTES_PER_BYTE = None  # computed from the measured ratio: 1 + 1/ratio
+NCU_TRAFFIC_BYTES = {(10, "lizard_encode_units_kernel"): 7.96e9, (10, "lizard_decode_units_kernel"): 3.02e9}
 
 
 def parse_args():
@@ -229,6 +230,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     nbytes = args.size_mib << 20
@@ -329,10 +331,10 @@ def run_ours(args, rank, world, local_rank):
                 raise SystemExit("LizardF_decompress: result %d, out %d, in %d of %d" % (r, so.value, si.value, fs))
             return fs
 
-        for _ in range(2):
+        # warm-up; the timed loop follows immediately (an idle gap lets the GPU drop to its idle clocks and the first
+        # kernel afterwards runs ~10x slower for tens of ms); the result is verified after the timed loop
+        for _ in range(max(args.warmup, 3)):
             frame_size = e2e_step()
-        if not torch.equal(h_back, h_src):
-            raise SystemExit("bench.py: e2e round trip mismatch")
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -342,6 +344,8 @@ def run_ours(args, rank, world, local_rank):
             e2e_step()
         torch.cuda.synchronize()
         e2e = time.perf_counter() - t0
+        if not torch.equal(h_back, h_src):
+            raise SystemExit("bench.py: e2e round trip mismatch")
         L.LizardF_freeDecompressionContext(dctx)
     clocks = sampler.stop()
     link = pcie_probe(torch, dev, h_src) if e2e is not None else None
@@ -376,8 +380,11 @@ def run_ours(args, rank, world, local_rank):
 
     def roof(t_total, kernel):
         ach = algo_per_launch / (t_total / K) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of this
+        # workload (profiles/r01_SUMMARY.md section 3); only known for the level-10 1 GiB launch
+        traffic = NCU_TRAFFIC_BYTES.get((level, kernel)) if nbytes == (1 << 30) else None
         return {"kernel": kernel, "bound": "hbm", "achieved": round(ach, 1), "peak": hbm_peak, "unit": "GB/s",
-                "frac": round(ach / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(ach / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(algo_per_launch), "avg_launch_ms": round(t_total / K * 1e3, 3)}
 
     line = {
