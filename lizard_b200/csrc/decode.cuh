@@ -108,6 +108,19 @@ template <class W> LZ_HD void lanes_match(u8* dst, long op, u32 off, u32 len)
 
 // ---- Huffman stream expansion -----------------------------------------------------------------
 // single-symbol decode of one of the 4 segments by one lane; true when the bitstream ended exactly
+LZ_HD u64 ld64_any(const u8* p)          // unaligned 8-byte little-endian load through aligned 8-byte words
+{
+#if defined(__CUDA_ARCH__)
+    const size_t a = (size_t)p;
+    const u64* q = reinterpret_cast<const u64*>(a & ~(size_t)7);
+    const u32 sh = (u32)(a & 7) * 8;
+    const u64 lo = q[0];
+    if (sh == 0) return lo;
+    return (lo >> sh) | (q[1] << (64 - sh));            // q[1] holds p[8 - (a&7)] .. p[7]: bytes of the same load
+#else
+    return rd_le64(p);
+#endif
+}
 LZ_HD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u16* table, u32 tl, int* init_err)
 {
     BitReader b;
@@ -115,6 +128,27 @@ LZ_HD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u
     *init_err = e;
     if (e < 0) return false;
     long p = 0;
+    // Bulk: same walk as the loop below (reload, then four symbols: HUF_decodeStreamX2, huf_decompress.c:155-176) with
+    // the window fetched by aligned loads and the four bytes stored as one word.  It stops 16 bytes before the start
+    // of the bitstream, where the reload rules change, and leaves a state the exact loop continues from.
+    if (len >= 24) {
+        while (p < count && ((size_t)(out + p) & 3) != 0 && b.ptr >= b.start + 16) {
+            if (bits_reload(b) != kBitsUnfinished) break;
+            out[p++] = (u8)hufx_sym(b, table, tl);
+        }
+        while (p + 4 <= count && b.ptr >= b.start + 16 && b.used <= 64 && ((size_t)(out + p) & 3) == 0) {
+            b.ptr -= b.used >> 3;                          // bits_reload, "ptr >= start + 8" case
+            b.used &= 7;
+            b.win = ld64_any(b.ptr);
+#if defined(__CUDA_ARCH__)
+            if (b.ptr >= b.start + 384 && ((size_t)b.ptr & 127) < 6) asm volatile("prefetch.global.L1 [%0];" :: "l"(b.ptr - 384));
+#endif
+            const u32 s0 = hufx_sym(b, table, tl), s1 = hufx_sym(b, table, tl);
+            const u32 s2 = hufx_sym(b, table, tl), s3 = hufx_sym(b, table, tl);
+            *reinterpret_cast<u32*>(out + p) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+            p += 4;
+        }
+    }
     for (;;) {
         if (bits_reload(b) != kBitsUnfinished) break;
         long k = count - p; if (k > 4) k = 4;
