@@ -64,8 +64,8 @@ enum : u32 {
     kHufHeaderFseLog    = 6,        // MAX_FSE_TABLELOG_FOR_HUFF_HEADER
 };
 
-// Parsers on the hot path.  Levels 10/30 fastSmall, 11/31 fast, 21/22/41/42 priceFast.
-enum Parser : int { kParserFastSmall = 0, kParserFast = 1, kParserPriceFast = 5, kParserUnsupported = -1 };
+// Parsers on the hot path.  Levels 10/30 fastSmall, 11/31 fast, 13-17/34-38 hashChain, 21/22/41/42 priceFast.
+enum Parser : int { kParserFastSmall = 0, kParserFast = 1, kParserHashChain = 3, kParserPriceFast = 5, kParserUnsupported = -1 };
 
 struct LevelParams {
     u32 windowLog;
@@ -75,17 +75,24 @@ struct LevelParams {
     int parser;
     int lizv1;            // 1: LIZv1 codewords, 0: LZ4 codewords
     int huffman;          // 1: Huffman on flags+literals (level >= 30)
+    u32 searchNum;        // hashChain: candidates walked per position
+    u32 chainLog;         // hashChain: log2 of the chain table (contentLog)
 };
 
 // lib/lizard_common.h:234-284 -- rows for the levels this library implements on the GPU.
 LZ_HD LevelParams level_params(int level)
 {
-    LevelParams p = {0, 0, 0, 0, kParserUnsupported, 0, 0};
-    int base = level >= 30 ? level - 20 : level;          // rows 30..49 mirror 10..29 with Huffman on
+    LevelParams p = {0, 0, 0, 0, kParserUnsupported, 0, 0, 0, 0};
+    int base = level >= 30 ? level - 20 : level;          // rows 30..49 mirror 10..29 with Huffman on ...
+    if (level >= 34 && level <= 38) base = level - 21;    // ... except 32-38: 32 is an extra noChain row, 34-38 = 13-17
+    else if (level >= 32 && level <= 33) base = -1;
     p.huffman = level >= 30;
     switch (base) {
     case 10: p.windowLog = 16; p.hashLog = 12; p.parser = kParserFastSmall; break;
     case 11: p.windowLog = 16; p.hashLog = 18; p.parser = kParserFast;      break;
+    case 13: case 14: case 15: case 16: case 17:          // searchNum 2,4,8,16,256; searchLength 5,5,5,4,4
+             p.windowLog = 16; p.hashLog = 18; p.chainLog = 16; p.parser = kParserHashChain;
+             p.searchNum = base == 17 ? 256u : (2u << (base - 13)); p.searchLength = base >= 16 ? 4 : 5; break;
     case 21: p.windowLog = 22; p.hashLog = 14; p.searchLength = 5; p.minMatchLongOff = kMmLongOff;
              p.parser = kParserPriceFast; p.lizv1 = 1; break;
     case 22: p.windowLog = 22; p.hashLog = 18; p.searchLength = 5; p.minMatchLongOff = kMmLongOff;

@@ -142,10 +142,24 @@ LZ_HD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u
             b.win = ld64_any(b.ptr);
 #if defined(__CUDA_ARCH__)
             if (b.ptr >= b.start + 384 && ((size_t)b.ptr & 127) < 6) asm volatile("prefetch.global.L1 [%0];" :: "l"(b.ptr - 384));
-#endif
+            // four table steps on a 2 x 32-bit copy of the window kept left-aligned (<= 7 + 4*12 bits leave it)
+            u32 hi = (u32)(b.win >> 32), lo = (u32)b.win;
+            hi = __funnelshift_l(lo, hi, b.used); lo <<= b.used;
+            const u32 down = 32 - tl;
+            u32 e = table[hi >> down], n = e >> 8, word = e & 255, used = b.used + n;
+            hi = __funnelshift_l(lo, hi, n); lo <<= n;
+            e = table[hi >> down]; n = e >> 8; word |= (e & 255) << 8; used += n;
+            hi = __funnelshift_l(lo, hi, n); lo <<= n;
+            e = table[hi >> down]; n = e >> 8; word |= (e & 255) << 16; used += n;
+            hi = __funnelshift_l(lo, hi, n);
+            e = table[hi >> down]; word |= e << 24; used += e >> 8;
+            b.used = used;
+            *reinterpret_cast<u32*>(out + p) = word;
+#else
             const u32 s0 = hufx_sym(b, table, tl), s1 = hufx_sym(b, table, tl);
             const u32 s2 = hufx_sym(b, table, tl), s3 = hufx_sym(b, table, tl);
             *reinterpret_cast<u32*>(out + p) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+#endif
             p += 4;
         }
     }

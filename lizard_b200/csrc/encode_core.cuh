@@ -623,6 +623,194 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
     emit_last_literals<W>(st, src, anchor, b1);
 }
 
+// ---- hashChain parser (levels 13-17 / 34-38): lib/lizard_parser_hashchain.h ---------------------------------------
+// LZ4HC-style: every position is entered into bucket + chain (the chain stores the distance to the previous position
+// of the same bucket, clamped to the window), a search walks at most searchNum chain links and keeps the longest
+// match, and up to three overlapping candidates are arbitrated before the first one is written.  The control flow is
+// uniform over the warp; lanes share the work of inserting a range of positions (same-bucket groups are replayed in
+// order, as in the priceFast search) and of measuring a candidate (forward / backward extension).
+struct ChainState {
+    u16* chain;          // [1 << chainLog] distance to the previous position of the bucket (<= 65535 = the window)
+    u32  chain_mask;
+    u32  next_insert;    // first position of the unit not yet entered (ctx->nextToUpdate)
+    u32  search_num;
+    u32  mls;            // 5 -> hash5, 4 -> hash4 (Lizard_hashPtr, lizard_compress.c:99-109)
+};
+LZ_HD u32 hc_hash(const u8* p, u32 hl, u32 mls)
+{
+    if (mls == 5) return hash5(ld64(p), hl);
+    return (u32)(ld32(p) * 2654435761U) >> (32 - hl);
+}
+// Lizard_Insert (:13-41): positions [next_insert, upto)
+template <class W, class TT> LZ_HD void hc_insert(const u8* src, const TT& T, u32 hl, u32 max_dist, ChainState& cs, u32 upto)
+{
+    const u32 lane = W::lane(), NL = W::lanes(), bias = kDictSize;
+    for (u32 base = cs.next_insert; base < upto; base += NL) {
+        const u32 P = base + lane;
+        const bool valid = P < upto;
+        const u32 idx = P + bias;
+        u32 h = 0x80000000u | lane;
+        if (valid) h = hc_hash(src + P, hl, cs.mls);
+        const u32 peers = W::match_any(h);
+        u32 below = peers & ((1u << lane) - 1);
+        u32 seen = valid ? T.get(h, P) : 0;
+        while (below) {                                   // earlier lanes of the same bucket, in order
+            const u32 bl = ctz32(below); below &= below - 1;
+            const u32 pb = base + bl + bias;
+            if (seen >= pb || pb >= seen + kMinOffset) seen = pb;
+        }
+        if (valid) {
+            const u32 dist = idx - seen;
+            cs.chain[P & cs.chain_mask] = (u16)(dist > max_dist ? max_dist : dist);
+        }
+        const u32 newval = (seen >= idx || idx >= seen + kMinOffset) ? idx : seen;
+        W::sync();
+        if (valid && highbit32(peers) == lane) T.set(h, newval);
+        W::sync();
+    }
+    cs.next_insert = upto;
+}
+// Lizard_InsertAndFindBestMatch (:45-106); returns the length (0 = none), *ref = match position
+template <class W, class TT> LZ_HD u32 hc_best(const u8* src, const TT& T, u32 hl, u32 max_dist, ChainState& cs,
+                                               u32 ip, const u8* limit, u32* ref)
+{
+    const u32 bias = kDictSize, cur = ip + bias;
+    const u32 low = (bias + max_dist >= cur) ? bias : cur - max_dist;
+    hc_insert<W, TT>(src, T, hl, max_dist, cs, ip);
+    u32 m = T.get(hc_hash(src + ip, hl, cs.mls), ip);
+    u32 tries = cs.search_num, best = 0;
+    const u32 v = ld32(src + ip);
+    while (m < cur && m >= low && tries) {
+        const u32 c = m - bias;
+        tries--;
+        if (ip - c >= kMinOffset && src[c + best] == src[ip + best] && ld32(src + c) == v) {
+            const u32 len = count_match_par<W>(src + ip + kMinMatch, src + c + kMinMatch, limit) + kMinMatch;
+            if (len > best) { best = len; *ref = c; }
+        }
+        const u32 d = cs.chain[c & cs.chain_mask];
+        if (d > m) break;
+        m -= d;
+    }
+    return best;
+}
+// Lizard_InsertAndGetWiderMatch (:109-185): candidates may also grow backwards, down to `floor`
+template <class W, class TT> LZ_HD u32 hc_wider(const u8* src, const TT& T, u32 hl, u32 max_dist, ChainState& cs,
+                                                u32 ip, u32 floor, const u8* limit, u32 longest, u32* ref, u32* start)
+{
+    const u32 bias = kDictSize, cur = ip + bias;
+    const u32 low = (bias + max_dist >= cur) ? bias : cur - max_dist;
+    const u32 lead = ip - floor;
+    hc_insert<W, TT>(src, T, hl, max_dist, cs, ip);
+    u32 m = T.get(hc_hash(src + ip, hl, cs.mls), ip);
+    u32 tries = cs.search_num;
+    const u32 v = ld32(src + ip);
+    while (m < cur && m >= low && tries) {
+        const u32 c = m - bias;
+        tries--;
+        // c - lead + longest >= c + 3 in both call sites (lead = longest - 3), so the probe stays inside the unit
+        if (ip - c >= kMinOffset && src[floor + longest] == src[c - lead + longest] && ld32(src + c) == v) {
+            u32 len = kMinMatch + count_match_par<W>(src + ip + kMinMatch, src + c + kMinMatch, limit);
+            const u32 back = extend_back_par<W>(src, ip, c, floor);
+            len += back;
+            if (len > longest) { longest = len; *ref = c - back; *start = ip - back; }
+        }
+        const u32 d = cs.chain[c & cs.chain_mask];
+        if (d > m) break;
+        m -= d;
+    }
+    return longest;
+}
+// Lizard_compress_hashChain (:188-369).  a = the match about to be written, b / c = the later candidates.
+template <class W, class TT> LZ_HD_COLD void parse_hash_chain(const ParseCtx<TT>& c, u32 b0, u32 b1, EncStreams& st, ChainState& cs)
+{
+    const u8* const src = c.src;
+    const TT T = c.T;
+    const u32 hl = c.hash_log;
+    const u32 max_dist = (1u << c.window_log) - 1;
+    const int kOpt = 18;                                     // OPTIMAL_ML = (ML_MASK_LZ4 - 1) + MINMATCH
+    u32 anchor = b0;
+    if (b1 - b0 > kMfLimit + 1) {
+        const u32 mflimit = b1 - kMfLimit;
+        const u8* const matchlimit = src + b1 - kLastLiterals;
+        u32 ip = b0 + 1;
+        int la = 0, lb = 0, lc = 0, l0 = 0;
+        u32 ra = 0, sb = 0, rb = 0, sc = 0, rc = 0, s0 = 0, r0 = 0;
+        while (ip < mflimit) {
+            la = (int)hc_best<W, TT>(src, T, hl, max_dist, cs, ip, matchlimit, &ra);
+            if (!la) { ip++; continue; }
+            s0 = ip; r0 = ra; l0 = la;
+            bool again2 = true;                               // _Search2
+            while (again2) {
+                again2 = false;
+                lb = (ip + (u32)la < mflimit) ? (int)hc_wider<W, TT>(src, T, hl, max_dist, cs, ip + (u32)la - 2, ip + 1, matchlimit, (u32)la, &rb, &sb) : la;
+                if (lb == la) { emit_lz4<W>(st, src, anchor, ip, (u32)la, ip - ra); ip += (u32)la; anchor = ip; break; }
+                if (s0 < ip && sb < ip + (u32)l0) { ip = s0; ra = r0; la = l0; }
+                if ((int)(sb - ip) < 3) { la = lb; ip = sb; ra = rb; again2 = true; continue; }
+                bool again3 = true;                           // _Search3
+                while (again3) {
+                    again3 = false;
+                    if ((int)(sb - ip) < kOpt) {
+                        int keep = la > kOpt ? kOpt : la;
+                        if ((long)ip + keep > (long)sb + lb - (int)kMinMatch) {
+                            keep = (int)(sb - ip) + lb - (int)kMinMatch;
+                            if (keep < (int)kMinMatch) { emit_lz4<W>(st, src, anchor, ip, (u32)la, ip - ra); ip += (u32)la; anchor = ip; break; }
+                        }
+                        const int shift = keep - (int)(sb - ip);
+                        if (shift > 0) { sb += (u32)shift; rb += (u32)shift; lb -= shift; }
+                    }
+                    lc = (sb + (u32)lb < mflimit) ? (int)hc_wider<W, TT>(src, T, hl, max_dist, cs, sb + (u32)lb - 3, sb, matchlimit, (u32)lb, &rc, &sc) : lb;
+                    if (lc == lb) {                            // two sequences
+                        if (sb < ip + (u32)la) la = (int)(sb - ip);
+                        emit_lz4<W>(st, src, anchor, ip, (u32)la, ip - ra); ip += (u32)la; anchor = ip;
+                        ip = sb;
+                        emit_lz4<W>(st, src, anchor, ip, (u32)lb, ip - rb); ip += (u32)lb; anchor = ip;
+                        break;
+                    }
+                    if (sc < ip + (u32)la + 3) {               // no room for b
+                        if (sc >= ip + (u32)la) {              // write a; b is dropped or trimmed, c becomes a
+                            if (sb < ip + (u32)la) {
+                                const int shift = (int)(ip + (u32)la - sb);
+                                sb += (u32)shift; rb += (u32)shift; lb -= shift;
+                                if (lb < (int)kMinMatch) { sb = sc; rb = rc; lb = lc; }
+                            }
+                            emit_lz4<W>(st, src, anchor, ip, (u32)la, ip - ra); ip += (u32)la; anchor = ip;
+                            ip = sc; ra = rc; la = lc;
+                            s0 = sb; r0 = rb; l0 = lb;
+                            again2 = true;
+                            break;
+                        }
+                        sb = sc; rb = rc; lb = lc;
+                        again3 = true;
+                        continue;
+                    }
+                    if (sb < ip + (u32)la) {                   // three ascending candidates: write the first
+                        if ((int)(sb - ip) < 15) {             // ML_MASK_LZ4
+                            if (la > kOpt) la = kOpt;
+                            if ((long)ip + la > (long)sb + lb - (int)kMinMatch) {
+                                la = (int)(sb - ip) + lb - (int)kMinMatch;
+                                if (la < (int)kMinMatch) {
+                                    emit_lz4<W>(st, src, anchor, ip, (u32)la, ip - ra); ip += (u32)la; anchor = ip;
+                                    ip = sc; ra = rc; la = lc;
+                                    s0 = sb; r0 = rb; l0 = lb;
+                                    again2 = true;
+                                    break;
+                                }
+                            }
+                            const int shift = la - (int)(sb - ip);
+                            if (shift > 0) { sb += (u32)shift; rb += (u32)shift; lb -= shift; }
+                        } else la = (int)(sb - ip);
+                    }
+                    emit_lz4<W>(st, src, anchor, ip, (u32)la, ip - ra); ip += (u32)la; anchor = ip;
+                    ip = sb; ra = rb; la = lb;
+                    sb = sc; rb = rc; lb = lc;
+                    again3 = true;
+                }
+            }
+        }
+    }
+    emit_last_literals<W>(st, src, anchor, b1);
+}
+
 // Lizard_compress_priceFast with the no-match run probed W::lanes() consecutive positions at a time.
 // Per position the reference (lizard_parser_pricefast.h:158-173) tests the repeat offset first, then the
 // bucket's candidate, then conditionally refreshes the bucket.  last_off is constant during a no-match run,
@@ -937,6 +1125,7 @@ template <class W> LZ_HD int write_block(const EncStreams& s, const u8* src, con
 
 struct EncWork {                 // per-warp global scratch
     SeqRec seq[kBlockSize / kMinMatch + 8];   // a sequence consumes >= 4 input bytes
+    u16 chain[1u << 16];         // hashChain levels: chain table (contentLog 16)
     u8 lits[kBlockSizePad];      // flags / literals streams, only when an entropy stage follows
     u8 flags[kBlockSizePad];
     EncHufWork huf;
@@ -957,13 +1146,15 @@ template <class W, class TT> LZ_HD int encode_unit_t(const u8* src, u32 src_size
     if (wr) dst[0] = (u8)level;
     op = 1;
     ParseCtx<TT> pc = { src, T, lp.hashLog, lp.windowLog };
+    ChainState cs = { work->chain, (1u << (lp.chainLog ? lp.chainLog : 16)) - 1, 0, lp.searchNum, lp.searchLength };
     u32 pos = 0;
     while (pos < src_size) {
         const u32 part = src_size - pos < kBlockSize ? src_size - pos : kBlockSize;
         EncStreams s;
         s.rec = work->seq; s.nseq = 0;
         s.nl = s.nf = s.n16 = s.n24 = 0; s.tail_anchor = pos; s.tail_len = 0;
-        if (lp.parser == kParserPriceFast) parse_price_fast_par<W, TT>(pc, pos, pos + part, s, lp.minMatchLongOff);
+        if (lp.parser == kParserHashChain) parse_hash_chain<W, TT>(pc, pos, pos + part, s, cs);
+        else if (lp.parser == kParserPriceFast) parse_price_fast_par<W, TT>(pc, pos, pos + part, s, lp.minMatchLongOff);
         else if (W::kLanes >= 4) parse_fast_win<W, TT>(pc, pos, pos + part, s);
         else parse_fast_par<W, TT>(pc, pos, pos + part, s);
         W::sync();

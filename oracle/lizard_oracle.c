@@ -745,15 +745,20 @@ size_t oracle_HUF_compress(void* dstv, size_t cap, const void* srcv, size_t n)
 /* =====================================================================================================
  * Block encoder
  * =================================================================================================== */
-typedef struct { int window_log, hash_log, pricefast, lizv1, huffman; u32 mm_long; } o_level;
+typedef struct { int window_log, hash_log, pricefast, lizv1, huffman; u32 mm_long; int chain_log, search_num, search_len; } o_level;
 
 static int o_level_get(int level, o_level* L)
 {   /* lib/lizard_common.h:234-284, rows on the hot path */
     int b = level >= 30 ? level - 20 : level;
+    if (level >= 34 && level <= 38) b = level - 21;          /* rows 34-38 mirror 13-17 (32 is an extra noChain row) */
     memset(L, 0, sizeof *L); L->huffman = level >= 30;
     switch (b) {
     case 10: L->window_log = 16; L->hash_log = 12; return 1;
     case 11: L->window_log = 16; L->hash_log = 18; return 1;
+    case 13: case 14: case 15: case 16: case 17: {   /* hashChain rows: searchNum 2,4,8,16,256; searchLength 5,5,5,4,4 */
+        static const int snum[5] = { 2, 4, 8, 16, 256 }, slen[5] = { 5, 5, 5, 4, 4 };
+        L->window_log = 16; L->hash_log = 18; L->chain_log = 16; L->search_num = snum[b - 13]; L->search_len = slen[b - 13];
+        return 1; }
     case 21: L->window_log = 22; L->hash_log = 14; L->pricefast = 1; L->lizv1 = 1; L->mm_long = 16; return 1;
     case 22: L->window_log = 22; L->hash_log = 18; L->pricefast = 1; L->lizv1 = 1; L->mm_long = 16; return 1;
     default: return 0;
@@ -763,6 +768,7 @@ static int o_level_get(int level, o_level* L)
 typedef struct {
     const u8* base;                 /* base[0] is the first byte of the call */
     u32* table; o_level L;
+    u32* chain; u32 next_insert;    /* hashChain: distance to the previous position of the same bucket; first index not yet inserted */
     u8 *lits, *flags, *o16, *o24;   /* stream write cursors */
     u8 *lits0, *flags0, *o160, *o240;
     u32 last_off;
@@ -859,6 +865,154 @@ static void o_parse_fast(o_enc* e, const u8* ip, const u8* const iend)
         ip++;
     }
 tail:
+    memcpy(e->lits, anchor, (size_t)(iend - anchor)); e->lits += iend - anchor;
+}
+
+/* ---- hashChain parser (levels 13-17 / 34-38) ---------------------------------------------------------------
+ * lib/lizard_parser_hashchain.h.  Indices are relative to the virtual base (first byte of the call = O_BIAS).
+ * noDict only: dictLimit == lowLimit == O_BIAS, so the external-dictionary branches are never taken. */
+static u32 o_hc_hash(const o_enc* e, const u8* p)
+{   /* Lizard_hashPtr, lizard_compress.c:99-109: searchLength 5 -> hash5, 4 -> hash4 (:85-89) */
+    if (e->L.search_len == 5) return o_hash(p, (u32)e->L.hash_log);
+    return (u32)(rd32(p) * 2654435761U) >> (32 - e->L.hash_log);
+}
+/* lizard_parser_hashchain.h:13-41: enter every position below `upto` into bucket + chain */
+static void o_hc_insert(o_enc* e, u32 upto)
+{
+    const u8* const vbase = e->base - O_BIAS;
+    const u32 cmask = (1u << e->L.chain_log) - 1, maxd = (1u << e->L.window_log) - 1;
+    u32 i;
+    for (i = e->next_insert; i < upto; ++i) {
+        u32* slot = &e->table[o_hc_hash(e, vbase + i)];
+        u32 dist = i - *slot;
+        e->chain[i & cmask] = dist > maxd ? maxd : dist;
+        if (*slot >= i || i >= *slot + 8) *slot = i;
+    }
+    e->next_insert = upto;               /* assigned unconditionally (:40) */
+}
+/* lizard_parser_hashchain.h:45-106 */
+static size_t o_hc_best(o_enc* e, const u8* ip, const u8* lim, const u8** ref)
+{
+    const u8* const vbase = e->base - O_BIAS;
+    const u32 cmask = (1u << e->L.chain_log) - 1, maxd = (1u << e->L.window_log) - 1;
+    const u32 cur = (u32)(ip - vbase);
+    const u32 low = (O_BIAS + maxd >= cur) ? O_BIAS : cur - maxd;
+    int tries = e->L.search_num; size_t best = 0; u32 m, d;
+    o_hc_insert(e, cur);
+    m = e->table[o_hc_hash(e, ip)];
+    while (m < cur && m >= low && tries) {
+        const u8* c = vbase + m;
+        tries--;
+        if ((u32)(ip - c) >= 8 && c[best] == ip[best] && rd32(c) == rd32(ip)) {
+            size_t len = o_count(ip + 4, c + 4, lim) + 4;
+            if (len > best) { best = len; *ref = c; }
+        }
+        d = e->chain[m & cmask];
+        if (d > m) break;
+        m -= d;
+    }
+    return best;
+}
+/* lizard_parser_hashchain.h:109-185: candidates may also grow backwards, down to `floor` */
+static int o_hc_wider(o_enc* e, const u8* ip, const u8* floor, const u8* lim, int longest, const u8** ref, const u8** start)
+{
+    const u8* const vbase = e->base - O_BIAS;
+    const u8* const first = e->base;
+    const u32 cmask = (1u << e->L.chain_log) - 1, maxd = (1u << e->L.window_log) - 1;
+    const u32 cur = (u32)(ip - vbase);
+    const u32 low = (O_BIAS + maxd >= cur) ? O_BIAS : cur - maxd;
+    const long lead = (long)(ip - floor);
+    int tries = e->L.search_num; u32 m, d;
+    o_hc_insert(e, cur);
+    m = e->table[o_hc_hash(e, ip)];
+    while (m < cur && m >= low && tries) {
+        const u8* c = vbase + m;
+        tries--;
+        if ((u32)(ip - c) >= 8 && floor[longest] == (c - lead)[longest] && rd32(c) == rd32(ip)) {
+            int len = 4 + (int)o_count(ip + 4, c + 4, lim), back = 0;
+            while (ip + back > floor && c + back > first && ip[back - 1] == c[back - 1]) back--;
+            len -= back;
+            if (len > longest) { longest = len; *ref = c + back; *start = ip + back; }
+        }
+        d = e->chain[m & cmask];
+        if (d > m) break;
+        m -= d;
+    }
+    return longest;
+}
+/* lizard_parser_hashchain.h:188-369: up to three overlapping candidates (a, b, c) are kept in flight and trimmed
+ * against each other before the first one is written */
+#define O_HC_OPT 18          /* OPTIMAL_ML = (ML_MASK_LZ4 - 1) + MINMATCH, :3 */
+static void o_parse_hashchain(o_enc* e, const u8* ip, const u8* const iend)
+{
+    const u8* const mflimit = iend - 20; const u8* const matchlimit = iend - 16; const u8* anchor = ip;
+    /* MFLIMIT = WILDCOPYLENGTH + MINMATCH = 20, LASTLITERALS = 16 (lizard_common.h:72-79) */
+    int la, lb, lc, l0; const u8 *ra = 0, *sb = 0, *rb = 0, *sc = 0, *rc = 0, *s0, *r0;
+    ip++;
+    while (ip < mflimit) {
+        la = (int)o_hc_best(e, ip, matchlimit, &ra);
+        if (!la) { ip++; continue; }
+        s0 = ip; r0 = ra; l0 = la;
+    second:
+        lb = (ip + la < mflimit) ? o_hc_wider(e, ip + la - 2, ip + 1, matchlimit, la, &rb, &sb) : la;
+        if (lb == la) { o_emit_lz4(e, &ip, &anchor, (size_t)la, ra); continue; }
+        if (s0 < ip && sb < ip + l0) { ip = s0; ra = r0; la = l0; }
+        if (sb - ip < 3) { la = lb; ip = sb; ra = rb; goto second; }
+    third:
+        if (sb - ip < O_HC_OPT) {
+            int keep = la > O_HC_OPT ? O_HC_OPT : la, shift;
+            if (ip + keep > sb + lb - 4) {
+                keep = (int)(sb - ip) + lb - 4;
+                if (keep < 4) { o_emit_lz4(e, &ip, &anchor, (size_t)la, ra); continue; }
+            }
+            shift = keep - (int)(sb - ip);
+            if (shift > 0) { sb += shift; rb += shift; lb -= shift; }
+        }
+        lc = (sb + lb < mflimit) ? o_hc_wider(e, sb + lb - 3, sb, matchlimit, lb, &rc, &sc) : lb;
+        if (lc == lb) {
+            if (sb < ip + la) la = (int)(sb - ip);
+            o_emit_lz4(e, &ip, &anchor, (size_t)la, ra);
+            ip = sb;
+            o_emit_lz4(e, &ip, &anchor, (size_t)lb, rb);
+            continue;
+        }
+        if (sc < ip + la + 3) {
+            if (sc >= ip + la) {
+                if (sb < ip + la) {
+                    int shift = (int)(ip + la - sb);
+                    sb += shift; rb += shift; lb -= shift;
+                    if (lb < 4) { sb = sc; rb = rc; lb = lc; }
+                }
+                o_emit_lz4(e, &ip, &anchor, (size_t)la, ra);
+                ip = sc; ra = rc; la = lc;
+                s0 = sb; r0 = rb; l0 = lb;
+                goto second;
+            }
+            sb = sc; rb = rc; lb = lc;
+            goto third;
+        }
+        if (sb < ip + la) {
+            if (sb - ip < 15) {
+                int shift;
+                if (la > O_HC_OPT) la = O_HC_OPT;
+                if (ip + la > sb + lb - 4) {
+                    la = (int)(sb - ip) + lb - 4;
+                    if (la < 4) {
+                        o_emit_lz4(e, &ip, &anchor, (size_t)la, ra);
+                        ip = sc; ra = rc; la = lc;
+                        s0 = sb; r0 = rb; l0 = lb;
+                        goto second;
+                    }
+                }
+                shift = la - (int)(sb - ip);
+                if (shift > 0) { sb += shift; rb += shift; lb -= shift; }
+            } else la = (int)(sb - ip);
+        }
+        o_emit_lz4(e, &ip, &anchor, (size_t)la, ra);
+        ip = sb; ra = rb; la = lb;
+        sb = sc; rb = rc; lb = lc;
+        goto third;
+    }
     memcpy(e->lits, anchor, (size_t)(iend - anchor)); e->lits += iend - anchor;
 }
 
@@ -982,17 +1136,19 @@ int oracle_Lizard_compress(const char* source, char* dest, int src_size, int max
     if (!o_level_get(level, &e.L) || src_size < 0 || max_dst < 1) return 0;
     e.base = ip;
     e.table = (u32*)calloc((size_t)1 << e.L.hash_log, 4);
+    if (e.L.search_num) { e.chain = (u32*)malloc((size_t)4 << e.L.chain_log); memset(e.chain, 1, (size_t)4 << e.L.chain_log); e.next_insert = O_BIAS; }
     e.lits0 = (u8*)malloc(4 * (size_t)O_BLOCK_PAD + O_BLOCK_PAD + 1024);
     e.flags0 = e.lits0 + O_BLOCK_PAD; e.o160 = e.flags0 + O_BLOCK_PAD; e.o240 = e.o160 + O_BLOCK_PAD; e.huf_tmp = e.o240 + O_BLOCK_PAD;
     *op++ = (u8)level;
     while (left > 0 && ok) {
         int part = left < (int)O_BLOCK ? left : (int)O_BLOCK;
         e.lits = e.lits0; e.flags = e.flags0; e.o16 = e.o160; e.o24 = e.o240; e.last_off = 0;
-        if (e.L.pricefast) o_parse_pricefast(&e, ip, ip + part); else o_parse_fast(&e, ip, ip + part);
+        if (e.L.search_num) o_parse_hashchain(&e, ip, ip + part);
+        else if (e.L.pricefast) o_parse_pricefast(&e, ip, ip + part); else o_parse_fast(&e, ip, ip + part);
         if (o_write_block(&e, ip, (u32)part, &op, oend)) ok = 0;
         ip += part; left -= part;
     }
-    free(e.table); free(e.lits0);
+    free(e.table); free(e.lits0); free(e.chain);
     return ok ? (int)(op - (u8*)dest) : 0;
 }
 

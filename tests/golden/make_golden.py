@@ -38,7 +38,7 @@ inputs = [{"kind": "datagen", "size": 4 << 20, "pct": 50, "seed": 0},
           {"kind": "pattern", "size": 70001}]
 for spec in inputs:
     data = make_input(spec)
-    for level in (10, 11, 21, 22, 30, 31, 41, 42):
+    for level in (10, 11, 13, 16, 21, 22, 30, 31, 34, 41, 42):
         c = refs.ref_compress(ref, data, level)
         out["compress"].append({"input": spec, "level": level, "mode": "single", "size": len(c),
                                 "sha256": hashlib.sha256(c).hexdigest()})
