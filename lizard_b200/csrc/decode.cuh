@@ -52,7 +52,7 @@ __device__ __forceinline__ void progress_wait(const Progress& pg, u32 unit, u32 
 __device__ __forceinline__ void progress_done(const Progress& pg, u32 unit, u32 lane)
 {
     if (pg.done_count && lane == 0) {
-        __threadfence();
+        __threadfence_system();                        // the unit's result may live in pinned host memory
         const u32 c = unit / pg.chunk_units;
         const u32 first = c * pg.chunk_units;
         const u32 cnt = (pg.n_units - first < pg.chunk_units) ? pg.n_units - first : pg.chunk_units;

@@ -223,18 +223,18 @@ template <class W> LZ_HD void emit_streams(const EncStreams& s, const u8* src, b
                 if (((shorts >> k0) & ((1u << LG::kRuns) - 1)) == 0) continue;
                 const u32 k = k0 + sub;
                 const u32 len0 = W::shfl(short_len, k), a0 = W::shfl(r.anchor, k), d0 = W::shfl(lit_dst, k);
-                lanes_copy_groups<W>(dl + d0, src + a0, len0);
+                lanes_copy_groups<W, true>(dl + d0, src + a0, len0);
             }
             for (; longs; longs &= longs - 1) {
                 const u32 k = ctz32(longs);
                 const u32 len0 = W::shfl(cp_len, k), a0 = W::shfl(r.anchor, k), d0 = W::shfl(lit_dst, k);
-                if (len0 >= kWideMinBytes) lanes_copy_wide<W>(dl + d0, src + a0, len0, false);
-                else lanes_copy_rows<W>(dl + d0, src + a0, len0);
+                if (len0 >= kWideMinBytes) lanes_copy_wide<W, true>(dl + d0, src + a0, len0, false);
+                else lanes_copy_rows<W, true>(dl + d0, src + a0, len0);
             }
         }
         pl += tl; pf += tf; p16 += t16; p24 += t24;
     }
-    lanes_copy_wide<W>(dl + pl, src + s.tail_anchor, s.tail_len, false);
+    lanes_copy_wide<W, true>(dl + pl, src + s.tail_anchor, s.tail_len, false);
     W::sync();
 }
 

@@ -229,11 +229,13 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
     }
     u8* dtab = (u8*)c.d_tab.p;
     const u64* d_in_off = (const u64*)dtab; const u64* d_out_off = d_in_off + n;
-    const u32* d_in_len = (const u32*)(d_out_off + n); const u32* d_out_cap = d_in_len + n; int* d_res = (int*)(d_out_cap + n);
+    const u32* d_in_len = (const u32*)(d_out_off + n); const u32* d_out_cap = d_in_len + n;
     if (cudaMemcpyAsync(dtab, c.pin_tab.p, tab_bytes, cudaMemcpyHostToDevice, c.s_in) != cudaSuccess) return -1;
     cudaEventRecord(sp.tables_ready, c.s_in);
     cudaStreamWaitEvent(c.stream, sp.tables_ready, 0);
-    if (launch_decode(c, c.d_in.p, d_in_off, d_in_len, c.d_out.p, d_out_off, d_out_cap, d_res, (u32)n, c.stream, &sp.pg) != LIZARDB200_OK) return -1;
+    // results go straight to pinned host memory (4-byte posted writes, fenced before the chunk's done flag): the host
+    // then needs no copy + synchronize between a chunk's flag and its output copy, and the output copies queue back to back
+    if (launch_decode(c, c.d_in.p, d_in_off, d_in_len, c.d_out.p, d_out_off, d_out_cap, (int*)t_res, (u32)n, c.stream, &sp.pg) != LIZARDB200_OK) return -1;
     {   // input chunks: [first block start, last block end) widened to 128-byte lines so that a cache line shared
         // with the next chunk's first unit is final the first time an SM touches it
         size_t copied_to = 0;
@@ -252,8 +254,6 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
         const size_t first = k * per_chunk, last = (k + 1 == nchunks ? n : first + per_chunk) - 1;
         if (!wait_chunk(c, &sp.h_done[k])) { failed = true; break; }
         tr.mark("decode: chunk done", (long)k);
-        cudaMemcpyAsync((void*)(t_res + first), d_res + first, (last - first + 1) * 4, cudaMemcpyDeviceToHost, c.s_out);
-        if (cudaStreamSynchronize(c.s_out) != cudaSuccess) { failed = true; break; }
         // copy back exactly what was produced: contiguous up to the end of the last good block of the chunk
         size_t lo = blocks[first].dst_pos, hi = lo;
         for (size_t i = first; i <= last; ++i) { sizes_out[i] = t_res[i]; if (t_res[i] > 0) hi = blocks[i].dst_pos + (size_t)t_res[i]; }

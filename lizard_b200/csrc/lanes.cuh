@@ -50,6 +50,15 @@ struct WarpLanes {
 };
 #endif
 
+// store with an optional streaming (evict-first) hint: data that this kernel will not read again should not push the
+// input window out of L2
+template <bool kStream> LZ_HD void st_u8(u8* p, u8 v)
+{
+#if defined(__CUDA_ARCH__)
+    if (kStream) { __stcs(p, v); return; }
+#endif
+    *p = v;
+}
 template <class W> LZ_HD void lanes_copy(u8* dst, const u8* src, u32 n)
 {
     for (u32 i = W::lane(); i < n; i += W::lanes()) dst[i] = src[i];
@@ -60,16 +69,16 @@ template <class W> LZ_HD void lanes_copy(u8* dst, const u8* src, u32 n)
 // stores, so a pass exposes one memory latency; every load/store instruction of the warp touches one contiguous
 // run of bytes (1-2 sectors).  No alignment requirements, which matters because literal runs and matches start
 // at arbitrary byte positions.  The source must not overlap the bytes written by the same pass.
-template <class W> LZ_HD void lanes_copy_rows(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
+template <class W, bool kStream = false> LZ_HD void lanes_copy_rows(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
 {
     const u32 l = W::lane(), L = W::lanes();
     const u8* s = src + l; u8* d = dst + l;
-    if (n <= L) { if (l < n) d[0] = s[0]; return; }              // most runs are shorter than one row
+    if (n <= L) { if (l < n) st_u8<kStream>(d, s[0]); return; }              // most runs are shorter than one row
     if (n <= 2 * L) {
         u8 b0 = s[0], b1 = 0;
         if (l + L < n) b1 = s[L];
-        d[0] = b0;
-        if (l + L < n) d[L] = b1;
+        st_u8<kStream>(d, b0);
+        if (l + L < n) st_u8<kStream>(d + L, b1);
         return;
     }
     for (u32 base = 0; base < n; base += 4 * L, s += 4 * L, d += 4 * L) {
@@ -79,10 +88,10 @@ template <class W> LZ_HD void lanes_copy_rows(u8* __restrict__ dst, const u8* __
         if (l + L < r) b1 = s[L];
         if (l + 2 * L < r) b2 = s[2 * L];
         if (l + 3 * L < r) b3 = s[3 * L];
-        if (l < r) d[0] = b0;
-        if (l + L < r) d[L] = b1;
-        if (l + 2 * L < r) d[2 * L] = b2;
-        if (l + 3 * L < r) d[3 * L] = b3;
+        if (l < r) st_u8<kStream>(d, b0);
+        if (l + L < r) st_u8<kStream>(d + L, b1);
+        if (l + 2 * L < r) st_u8<kStream>(d + 2 * L, b2);
+        if (l + 3 * L < r) st_u8<kStream>(d + 3 * L, b3);
     }
 }
 
@@ -115,7 +124,7 @@ template <class W> struct LaneGroups {
     static constexpr u32 kRuns = W::kLanes / kGroup;                   // runs per step
     static constexpr u32 kMaxBytes = 4 * kGroup;                       // longest run a step can take
 };
-template <class W> LZ_HD void lanes_copy_groups(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
+template <class W, bool kStream = false> LZ_HD void lanes_copy_groups(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
 {
     constexpr u32 G = LaneGroups<W>::kGroup;
     const u32 o = W::lane() & (G - 1);
@@ -125,10 +134,10 @@ template <class W> LZ_HD void lanes_copy_groups(u8* __restrict__ dst, const u8* 
     if (o + G < n) b1 = s[G];
     if (o + 2 * G < n) b2 = s[2 * G];
     if (o + 3 * G < n) b3 = s[3 * G];
-    if (o < n) d[0] = b0;
-    if (o + G < n) d[G] = b1;
-    if (o + 2 * G < n) d[2 * G] = b2;
-    if (o + 3 * G < n) d[3 * G] = b3;
+    if (o < n) st_u8<kStream>(d, b0);
+    if (o + G < n) st_u8<kStream>(d + G, b1);
+    if (o + 2 * G < n) st_u8<kStream>(d + 2 * G, b2);
+    if (o + 3 * G < n) st_u8<kStream>(d + 3 * G, b3);
 }
 
 // ---- 16 bytes per lane: long runs -------------------------------------------------------------------------------
@@ -148,9 +157,10 @@ LZ_HD Vec16 ld_vec16(const u8* p)          // p is 16-byte aligned
     Vec16 r; memcpy(&r, p, 16); return r;
 #endif
 }
-LZ_HD void st_vec16(u8* p, u32 a, u32 b, u32 c, u32 d)
+template <bool kStream = false> LZ_HD void st_vec16(u8* p, u32 a, u32 b, u32 c, u32 d)
 {
 #if defined(__CUDA_ARCH__)
+    if (kStream) { __stcs(reinterpret_cast<uint4*>(p), make_uint4(a, b, c, d)); return; }
     *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 #else
     const u32 t[4] = { a, b, c, d }; memcpy(p, t, 16);
@@ -166,12 +176,12 @@ LZ_HD u32 funnel_r(u32 lo, u32 hi, u32 bits)   // bits in {0, 8, 16, 24}
 }
 enum : u32 { kWideMinBytes = 64 };
 template <class W> LZ_HD u32 wide_min_offset() { return 16 * W::kLanes + 32; }
-template <class W> LZ_HD void lanes_copy_wide(u8* dst, const u8* src, u32 n, bool fence)
+template <class W, bool kStream = false> LZ_HD void lanes_copy_wide(u8* dst, const u8* src, u32 n, bool fence)
 {
     const u32 l = W::lane(), L = W::lanes();
     u32 head = (u32)((16 - ((size_t)dst & 15)) & 15);
     if (head > n) head = n;
-    for (u32 i = l; i < head; i += L) dst[i] = src[i];
+    for (u32 i = l; i < head; i += L) st_u8<kStream>(dst + i, src[i]);
     dst += head; src += head; n -= head;
     const u32 chunks = n >> 4;
     const size_t sa = (size_t)src;
@@ -192,12 +202,12 @@ template <class W> LZ_HD void lanes_copy_wide(u8* dst, const u8* src, u32 n, boo
             case 2:  o0 = funnel_r(a.w[2], a.w[3], bs); o1 = funnel_r(a.w[3], b.w[0], bs); o2 = funnel_r(b.w[0], b.w[1], bs); o3 = funnel_r(b.w[1], b.w[2], bs); break;
             default: o0 = funnel_r(a.w[3], b.w[0], bs); o1 = funnel_r(b.w[0], b.w[1], bs); o2 = funnel_r(b.w[1], b.w[2], bs); o3 = funnel_r(b.w[2], b.w[3], bs); break;
             }
-            st_vec16(dst + 16 * (size_t)c, o0, o1, o2, o3);
+            st_vec16<kStream>(dst + 16 * (size_t)c, o0, o1, o2, o3);
         }
         if (fence && base + L < chunks) W::sync();
     }
     if (fence) W::sync();
-    for (u32 i = 16 * chunks + l; i < n; i += L) dst[i] = src[i];
+    for (u32 i = 16 * chunks + l; i < n; i += L) st_u8<kStream>(dst + i, src[i]);
 }
 
 // ---- 4-bytes-per-lane copy pieces: one pass moves 4*lanes bytes ------------------------------------------
