@@ -59,6 +59,13 @@ template <bool kStream> LZ_HD void st_u8(u8* p, u8 v)
 #endif
     *p = v;
 }
+template <bool kStream> LZ_HD u8 ld_u8(const u8* p)      // read-once data: evict-first
+{
+#if defined(__CUDA_ARCH__)
+    if (kStream) return __ldcs(p);
+#endif
+    return *p;
+}
 template <class W> LZ_HD void lanes_copy(u8* dst, const u8* src, u32 n)
 {
     for (u32 i = W::lane(); i < n; i += W::lanes()) dst[i] = src[i];
@@ -69,14 +76,14 @@ template <class W> LZ_HD void lanes_copy(u8* dst, const u8* src, u32 n)
 // stores, so a pass exposes one memory latency; every load/store instruction of the warp touches one contiguous
 // run of bytes (1-2 sectors).  No alignment requirements, which matters because literal runs and matches start
 // at arbitrary byte positions.  The source must not overlap the bytes written by the same pass.
-template <class W, bool kStream = false> LZ_HD void lanes_copy_rows(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
+template <class W, bool kStream = false, bool kStreamLd = false> LZ_HD void lanes_copy_rows(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
 {
     const u32 l = W::lane(), L = W::lanes();
     const u8* s = src + l; u8* d = dst + l;
-    if (n <= L) { if (l < n) st_u8<kStream>(d, s[0]); return; }              // most runs are shorter than one row
+    if (n <= L) { if (l < n) st_u8<kStream>(d, ld_u8<kStreamLd>(s)); return; }              // most runs are shorter than one row
     if (n <= 2 * L) {
-        u8 b0 = s[0], b1 = 0;
-        if (l + L < n) b1 = s[L];
+        u8 b0 = ld_u8<kStreamLd>(s), b1 = 0;
+        if (l + L < n) b1 = ld_u8<kStreamLd>(s + L);
         st_u8<kStream>(d, b0);
         if (l + L < n) st_u8<kStream>(d + L, b1);
         return;
@@ -84,10 +91,10 @@ template <class W, bool kStream = false> LZ_HD void lanes_copy_rows(u8* __restri
     for (u32 base = 0; base < n; base += 4 * L, s += 4 * L, d += 4 * L) {
         const u32 r = n - base;                                   // bytes left; row k is live for lane l when l + k*L < r
         u8 b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-        if (l < r) b0 = s[0];
-        if (l + L < r) b1 = s[L];
-        if (l + 2 * L < r) b2 = s[2 * L];
-        if (l + 3 * L < r) b3 = s[3 * L];
+        if (l < r) b0 = ld_u8<kStreamLd>(s);
+        if (l + L < r) b1 = ld_u8<kStreamLd>(s + L);
+        if (l + 2 * L < r) b2 = ld_u8<kStreamLd>(s + 2 * L);
+        if (l + 3 * L < r) b3 = ld_u8<kStreamLd>(s + 3 * L);
         if (l < r) st_u8<kStream>(d, b0);
         if (l + L < r) st_u8<kStream>(d + L, b1);
         if (l + 2 * L < r) st_u8<kStream>(d + 2 * L, b2);
@@ -124,16 +131,16 @@ template <class W> struct LaneGroups {
     static constexpr u32 kRuns = W::kLanes / kGroup;                   // runs per step
     static constexpr u32 kMaxBytes = 4 * kGroup;                       // longest run a step can take
 };
-template <class W, bool kStream = false> LZ_HD void lanes_copy_groups(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
+template <class W, bool kStream = false, bool kStreamLd = false> LZ_HD void lanes_copy_groups(u8* __restrict__ dst, const u8* __restrict__ src, u32 n)
 {
     constexpr u32 G = LaneGroups<W>::kGroup;
     const u32 o = W::lane() & (G - 1);
     const u8* s = src + o; u8* d = dst + o;
     u8 b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-    if (o < n) b0 = s[0];
-    if (o + G < n) b1 = s[G];
-    if (o + 2 * G < n) b2 = s[2 * G];
-    if (o + 3 * G < n) b3 = s[3 * G];
+    if (o < n) b0 = ld_u8<kStreamLd>(s);
+    if (o + G < n) b1 = ld_u8<kStreamLd>(s + G);
+    if (o + 2 * G < n) b2 = ld_u8<kStreamLd>(s + 2 * G);
+    if (o + 3 * G < n) b3 = ld_u8<kStreamLd>(s + 3 * G);
     if (o < n) st_u8<kStream>(d, b0);
     if (o + G < n) st_u8<kStream>(d + G, b1);
     if (o + 2 * G < n) st_u8<kStream>(d + 2 * G, b2);
@@ -148,10 +155,10 @@ template <class W, bool kStream = false> LZ_HD void lanes_copy_groups(u8* __rest
 // itself occupies.  `fence` = barrier between passes (needed when the source is data an earlier pass wrote, i.e.
 // a match whose offset is at least one pass + one vector, kWideMinOffset).
 struct Vec16 { u32 w[4]; };
-LZ_HD Vec16 ld_vec16(const u8* p)          // p is 16-byte aligned
+template <bool kStream = false> LZ_HD Vec16 ld_vec16(const u8* p)          // p is 16-byte aligned
 {
 #if defined(__CUDA_ARCH__)
-    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint4 v = kStream ? __ldcs(reinterpret_cast<const uint4*>(p)) : *reinterpret_cast<const uint4*>(p);
     Vec16 r; r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w; return r;
 #else
     Vec16 r; memcpy(&r, p, 16); return r;
@@ -176,12 +183,12 @@ LZ_HD u32 funnel_r(u32 lo, u32 hi, u32 bits)   // bits in {0, 8, 16, 24}
 }
 enum : u32 { kWideMinBytes = 64 };
 template <class W> LZ_HD u32 wide_min_offset() { return 16 * W::kLanes + 32; }
-template <class W, bool kStream = false> LZ_HD void lanes_copy_wide(u8* dst, const u8* src, u32 n, bool fence)
+template <class W, bool kStream = false, bool kStreamLd = false> LZ_HD void lanes_copy_wide(u8* dst, const u8* src, u32 n, bool fence)
 {
     const u32 l = W::lane(), L = W::lanes();
     u32 head = (u32)((16 - ((size_t)dst & 15)) & 15);
     if (head > n) head = n;
-    for (u32 i = l; i < head; i += L) st_u8<kStream>(dst + i, src[i]);
+    for (u32 i = l; i < head; i += L) st_u8<kStream>(dst + i, ld_u8<kStreamLd>(src + i));
     dst += head; src += head; n -= head;
     const u32 chunks = n >> 4;
     const size_t sa = (size_t)src;
@@ -192,9 +199,9 @@ template <class W, bool kStream = false> LZ_HD void lanes_copy_wide(u8* dst, con
     for (u32 base = 0; base < chunks; base += L) {
         const u32 c = base + l;
         if (c < chunks) {
-            const Vec16 a = ld_vec16(q + 16 * (size_t)c);
+            const Vec16 a = ld_vec16<kStreamLd>(q + 16 * (size_t)c);
             Vec16 b = a;
-            if (delta) b = ld_vec16(q + 16 * (size_t)c + 16);   // holds byte 16c+16 <= 16c+delta+15 of the run
+            if (delta) b = ld_vec16<kStreamLd>(q + 16 * (size_t)c + 16);   // holds byte 16c+16 <= 16c+delta+15 of the run
             u32 o0, o1, o2, o3;
             switch (ws) {
             case 0:  o0 = funnel_r(a.w[0], a.w[1], bs); o1 = funnel_r(a.w[1], a.w[2], bs); o2 = funnel_r(a.w[2], a.w[3], bs); o3 = funnel_r(a.w[3], b.w[0], bs); break;
@@ -207,7 +214,7 @@ template <class W, bool kStream = false> LZ_HD void lanes_copy_wide(u8* dst, con
         if (fence && base + L < chunks) W::sync();
     }
     if (fence) W::sync();
-    for (u32 i = 16 * chunks + l; i < n; i += L) st_u8<kStream>(dst + i, src[i]);
+    for (u32 i = 16 * chunks + l; i < n; i += L) st_u8<kStream>(dst + i, ld_u8<kStreamLd>(src + i));
 }
 
 // ---- 4-bytes-per-lane copy pieces: one pass moves 4*lanes bytes ------------------------------------------
