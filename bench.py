@@ -7,8 +7,10 @@
   step     : one pass of the hot path over the batch: compress all 8192 blocks, then decompress them.
   value    : uncompressed MB (10^6 B) per second of that round trip, inputs resident in HBM, CUDA-event timed,
              whole job over all ranks (weak scaling: every rank owns its own 1 GiB shard, no data-path collective).
-  e2e      : same round trip through the host-buffer C-ABI (LizardB200_compress_blocks / _decompress_blocks):
-             pinned host buffers in, H2D + kernels + D2H inside the timed region.
+  e2e      : same round trip through the reference-facing frame API on HOST buffers (LizardF_compressFrame +
+             LizardF_decompress, 128 KiB independent blocks, pinned memory): H2D + kernels + D2H inside the timed
+             region, wall clock; per-call split, the box's PCIe copy rates and the NUMA node the process was bound to
+             are reported next to it.
 
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/liblizard_ref_speed.so, default flags) on the box's
 host cores through the pthread harness in oracle/liboracle.so, same workload, all hardware threads.

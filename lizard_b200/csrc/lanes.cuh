@@ -102,27 +102,6 @@ template <class W, bool kStream = false, bool kStreamLd = false> LZ_HD void lane
     }
 }
 
-// two independent copies: the first rows of both are loaded before anything is stored (one exposed latency)
-template <class W> LZ_HD void lanes_copy_rows2(u8* __restrict__ dA, const u8* __restrict__ sA, u32 nA,
-                                               u8* __restrict__ dB, const u8* __restrict__ sB, u32 nB)
-{
-    const u32 l = W::lane(), L = W::lanes();
-    if (nA <= 2 * L && nB <= 2 * L) {
-        u8 a0 = 0, a1 = 0, b0 = 0, b1 = 0;
-        if (l < nA) a0 = sA[l];
-        if (l + L < nA) a1 = sA[l + L];
-        if (l < nB) b0 = sB[l];
-        if (l + L < nB) b1 = sB[l + L];
-        if (l < nA) dA[l] = a0;
-        if (l + L < nA) dA[l + L] = a1;
-        if (l < nB) dB[l] = b0;
-        if (l + L < nB) dB[l + L] = b1;
-        return;
-    }
-    lanes_copy_rows<W>(dA, sA, nA);
-    lanes_copy_rows<W>(dB, sB, nB);
-}
-
 // ---- several short runs at once: groups of 8 lanes --------------------------------------------------------------
 // Lane group g (lanes 8g..8g+7) copies its own run of at most 4*8 bytes, all groups in the same instructions: the
 // arguments are per lane (equal within a group).  One load phase, one store phase for up to lanes/8 runs.
@@ -215,49 +194,6 @@ template <class W, bool kStream = false, bool kStreamLd = false> LZ_HD void lane
     }
     if (fence) W::sync();
     for (u32 i = 16 * chunks + l; i < n; i += L) st_u8<kStream>(dst + i, ld_u8<kStreamLd>(src + i));
-}
-
-// ---- 4-bytes-per-lane copy pieces: one pass moves 4*lanes bytes ------------------------------------------
-LZ_HD u32 ld32u(const u8* p)      // unaligned little-endian load; may touch the aligned words around p only
-{
-#if defined(__CUDA_ARCH__)
-    const size_t a = (size_t)p;
-    const u32* q = (const u32*)(a & ~(size_t)3);
-    const u32 sh = (u32)(a & 3) * 8;
-    const u32 lo = q[0];
-    if (sh == 0) return lo;
-    return __funnelshift_r(lo, q[1], sh);
-#else
-    return rd_le32(p);
-#endif
-}
-// this lane's 4 bytes (index 4*lane) of a run of n bytes; bytes past n read as 0
-template <class W> LZ_HD u32 load_chunk4(const u8* src, u32 n)
-{
-    const u32 i = 4 * W::lane();
-    if (i + 4 <= n) return ld32u(src + i);
-    u32 v = 0;
-    for (u32 j = 0; j < 4; ++j) if (i + j < n) v |= (u32)src[i + j] << (8 * j);
-    return v;
-}
-template <class W> LZ_HD void store_chunk4(u8* dst, u32 v, u32 n)
-{
-    const u32 i = 4 * W::lane();
-    if (i >= n) return;
-    u8* d = dst + i;
-    if (i + 4 <= n && ((size_t)d & 3) == 0) { *(u32*)d = v; return; }
-    const u32 cnt = n - i < 4 ? n - i : 4;
-    for (u32 j = 0; j < cnt; ++j) d[j] = (u8)(v >> (8 * j));
-}
-// non-overlapping copy (src and dst ranges disjoint, or src entirely before dst with distance >= n)
-template <class W> LZ_HD void lanes_copy4(u8* dst, const u8* src, u32 n)
-{
-    const u32 step = 4 * W::lanes();
-    for (u32 base = 0; base < n; base += step) {
-        const u32 part = n - base < step ? n - base : step;
-        const u32 v = load_chunk4<W>(src + base, part);
-        store_chunk4<W>(dst + base, v, part);
-    }
 }
 
 LZ_HD u32 ctz32(u32 v)
