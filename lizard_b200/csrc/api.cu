@@ -22,7 +22,9 @@ namespace {
 constexpr int kDecWarps = 8;                 // warps per CTA in the decode kernel
 constexpr int kMaxDevices = 16;
 
-__global__ void __launch_bounds__(kDecWarps * 32, 4)
+// V = schedule of the token loops, two bits: 1 = pooled copy sweeps, 2 = compact length-extension chain (default 3 = both;
+// LIZARDB200_DEC_VARIANT=0..3 or LizardB200_setDecodeVariant select the others for A/B runs)
+template <int V> __global__ void __launch_bounds__(kDecWarps * 32, 4)
 lizard_decode_units_kernel(DecodeBatch b)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -38,11 +40,22 @@ lizard_decode_units_kernel(DecodeBatch b)
         unit = __shfl_sync(LZB_FULL, unit, 0);
         if (unit >= b.n_units) break;
         progress_wait(b.progress, unit, lane);
-        const int r = decode_unit<WarpLanes>(b.src_base + b.src_off[unit], b.src_len[unit],
+        const int r = decode_unit<WarpLanes, V>(b.src_base + b.src_off[unit], b.src_len[unit],
                                              b.dst_base + b.dst_off[unit], b.dst_cap[unit], scratch, sh);
         if (lane == 0) b.result[unit] = r;
         __syncwarp();
         progress_done(b.progress, unit, lane);
+    }
+}
+
+typedef void (*DecodeKernel)(DecodeBatch);
+DecodeKernel decode_kernel(int v)
+{
+    switch (v & 3) {
+    case 0: return lizard_decode_units_kernel<0>;
+    case 1: return lizard_decode_units_kernel<1>;
+    case 2: return lizard_decode_units_kernel<2>;
+    default: return lizard_decode_units_kernel<3>;
     }
 }
 
@@ -80,7 +93,7 @@ struct Context {
     bool ready = false, failed = false;
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // compute / H2D / D2H
-    int dec_grid = 0;
+    int dec_grid = 0, dec_variant = 3;
     DeviceBuffer dec_scratch, enc_scratch, counters;
     u32 counter_slot = 0;
     // staging for the host-pointer entry points
@@ -132,10 +145,17 @@ int ensure_context(Context& c, int device)
         c.failed = true; fail("cudaStreamCreate", e); return LIZARDB200_ERR_CUDA;
     }
     const size_t dec_smem = sizeof(DecWarpShared) * kDecWarps;
-    e = cudaFuncSetAttribute(lizard_decode_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
+    if (const char* v = getenv("LIZARDB200_DEC_VARIANT")) if (*v >= '0' && *v <= '3') c.dec_variant = *v - '0';
+    e = cudaSuccess;
+    for (int v = 0; v < 4 && e == cudaSuccess; ++v)
+        e = cudaFuncSetAttribute(decode_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
     if (e != cudaSuccess) { c.failed = true; fail("cudaFuncSetAttribute(decode)", e); return LIZARDB200_ERR_CUDA; }
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lizard_decode_units_kernel, kDecWarps * 32, dec_smem);
+    for (int v = 0; v < 4; ++v) {          // all schedules share one launch shape (same registers and shared memory)
+        int p = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p, decode_kernel(v), kDecWarps * 32, dec_smem);
+        if (v == 0 || p < per_sm) per_sm = p;
+    }
     if (per_sm < 1) per_sm = 1;
     c.dec_grid = c.sm_count * per_sm;
     if ((e = c.dec_scratch.reserve((size_t)c.dec_grid * kDecWarps * kDecScratchPerWarp)) != cudaSuccess) {
@@ -176,7 +196,7 @@ int launch_decode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* d
     u32 warps_needed = n;
     int grid = (int)((warps_needed + kDecWarps - 1) / kDecWarps);
     if (grid > c.dec_grid) grid = c.dec_grid;
-    lizard_decode_units_kernel<<<grid, kDecWarps * 32, sizeof(DecWarpShared) * kDecWarps, s>>>(b);
+    decode_kernel(c.dec_variant)<<<grid, kDecWarps * 32, sizeof(DecWarpShared) * kDecWarps, s>>>(b);
     g_launches++;
     CU_OK(cudaGetLastError());
     return LIZARDB200_OK;
@@ -312,6 +332,17 @@ int LizardB200_available(void)
 }
 const char* LizardB200_lastError(void) { return g_last_error.c_str(); }
 unsigned long long LizardB200_launchCount(void) { return g_launches.load(); }
+
+// diagnostics (tools/dec_bench.py): batch schedule of the decode kernel on this thread's device, see lizard_decode_units_kernel
+int LizardB200_setDecodeVariant(int variant)
+{
+    Context& c = g_ctx[g_device];
+    std::lock_guard<std::mutex> lk(c.mu);
+    int st = ensure_context(c, g_device);
+    if (st != LIZARDB200_OK) return st;
+    c.dec_variant = variant & 3;
+    return LIZARDB200_OK;
+}
 
 int LizardB200_decompress_device(const void* dSrc, const uint64_t* dSrcOff, const uint32_t* dSrcLen,
                                  void* dDst, const uint64_t* dDstOff, const uint32_t* dDstCap,

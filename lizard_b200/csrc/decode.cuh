@@ -79,13 +79,16 @@ enum : u32 { kDecStreamScratch = kBlockSize + 64, kDecBigTableBytes = 2u << kHuf
              kDecScratchPerWarp = 4 * kDecStreamScratch + kDecBigTableBytes };
 enum : u32 { kDecSmemTableLog = 11 };    // Lizard's encoder never exceeds 11 (HUF_TABLELOG_DEFAULT); 12 is legal input
 
-struct alignas(16) SeqDesc { u32 a, b, c, d; };   // 16-byte sequence descriptor (see run_batch_copies)
+typedef PoolRun SeqDesc;                          // 16-byte sequence descriptor (see run_batch_copies)
 
 struct DecWarpShared {             // per-warp shared memory
     SeqDesc desc[64];              // literal-run and match descriptors of the current token batch
     u16 table[1u << kDecSmemTableLog];
     u16* big_table;                // 2^12-entry table in the warp's global scratch, used only for tableLog 12
-    HufStatsScratch stats;
+    union {
+        HufStatsScratch stats;                       // while a Huffman header is being read
+        struct { u32 ent[32]; u32 epre[32]; } chain; // during the token loops: length-extension chain of a batch
+    };
     u8  weights[256];
     u32 rank[kHufTableLogMax + 1];
     u32 pad[3];
@@ -121,7 +124,8 @@ LZ_HD u64 ld64_any(const u8* p)          // unaligned 8-byte little-endian load 
     return rd_le64(p);
 #endif
 }
-LZ_HD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u16* table, u32 tl, int* init_err)
+// own function on the device: its loop must not share a register allocation with the token loops
+LZ_HD_COLD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u16* table, u32 tl, int* init_err)
 {
     BitReader b;
     int e = bits_init(b, src, len);
@@ -442,9 +446,94 @@ template <class W> LZ_HD void run_batch_copies(u8* dst, const u8* lits, u32 nb, 
     }
 }
 
+// ---- batch execution, pooled form (decode variant 1) ---------------------------------------------------------------
+// Same contract as run_batch_copies, different schedule: instead of walking the batch run by run, the runs are sorted
+// into four pools -- short / long literal runs, short / long matches that read nothing a match of this batch writes --
+// and every pool is moved by one sweep that keeps all lanes busy (pool_copy_short / pool_copy_long, lanes.cuh).  Only
+// the matches that do read the output of an earlier match of the same batch (or themselves) follow one by one, in order.
+template <class W> LZ_HD void run_batch_copies_pool(u8* dst, const u8* lits, u32 nb, u32 lit_src, u32 lit_len,
+                                                    u32 opos, u32 off, u32 ml, PoolRun* pool)
+{
+    typedef LaneGroups<W> LG;
+    const u32 lane = W::lane(), L = W::lanes();
+    const bool act = lane < nb;
+    const u32 mdst = opos + lit_len;
+    if (W::kLanes == 1) {                                   // one-lane host build: the reference's order
+        if (act) { for (u32 i = 0; i < lit_len; ++i) dst[opos + i] = lits[lit_src + i]; lanes_match<W>(dst, (long)mdst, off, ml); }
+        return;
+    }
+    if (act && off != 0 && off <= mdst) W::prefetch(dst + (mdst - off));
+    pool_copy_short<W>(dst, lits, W::ballot(act && lit_len != 0 && lit_len <= LG::kMaxBytes), opos, lit_src, lit_len, pool);
+    pool_copy_long<W>(dst, lits, W::ballot(act && lit_len > LG::kMaxBytes), opos, lit_src, lit_len, pool + 32);
+    W::sync();
+    // A match is "free" when its source lies before the first match destination of this batch (older output, or the
+    // first literal run), or inside ONE literal run of this batch: those bytes are final now.
+    const u32 msrc = mdst - off;                            // off <= mdst was checked by the caller
+    const bool real = act && ml != 0 && off != 0;
+    const u32 first = W::shfl(mdst, 0);
+    bool free_m = real && msrc + ml <= first;
+    {
+        u32 pos = 0;                                        // last sequence whose output starts at or before msrc
+        for (u32 st = W::kLanes >> 1; st; st >>= 1) { const u32 v = W::shfl(opos, pos + st); if (v <= msrc) pos += st; }
+        const u32 lit_beg = W::shfl(opos, pos), lit_end = W::shfl(mdst, pos);
+        if (real && msrc >= lit_beg && msrc + ml <= lit_end) free_m = true;
+    }
+    pool_copy_short<W>(dst, dst, W::ballot(free_m && ml <= LG::kMaxBytes), mdst, msrc, ml, pool);
+    pool_copy_long<W>(dst, dst, W::ballot(free_m && ml > LG::kMaxBytes), mdst, msrc, ml, pool + 32);
+    u32 rest = W::ballot(act && ml != 0 && !free_m);
+    if (rest == 0) return;
+    W::sync();
+    for (; rest; rest &= rest - 1) {
+        const u32 k = ctz32(rest);
+        const u32 m = W::shfl(ml, k), o = W::shfl(off, k);
+        u8* const to = dst + W::shfl(mdst, k);
+        if (m >= kWideMinBytes && o >= wide_min_offset<W>()) lanes_copy_wide<W>(to, to - o, m, true);
+        else if (o >= m || o >= 4 * L) {
+            for (u32 base = 0; base < m; base += 4 * L) {
+                const u32 part = m - base < 4 * L ? m - base : 4 * L;
+                lanes_copy_rows<W>(to + base, to + base - o, part);
+                if (base + 4 * L < m) W::sync();
+            }
+        } else lanes_match<W>(dst, (long)(to - dst), o, m);
+        W::sync();
+    }
+}
+
+// Length-extension chain of one batch, compact form.  Lanes whose token carries an extension field put
+// (A | litn << 16 | has-literal-ext << 24 | has-match-ext << 25) into `ent` in token order; the warp then walks that list
+// with uniform loads: only the VALUE of a literal-length field and the SIZE of any field move later tokens.  epre[j] = bytes
+// of extension data before list entry j (beyond the one byte per field already counted in A).  Returns false when a field
+// is cut off by the end of the stream (the serial path then reproduces the reference's verdict).  `lbias` = 15 (LZ4
+// codewords, fields read only while base <= nl-5) or 7 (LIZv1, base <= nl-1); `gap` = bytes between the literal run and
+// the match-length field (the inline 16-bit offset of the LZ4 flavour).
+template <class W> LZ_HD bool ext_chain(const u8* lits, long nl, long lp, u32 npend, const u32* ent, u32* epre,
+                                        u32 lbias, long room, u32 gap, u32* total)
+{
+    u32 E = 0;
+    for (u32 j = 0; j < npend; ++j) {
+        const u32 e = ent[j];
+        const long base = lp + (long)(e & 0xffffu) + (long)E;
+        if (W::lane() == 0) epre[j] = E;
+        long pm;
+        if (e & (1u << 24)) {
+            u32 v, sz;
+            if (base > nl - room || !ext_field(lits, nl, base, &v, &sz)) return false;
+            E += lbias + v + (sz - 1);
+            pm = base + (long)sz + (long)(lbias + v) + (long)gap;
+        } else pm = base + (long)((e >> 16) & 255u) + (long)gap;
+        if (e & (1u << 25)) {
+            u32 v, sz;
+            if (pm > nl - room || !ext_field(lits, nl, pm, &v, &sz)) return false;
+            E += sz - 1;
+        }
+    }
+    *total = E;
+    return true;
+}
+
 // fastLZ4 codewords (lib/lizard_decompress_lz4.h:7-163).  `op0` is the offset inside the unit's output,
 // `oend` the unit's capacity; matches may reach back to offset 0 of the unit.
-template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op0, u32 oend_u, SeqDesc* desc)
+template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op0, u32 oend_u, DecWarpShared* sh)
 {
     const long nl = (long)s.nlits, oend = (long)oend_u;
     const u32 NL = W::lanes(), lane = W::lane();
@@ -464,32 +553,50 @@ template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op
         // Serial chain over the tokens that carry a length extension (literal length and/or match length): only
         // these make a token's position in the literals stream data dependent.  E = bytes not yet counted in A.
         const bool needm = act && mln == 15;
-        u32 pending = W::ballot(need || needm), E = 0;
-        const u32 needl_mask = W::ballot(need), needm_mask = W::ballot(needm);
         u32 my_lit = 0, my_lx = 0, my_mlv = 0, my_mx = 0;          // literal length / its field size, ml-ext value / size
         bool slow = false;
-        while (pending) {
-            const u32 k = ctz32(pending); pending &= pending - 1;
-            const long base = c.lp + (long)W::shfl(A, k) + (long)E;     // first stream byte of token k
-            long pm;                                                     // where its match-length field would sit
-            if ((needl_mask >> k) & 1) {
-                u32 v, sz;
-                if (base > nl - 5 || !ext_field(s.lits, nl, base, &v, &sz)) { slow = true; break; }
-                if (lane == k) { my_lit = 15 + v; my_lx = sz; }
-                E += 15 + v + (sz - 1);
-                pm = base + sz + 15 + v + 2;
-            } else pm = base + (long)W::shfl(litn, k) + 2;
-            if ((needm_mask >> k) & 1) {
-                u32 v, sz;
-                if (pm > nl - 5 || !ext_field(s.lits, nl, pm, &v, &sz)) { slow = true; break; }
-                if (lane == k) { my_mlv = v; my_mx = sz; }
-                E += sz - 1;
+        u32 tot_ext = 0;
+        long tokpos = 0;
+        if ((V & 2) == 0) {
+            u32 pending = W::ballot(need || needm), E = 0;
+            const u32 needl_mask = W::ballot(need), needm_mask = W::ballot(needm);
+            while (pending) {
+                const u32 k = ctz32(pending); pending &= pending - 1;
+                const long base = c.lp + (long)W::shfl(A, k) + (long)E;     // first stream byte of token k
+                long pm;                                                     // where its match-length field would sit
+                if ((needl_mask >> k) & 1) {
+                    u32 v, sz;
+                    if (base > nl - 5 || !ext_field(s.lits, nl, base, &v, &sz)) { slow = true; break; }
+                    if (lane == k) { my_lit = 15 + v; my_lx = sz; }
+                    E += 15 + v + (sz - 1);
+                    pm = base + sz + 15 + v + 2;
+                } else pm = base + (long)W::shfl(litn, k) + 2;
+                if ((needm_mask >> k) & 1) {
+                    u32 v, sz;
+                    if (pm > nl - 5 || !ext_field(s.lits, nl, pm, &v, &sz)) { slow = true; break; }
+                    if (lane == k) { my_mlv = v; my_mx = sz; }
+                    E += sz - 1;
+                }
+            }
+            if (!slow) {
+                const u32 Eex = W::excl_scan((need ? my_lit + (my_lx - 1) : 0u) + (needm ? my_mx - 1 : 0u), &tot_ext);
+                tokpos = c.lp + (long)A + (long)Eex;
+            }
+        } else {
+            const u32 pendmask = W::ballot(need || needm);
+            const u32 npend = popc32(pendmask), myidx = popc32(pendmask & ((1u << lane) - 1));
+            if (need || needm) sh->chain.ent[myidx] = A | (litn << 16) | (need ? 1u << 24 : 0u) | (needm ? 1u << 25 : 0u);
+            W::sync();
+            slow = !ext_chain<W>(s.lits, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, 15, 5, 2, &tot_ext);
+            if (!slow) {
+                W::sync();
+                tokpos = c.lp + (long)A + (long)(myidx < npend ? sh->chain.epre[myidx] : tot_ext);
+                // every lane reads its own fields (the chain has checked that they are inside the stream)
+                if (need) { u32 v = 0, sz = 1; ext_field(s.lits, nl, tokpos, &v, &sz); my_lit = 15 + v; my_lx = sz; }
+                if (needm) { u32 v = 0, sz = 1; ext_field(s.lits, nl, tokpos + (need ? (long)(my_lx + my_lit) : (long)litn) + 2, &v, &sz); my_mlv = v; my_mx = sz; }
             }
         }
         if (!slow) {
-            u32 tot_ext = 0;
-            const u32 Eex = W::excl_scan((need ? my_lit + (my_lx - 1) : 0u) + (needm ? my_mx - 1 : 0u), &tot_ext);
-            const long tokpos = c.lp + (long)A + (long)Eex;
             const u32 lit_len = need ? my_lit : (act ? litn : 0);
             const long lit_src = tokpos + (need ? (long)my_lx : 0);
             const long off_pos = lit_src + lit_len;
@@ -512,7 +619,8 @@ template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op
             }
             if (W::ballot(bad) == 0) {
                 LZB_COUNT_FAST(W::lane() == 0 ? nb : 0);
-                run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, desc);
+                if ((V & 1) == 0) run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, sh->desc);
+                else run_batch_copies_pool<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, sh->desc);
                 c.fp += nb; c.lp += (long)tot_adv + (long)tot_ext; c.op += (long)tot_out;
                 continue;
             }
@@ -523,14 +631,15 @@ template <class W> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op
     }
     const long rest = nl - c.lp;
     if (rest < 0 || c.op + rest > oend) return -(int)c.fp - 1;
-    lanes_copy<W>(dst + c.op, s.lits + c.lp, (u32)rest);
+    if (V != 0 && rest >= (long)kWideMinBytes) lanes_copy_wide<W>(dst + c.op, s.lits + c.lp, (u32)rest, false);
+    else lanes_copy<W>(dst + c.op, s.lits + c.lp, (u32)rest);
     W::sync();
     c.op += rest;
     return (int)(c.op - (long)op0);
 }
 
 // LIZv1 codewords (lib/lizard_decompress_liz.h:14-220)
-template <class W> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 op0, u32 oend_u, SeqDesc* desc)
+template <class W, int V> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 op0, u32 oend_u, DecWarpShared* sh)
 {
     const long nl = (long)s.nlits, oend = (long)oend_u;
     const u32 NL = W::lanes(), lane = W::lane();
@@ -552,32 +661,49 @@ template <class W> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 
         const u32 A = W::excl_scan(adv, &tot_adv);
         const u32 P16 = W::excl_scan(new16 ? 2u : 0u, &tot16);
         const u32 P24 = W::excl_scan((act && !shortf) ? 3u : 0u, &tot24);
-        u32 pending = W::ballot(need || mlext), E = 0;
-        const u32 needl_mask = W::ballot(need), needm_mask = W::ballot(mlext);
         u32 my_lit = 0, my_lx = 0, my_mlv = 0, my_mx = 0;
         bool slow = false;
-        while (pending) {
-            const u32 k = ctz32(pending); pending &= pending - 1;
-            const long base = c.lp + (long)W::shfl(A, k) + (long)E;
-            long pm;
-            if ((needl_mask >> k) & 1) {
-                u32 v, sz;
-                if (base > nl - 1 || !ext_field(s.lits, nl, base, &v, &sz)) { slow = true; break; }
-                if (lane == k) { my_lit = 7 + v; my_lx = sz; }
-                E += 7 + v + (sz - 1);
-                pm = base + sz + 7 + v;
-            } else pm = base + (long)W::shfl(litn, k);
-            if ((needm_mask >> k) & 1) {
-                u32 v, sz;
-                if (pm > nl - 1 || !ext_field(s.lits, nl, pm, &v, &sz)) { slow = true; break; }
-                if (lane == k) { my_mlv = v; my_mx = sz; }
-                E += sz - 1;
+        u32 tot_ext = 0;
+        long tokpos = 0;
+        if ((V & 2) == 0) {
+            u32 pending = W::ballot(need || mlext), E = 0;
+            const u32 needl_mask = W::ballot(need), needm_mask = W::ballot(mlext);
+            while (pending) {
+                const u32 k = ctz32(pending); pending &= pending - 1;
+                const long base = c.lp + (long)W::shfl(A, k) + (long)E;
+                long pm;
+                if ((needl_mask >> k) & 1) {
+                    u32 v, sz;
+                    if (base > nl - 1 || !ext_field(s.lits, nl, base, &v, &sz)) { slow = true; break; }
+                    if (lane == k) { my_lit = 7 + v; my_lx = sz; }
+                    E += 7 + v + (sz - 1);
+                    pm = base + sz + 7 + v;
+                } else pm = base + (long)W::shfl(litn, k);
+                if ((needm_mask >> k) & 1) {
+                    u32 v, sz;
+                    if (pm > nl - 1 || !ext_field(s.lits, nl, pm, &v, &sz)) { slow = true; break; }
+                    if (lane == k) { my_mlv = v; my_mx = sz; }
+                    E += sz - 1;
+                }
+            }
+            if (!slow) {
+                const u32 Eex = W::excl_scan((need ? my_lit + (my_lx - 1) : 0u) + (mlext ? my_mx - 1 : 0u), &tot_ext);
+                tokpos = c.lp + (long)A + (long)Eex;
+            }
+        } else {
+            const u32 pendmask = W::ballot(need || mlext);
+            const u32 npend = popc32(pendmask), myidx = popc32(pendmask & ((1u << lane) - 1));
+            if (need || mlext) sh->chain.ent[myidx] = A | (litn << 16) | (need ? 1u << 24 : 0u) | (mlext ? 1u << 25 : 0u);
+            W::sync();
+            slow = !ext_chain<W>(s.lits, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, 7, 1, 0, &tot_ext);
+            if (!slow) {
+                W::sync();
+                tokpos = c.lp + (long)A + (long)(myidx < npend ? sh->chain.epre[myidx] : tot_ext);
+                if (need) { u32 v = 0, sz = 1; ext_field(s.lits, nl, tokpos, &v, &sz); my_lit = 7 + v; my_lx = sz; }
+                if (mlext) { u32 v = 0, sz = 1; ext_field(s.lits, nl, tokpos + (need ? (long)(my_lx + my_lit) : (long)litn), &v, &sz); my_mlv = v; my_mx = sz; }
             }
         }
         if (!slow) {
-            u32 tot_ext = 0;
-            const u32 Eex = W::excl_scan((need ? my_lit + (my_lx - 1) : 0u) + (mlext ? my_mx - 1 : 0u), &tot_ext);
-            const long tokpos = c.lp + (long)A + (long)Eex;
             const u32 lit_len = need ? my_lit : (act ? litn : 0);
             const long lit_src = tokpos + (need ? (long)my_lx : 0);
             bool bad = false;
@@ -613,7 +739,8 @@ template <class W> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 
             }
             if (W::ballot(bad) == 0) {
                 LZB_COUNT_FAST(W::lane() == 0 ? nb : 0);
-                run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, desc);
+                if ((V & 1) == 0) run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, sh->desc);
+                else run_batch_copies_pool<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, sh->desc);
                 c.fp += nb; c.lp += (long)tot_adv + (long)tot_ext; c.op += (long)tot_out;
                 c.p16 += tot16; c.p24 += tot24;
                 c.last_off = W::shfl(off, nb - 1);
@@ -626,7 +753,8 @@ template <class W> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* dst, u32 
     }
     const long rest = nl - c.lp;
     if (rest < 0 || c.op + rest > oend) return -(int)c.fp - 1;
-    lanes_copy<W>(dst + c.op, s.lits + c.lp, (u32)rest);
+    if (V != 0 && rest >= (long)kWideMinBytes) lanes_copy_wide<W>(dst + c.op, s.lits + c.lp, (u32)rest, false);
+    else lanes_copy<W>(dst + c.op, s.lits + c.lp, (u32)rest);
     W::sync();
     c.op += rest;
     return (int)(c.op - (long)op0);
@@ -655,7 +783,7 @@ template <class W> LZ_HD int read_stream(bool huff, const u8* src, long csize, l
 }
 
 // Lizard_decompress_safe for one unit; every lane returns the same value.
-template <class W> LZ_HD int decode_unit(const u8* src, u32 csize_u, u8* dst, u32 cap, u8* scratch, DecWarpShared* sh)
+template <class W, int V> LZ_HD int decode_unit(const u8* src, u32 csize_u, u8* dst, u32 cap, u8* scratch, DecWarpShared* sh)
 {
     const long csize = (long)csize_u;
     if (csize < 1) return 0;
@@ -670,7 +798,8 @@ template <class W> LZ_HD int decode_unit(const u8* src, u32 csize_u, u8* dst, u3
             if (ip > csize - 3) return -1;
             const u32 len = rd_le24(src + ip); ip += 3;
             if (ip + (long)len > csize || op + (long)len > (long)cap) return -1;
-            lanes_copy<W>(dst + op, src + ip, len);
+            if (V != 0 && len >= kWideMinBytes) lanes_copy_wide<W>(dst + op, src + ip, len, false);
+            else lanes_copy<W>(dst + op, src + ip, len);
             W::sync();
             op += len; ip += len;
             continue;
@@ -690,7 +819,7 @@ template <class W> LZ_HD int decode_unit(const u8* src, u32 csize_u, u8* dst, u3
         if (!read_stream<W>(hdr & kFlagFlags, src, csize, ip, scratch + 1 * kDecStreamScratch, &s.flags, &s.nflags, sh)) return -1;
         if (!read_stream<W>(hdr & kFlagLiterals, src, csize, ip, scratch, &s.lits, &s.nlits, sh)) return -1;
         if (ip > csize) return -1;
-        const int res = lizv1 ? decode_tokens_lizv1<W>(s, dst, (u32)op, cap, sh->desc) : decode_tokens_lz4<W>(s, dst, (u32)op, cap, sh->desc);
+        const int res = lizv1 ? decode_tokens_lizv1<W, V>(s, dst, (u32)op, cap, sh) : decode_tokens_lz4<W, V>(s, dst, (u32)op, cap, sh);
         if (res <= 0) return res;
         op += res;
     }

@@ -42,6 +42,10 @@ extern "C" int lzb_host_compress(const unsigned char* src, int n, unsigned char*
     return r;
 }
 
+// which schedule the decoder entry points below run (bit 0 pooled copies, bit 1 compact chain; device default 3)
+static int g_dec_variant = 3;
+extern "C" void lzb_set_decode_variant(int v) { g_dec_variant = v; }
+
 // Lizard_decompress_safe through the one-lane instantiation of the device decoder
 extern "C" int lzb_host_decompress(const unsigned char* src, int csize, unsigned char* dst, int cap)
 {
@@ -50,7 +54,13 @@ extern "C" int lzb_host_decompress(const unsigned char* src, int csize, unsigned
     unsigned char* scratch = (unsigned char*)malloc(lzb::kDecScratchPerWarp);
     lzb::DecWarpShared* sh = (lzb::DecWarpShared*)malloc(sizeof(lzb::DecWarpShared));
     sh->big_table = (lzb::u16*)(scratch + 4 * lzb::kDecStreamScratch);
-    int r = lzb::decode_unit<lzb::HostLanes>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, sh);
+    int r;
+    switch (g_dec_variant & 3) {
+    case 0: r = lzb::decode_unit<lzb::HostLanes, 0>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, sh); break;
+    case 1: r = lzb::decode_unit<lzb::HostLanes, 1>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, sh); break;
+    case 2: r = lzb::decode_unit<lzb::HostLanes, 2>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, sh); break;
+    default: r = lzb::decode_unit<lzb::HostLanes, 3>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, sh); break;
+    }
     free(scratch); free(sh);
     return r;
 }
@@ -88,6 +98,7 @@ struct Warp {
     void* arg = nullptr;
 };
 static Warp* g = nullptr;
+static int g_order = 0;          // 0 forward, 1 reverse, 2 shuffled per round
 
 static void yield() { swapcontext(&g->ctx[g->cur], &g->sched); }
 
@@ -128,9 +139,21 @@ static void run(void (*body)(void*), void* arg)
         w.ctx[i].uc_link = &w.sched;
         makecontext(&w.ctx[i], (void (*)())trampoline, 0);
     }
+    unsigned rng = 12345u;
     for (;;) {
         bool any = false;
-        for (int i = 0; i < kLanes; ++i) {
+        // lane order inside a round: forward, reverse, or shuffled -- code that is missing a barrier between a write
+        // by one lane and a read by another only fails under SOME orders, so the tests run all three
+        int order[kLanes];
+        for (int i = 0; i < kLanes; ++i) order[i] = g_order == 1 ? kLanes - 1 - i : i;
+        if (g_order == 2)
+            for (int i = kLanes - 1; i > 0; --i) {
+                rng = rng * 1664525u + 1013904223u;
+                const int j = (int)((rng >> 8) % (unsigned)(i + 1));
+                const int t = order[i]; order[i] = order[j]; order[j] = t;
+            }
+        for (int n = 0; n < kLanes; ++n) {
+            const int i = order[n];
             if (w.done[i]) continue;
             any = true;
             w.cur = i;
@@ -141,6 +164,8 @@ static void run(void (*body)(void*), void* arg)
     g = nullptr;
 }
 }  // namespace emu
+
+extern "C" void lzb_emu_lane_order(int o) { emu::g_order = o; }
 
 struct EmuLanes {
     static constexpr bool kDevice = false;
@@ -167,6 +192,11 @@ struct EmuLanes {
         unsigned long long t[emu::kLanes]; emu::exchange(v, t); return (lzb::u32)t[src & 31];
     }
     static void prefetch(const void*) {}
+    static lzb::u32 red_or(lzb::u32 v)
+    {
+        unsigned long long t[emu::kLanes]; emu::exchange(v, t);
+        lzb::u32 m = 0; for (int i = 0; i < emu::kLanes; ++i) m |= (lzb::u32)t[i]; return m;
+    }
     static lzb::u32 match_any(lzb::u32 v)
     {
         unsigned long long t[emu::kLanes]; emu::exchange(v, t);
@@ -205,7 +235,13 @@ struct EmuDecompressArgs { const unsigned char* src; int csize; unsigned char* d
 static void emu_decompress_body(void* p)
 {
     EmuDecompressArgs* a = (EmuDecompressArgs*)p;
-    int r = lzb::decode_unit<EmuLanes>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh);
+    int r;
+    switch (g_dec_variant & 3) {
+    case 0: r = lzb::decode_unit<EmuLanes, 0>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh); break;
+    case 1: r = lzb::decode_unit<EmuLanes, 1>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh); break;
+    case 2: r = lzb::decode_unit<EmuLanes, 2>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh); break;
+    default: r = lzb::decode_unit<EmuLanes, 3>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh); break;
+    }
     if (EmuLanes::lane() == 0) a->result = r;
 }
 

@@ -21,6 +21,7 @@ struct HostLanes {
     LZ_HDM static u32 ballot(bool p) { return p ? 1u : 0u; }
     LZ_HDM static u32 shfl(u32 v, u32) { return v; }
     LZ_HDM static u32 match_any(u32) { return 1u; }
+    LZ_HDM static u32 red_or(u32 v) { return v; }
     LZ_HDM static void prefetch(const void*) {}
 };
 #if defined(__CUDACC__)
@@ -46,6 +47,7 @@ struct WarpLanes {
     __device__ __forceinline__ static u32 ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
     __device__ __forceinline__ static u32 shfl(u32 v, u32 src) { return __shfl_sync(0xffffffffu, v, (int)src); }
     __device__ __forceinline__ static u32 match_any(u32 v) { return __match_any_sync(0xffffffffu, v); }
+    __device__ __forceinline__ static u32 red_or(u32 v) { return __reduce_or_sync(0xffffffffu, v); }
     __device__ __forceinline__ static void prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 };
 #endif
@@ -203,6 +205,145 @@ LZ_HD u32 ctz32(u32 v)
 #else
     return (u32)__builtin_ctz(v);
 #endif
+}
+
+LZ_HD u32 popc32(u32 v)
+{
+#if defined(__CUDA_ARCH__)
+    return (u32)__popc(v);
+#else
+    return (u32)__builtin_popcount(v);
+#endif
+}
+
+// ---- pooled copies: many runs, one sweep --------------------------------------------------------------------------
+// The decoder hands over the runs of a whole token batch at once (one run per lane, selected by a ballot mask).  Moving
+// them run by run leaves most lanes idle and exposes one memory latency per run; here the runs are packed into a small
+// table in the warp's shared memory and the warp sweeps over the UNION of their pieces, every lane busy.
+struct alignas(16) PoolRun { u32 a, b, c, d; };
+
+// 16 bytes from an arbitrary address, fetched as the (one or two) aligned 16-byte vectors that hold them.  Branch free
+// in the byte phase, because the lanes of a sweep work on different runs.  Every byte of [p, p+16) must be readable.
+LZ_HD Vec16 ld_chunk16(const u8* p)
+{
+#if defined(__CUDA_ARCH__)
+    const u32 delta = (u32)((size_t)p & 15);
+    const u8* q = p - delta;
+    const Vec16 a = ld_vec16(q);
+    Vec16 b = a;
+    if (delta) b = ld_vec16(q + 16);
+    const bool w2 = (delta & 8) != 0, w1 = (delta & 4) != 0;
+    const u32 bs = (delta & 3) * 8;
+    const u32 y0 = w2 ? a.w[2] : a.w[0], y1 = w2 ? a.w[3] : a.w[1], y2 = w2 ? b.w[0] : a.w[2],
+              y3 = w2 ? b.w[1] : a.w[3], y4 = w2 ? b.w[2] : b.w[0], y5 = w2 ? b.w[3] : b.w[1];
+    const u32 x0 = w1 ? y1 : y0, x1 = w1 ? y2 : y1, x2 = w1 ? y3 : y2, x3 = w1 ? y4 : y3, x4 = w1 ? y5 : y4;
+    Vec16 r;
+    r.w[0] = __funnelshift_r(x0, x1, bs); r.w[1] = __funnelshift_r(x1, x2, bs);
+    r.w[2] = __funnelshift_r(x2, x3, bs); r.w[3] = __funnelshift_r(x3, x4, bs);
+    return r;
+#else
+    Vec16 r; memcpy(&r, p, 16); return r;
+#endif
+}
+
+// Short runs (each at most LaneGroups::kMaxBytes bytes): the lanes in `sel` pass their own (d, s, n); the runs are
+// packed and moved kRuns at a time, one lane group each: dst[d, d+n) = src[s, s+n).  A run must not read what another
+// run of the same call writes.  `pool` holds 32 entries; the caller orders reuse of it with a barrier.
+template <class W> LZ_HD void pool_copy_short(u8* dst, const u8* src, u32 sel, u32 d, u32 s, u32 n, PoolRun* pool)
+{
+    typedef LaneGroups<W> LG;
+    if (sel == 0) return;
+    const u32 lane = W::lane();
+    const u32 cnt = popc32(sel);
+    if ((sel >> lane) & 1) {
+        PoolRun e; e.a = d; e.b = s; e.c = n; e.d = 0;
+        pool[popc32(sel & ((1u << lane) - 1))] = e;
+    }
+    W::sync();
+    const u32 sub = lane / LG::kGroup;
+    for (u32 i = 0; i < cnt; i += LG::kRuns) {
+        const u32 k = i + sub;
+        const PoolRun e = pool[k < cnt ? k : 0];
+        lanes_copy_groups<W>(dst + e.a, src + e.b, k < cnt ? e.c : 0u);
+    }
+}
+
+// Long runs (each longer than 32 bytes).  A run is cut at the 16-byte boundaries of its DESTINATION: a head of < 16
+// bytes, aligned 16-byte chunks, a tail of < 16 bytes.  All chunks of all runs form one index space (exclusive scan of
+// the chunk counts); a sweep step gives every lane one chunk: aligned 16-byte store, source realigned from the aligned
+// vectors that hold it (ld_chunk16), two steps in flight.  The lane finds its run without a search: the runs that begin
+// inside the step's 32 chunks are marked in a bit mask (one warp reduction), and a population count below the lane
+// gives the run's index.  Heads and tails then go two runs per step, one lane group per piece.
+template <class W> LZ_HD void pool_copy_long(u8* dst, const u8* src, u32 sel, u32 d, u32 s, u32 n, PoolRun* pool)
+{
+    typedef LaneGroups<W> LG;
+    if (sel == 0) return;
+    const u32 lane = W::lane(), L = W::lanes();
+    const u32 cnt = popc32(sel);
+    const bool mine = ((sel >> lane) & 1) != 0;
+    u32 head = 0, nbody = 0;
+    if (mine) {
+        head = (u32)((16 - ((size_t)(dst + d) & 15)) & 15);          // n > 32 > head
+        nbody = (n - head) >> 4;                                      // >= 1
+    }
+    u32 total = 0;
+    const u32 cstart = W::excl_scan(nbody, &total);
+    if (mine) {
+        PoolRun e; e.a = cstart; e.b = d + head; e.c = s + head; e.d = head | (((n - head) & 15) << 4) | (nbody << 8);
+        pool[popc32(sel & ((1u << lane) - 1))] = e;
+    }
+    W::sync();
+    const bool is_run = lane < cnt;
+    const u32 my_start = pool[is_run ? lane : 0].a;                  // lane r speaks for run r in the step masks
+    const u32 le_mask = (2u << lane) - 1;
+    for (u32 base = 0; base < total; base += 2 * L) {
+        const bool two = base + L < total;
+        // step 0: chunks [base, base+L); step 1: chunks [base+L, base+2L)
+        const u32 r0 = popc32(W::ballot(is_run && my_start <= base)) - 1;
+        const u32 f0 = W::red_or((is_run && my_start > base && my_start < base + L) ? 1u << (my_start - base) : 0u);
+        u32 r1 = 0, f1 = 0;
+        if (two) {
+            r1 = popc32(W::ballot(is_run && my_start <= base + L)) - 1;
+            f1 = W::red_or((is_run && my_start > base + L && my_start < base + 2 * L) ? 1u << (my_start - base - L) : 0u);
+        }
+        const u32 c0 = base + lane, c1 = base + L + lane;
+        const bool v0 = c0 < total, v1 = two && c1 < total;
+        Vec16 x0, x1;
+        u8* to0 = dst; u8* to1 = dst;
+        if (v0) {
+            const PoolRun e = pool[r0 + popc32(f0 & le_mask)];
+            const u32 j = 16 * (c0 - e.a);
+            to0 = dst + e.b + j;
+            x0 = ld_chunk16(src + e.c + j);
+        }
+        if (v1) {
+            const PoolRun e = pool[r1 + popc32(f1 & le_mask)];
+            const u32 j = 16 * (c1 - e.a);
+            to1 = dst + e.b + j;
+            x1 = ld_chunk16(src + e.c + j);
+        }
+        if (v0) st_vec16(to0, x0.w[0], x0.w[1], x0.w[2], x0.w[3]);
+        if (v1) st_vec16(to1, x1.w[0], x1.w[1], x1.w[2], x1.w[3]);
+    }
+    // heads and tails: piece q = 2*run + (0 head | 1 tail), one lane group per piece, ceil(15 / group) rows
+    constexpr u32 G = LG::kGroup, PS = LG::kRuns;
+    const u32 o = lane & (G - 1), pi = lane / G;
+    for (u32 q0 = 0; q0 < 2 * cnt; q0 += PS) {
+        const u32 q = q0 + pi;
+        const PoolRun e = pool[q < 2 * cnt ? (q >> 1) : 0];
+        const u32 hd = e.d & 15, tl = (e.d >> 4) & 15, nbd = e.d >> 8;
+        u32 len = 0, db, sb;
+        if (q & 1) { len = tl; db = e.b + 16 * nbd; sb = e.c + 16 * nbd; }
+        else { len = hd; db = e.b - hd; sb = e.c - hd; }
+        if (q >= 2 * cnt) len = 0;
+        const u8* sp = src + sb + o; u8* dp = dst + db + o;
+        u8 b0 = 0, b1 = 0;
+        if (o < len) b0 = sp[0];
+        if (G < 15 && o + G < len) b1 = sp[G];
+        if (o < len) dp[0] = b0;
+        if (G < 15 && o + G < len) dp[G] = b1;
+        if (2 * G < 15) for (u32 i = o + 2 * G; i < len; i += G) dp[i - o] = sp[i - o];     // groups narrower than 8 lanes (tests)
+    }
 }
 
 }  // namespace lzb

@@ -260,10 +260,18 @@ def _content_is_defined(ref, comp, cap):
     return outs[0] == outs[1]
 
 
-@pytest.mark.parametrize("fn,count", [("lzb_host_decompress", 90), ("lzb_emu_decompress", 14)])
-def test_device_decoder_code_on_host_matches_reference(ref, shim, fn, count):
+@pytest.mark.parametrize("fn,count,variant,order", [("lzb_host_decompress", 90, 3, 0), ("lzb_host_decompress", 40, 0, 0),
+                                                    ("lzb_emu_decompress", 14, 3, 0), ("lzb_emu_decompress", 14, 3, 2),
+                                                    ("lzb_emu_decompress", 10, 3, 1), ("lzb_emu_decompress", 8, 0, 2),
+                                                    ("lzb_emu_decompress", 6, 1, 1), ("lzb_emu_decompress", 6, 2, 2)])
+def test_device_decoder_code_on_host_matches_reference(ref, shim, fn, count, variant, order):
     """The batch token loops (1 lane, and 32 emulated lanes = what the GPU runs): same return codes as the
-    reference on valid and damaged streams, same bytes whenever the reference's own output is well defined."""
+    reference on valid and damaged streams, same bytes whenever the reference's own output is well defined.
+    `variant` = schedule of the token loops (bit 0 pooled copy sweeps, bit 1 compact extension chain; the device
+    default is 3), `order` = order in which the emulator runs the lanes between two collectives (forward, reverse,
+    shuffled): a missing barrier only shows under some orders."""
+    shim.lzb_set_decode_variant(variant)
+    shim.lzb_emu_lane_order(order)
     rnd = random.Random(21)
     compared = 0
     for data in _inputs(21, count):
@@ -289,7 +297,32 @@ def test_device_decoder_code_on_host_matches_reference(ref, shim, fn, count):
             if rr > 0 and refs.stream_obeys_min_offset(c, cap):
                 compared += 1
                 assert o == ro, (fn, level, len(data), cap)
+    shim.lzb_set_decode_variant(3)
+    shim.lzb_emu_lane_order(0)
     assert compared > 0
+
+
+@pytest.mark.parametrize("level", [10, 21, 41])
+def test_emulated_decoder_full_blocks_all_schedules(ref, shim, level):
+    """Whole 128 KiB datagen blocks (long literal runs and matches, multi-byte length extensions), a two-inner-block
+    unit and highly repetitive input (overlapping and near matches) through every schedule of the 32-lane decoder, at
+    odd destination alignments (the pooled sweeps cut runs at the 16-byte boundaries of the destination)."""
+    data = lz.datagen(3 * BS)
+    rep = b"abcdefghij" * 3000 + bytes(range(256)) * 40 + b"\0" * 5000 + b"xyzw" * 4000 + data[:3000]
+    cases = [data[:BS], data[BS:2 * BS + 4321], rep]
+    for variant, order in ((3, 0), (3, 2), (1, 1), (2, 2)):
+        shim.lzb_set_decode_variant(variant)
+        shim.lzb_emu_lane_order(order)
+        for i, c in enumerate(cases):
+            comp = refs.ref_compress(ref, c, level)
+            buf = ctypes.create_string_buffer(len(c) + 96)
+            mis = (5 * i + variant + order) % 16
+            base = ctypes.addressof(buf) + mis
+            r = shim.lzb_emu_decompress(comp, len(comp), ctypes.cast(base, ctypes.c_char_p), len(c))
+            assert r == len(c) and ctypes.string_at(base, len(c)) == c, (level, variant, order, i, r)
+            assert ctypes.string_at(base + len(c), 16) == bytes(16), "wrote past the end of the destination"
+    shim.lzb_set_decode_variant(3)
+    shim.lzb_emu_lane_order(0)
 
 
 def test_huffman_stage_parity(ref, oracle, shim):
