@@ -2,6 +2,7 @@
 // launches, host staging.  Host-side logic only; the codec lives in decode.cuh / encode.cuh.
 #include "../../include/lizard_b200.h"
 #include "decode.cuh"
+#include "prepass.cuh"
 #include "encode.cuh"
 
 #include <cuda_runtime.h>
@@ -41,7 +42,9 @@ lizard_decode_units_kernel(DecodeBatch b)
         if (unit >= b.n_units) break;
         progress_wait(b.progress, unit, lane);
         const int r = decode_unit<WarpLanes, V>(b.src_base + b.src_off[unit], b.src_len[unit],
-                                             b.dst_base + b.dst_off[unit], b.dst_cap[unit], scratch, sh);
+                                                b.dst_base + b.dst_off[unit], b.dst_cap[unit], scratch, sh,
+                                                b.pre ? b.pre + unit : nullptr, b.arena,
+                                                b.seq ? b.seq + unit : nullptr, b.recs);
         if (lane == 0) b.result[unit] = r;
         __syncwarp();
         progress_done(b.progress, unit, lane);
@@ -93,7 +96,8 @@ struct Context {
     bool ready = false, failed = false;
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // compute / H2D / D2H
-    int dec_grid = 0, dec_variant = 3;
+    int dec_grid = 0, dec_variant = 15;       // bits 0-1: schedule of the token loops, bit 2: Huffman pre-pass, bit 3: token pre-pass
+    DeviceBuffer pre_ws, pre_arena, pre_scratch, seq_ws, seq_recs;
     DeviceBuffer dec_scratch, enc_scratch, counters;
     u32 counter_slot = 0;
     // staging for the host-pointer entry points
@@ -145,7 +149,9 @@ int ensure_context(Context& c, int device)
         c.failed = true; fail("cudaStreamCreate", e); return LIZARDB200_ERR_CUDA;
     }
     const size_t dec_smem = sizeof(DecWarpShared) * kDecWarps;
-    if (const char* v = getenv("LIZARDB200_DEC_VARIANT")) if (*v >= '0' && *v <= '3') c.dec_variant = *v - '0';
+    if (const char* v = getenv("LIZARDB200_DEC_VARIANT")) c.dec_variant = atoi(v) & 15;
+    e = cudaFuncSetAttribute(lizard_huf_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ExpWarpShared) * kExpWarps));
+    if (e != cudaSuccess) { c.failed = true; fail("cudaFuncSetAttribute(expand)", e); return LIZARDB200_ERR_CUDA; }
     e = cudaSuccess;
     for (int v = 0; v < 4 && e == cudaSuccess; ++v)
         e = cudaFuncSetAttribute(decode_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dec_smem);
@@ -181,6 +187,69 @@ u32* next_counter(Context& c, cudaStream_t s)
     return p;
 }
 
+// Huffman pre-pass (huf_expand.cuh / prepass.cuh): plan + expand kernels ahead of the token kernel, same stream.
+// Worth two extra launches only for real batches; the streaming (progress) launches of the frame path keep the
+// in-kernel expansion because their units arrive while the kernel is already running.
+constexpr u32 kPrepassMinUnits = 32;
+constexpr size_t kPrepassArenaPerUnit = 160u << 10;     // literals + flags of one 128 KiB block; overflow falls back in-kernel
+
+int launch_prepass(Context& c, DecodeBatch& b, cudaStream_t s)
+{
+    const size_t n = b.n_units;
+    const size_t ws_bytes = 256 + n * sizeof(UnitPre) + 2 * n * sizeof(HufJob);
+    const size_t arena_bytes = n * kPrepassArenaPerUnit;
+    const size_t scratch_bytes = (size_t)c.sm_count * kExpWarps * kExpJobs * sizeof(HufJobScratch);
+    if (ws_bytes > c.pre_ws.bytes || arena_bytes > c.pre_arena.bytes || scratch_bytes > c.pre_scratch.bytes) {
+        cudaStreamSynchronize(s);                       // an earlier launch may still be reading the buffers we are about to replace
+        CU_OK(c.pre_ws.reserve(ws_bytes));
+        CU_OK(c.pre_arena.reserve(arena_bytes));
+        CU_OK(c.pre_scratch.reserve(scratch_bytes));
+    }
+    PrepassBatch p;
+    p.src_base = b.src_base; p.src_off = b.src_off; p.src_len = b.src_len; p.n_units = b.n_units;
+    p.hdr = (PreHeader*)c.pre_ws.p;
+    p.pre = (UnitPre*)((u8*)c.pre_ws.p + 256);
+    p.jobs = (HufJob*)((u8*)c.pre_ws.p + 256 + n * sizeof(UnitPre));
+    p.arena = (u8*)c.pre_arena.p; p.arena_bytes = c.pre_arena.bytes;
+    p.scratch = (HufJobScratch*)c.pre_scratch.p;
+    CU_OK(cudaMemsetAsync(p.hdr, 0, sizeof(PreHeader), s));
+    lizard_huf_plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
+    lizard_huf_expand_kernel<<<c.sm_count, kExpWarps * 32, sizeof(ExpWarpShared) * kExpWarps, s>>>(p);
+    g_launches += 2;
+    CU_OK(cudaGetLastError());
+    b.pre = p.pre; b.arena = p.arena;
+    return LIZARDB200_OK;
+}
+
+// Token pre-pass (prepass.cuh: lizard_token_parse_kernel): one lane per unit parses the first inner block into sequence
+// records; runs behind the Huffman pre-pass (it reads the expanded streams) and ahead of the token kernel.
+constexpr size_t kSeqRecordsPerUnit = 2048;             // 32 KiB of records per unit on average; overflow falls back in-kernel
+
+int launch_token_parse(Context& c, DecodeBatch& b, cudaStream_t s)
+{
+    const size_t n = b.n_units;
+    const size_t ws_bytes = 64 + n * sizeof(UnitSeq);
+    size_t rec_bytes = n * kSeqRecordsPerUnit * sizeof(PoolRun);
+    if (rec_bytes < ((size_t)64 << 20)) rec_bytes = (size_t)64 << 20;
+    if (ws_bytes > c.seq_ws.bytes || rec_bytes > c.seq_recs.bytes) {
+        cudaStreamSynchronize(s);
+        CU_OK(c.seq_ws.reserve(ws_bytes));
+        CU_OK(c.seq_recs.reserve(rec_bytes));
+    }
+    SeqBatch q;
+    q.src_base = b.src_base; q.src_off = b.src_off; q.src_len = b.src_len; q.dst_cap = b.dst_cap; q.n_units = b.n_units;
+    q.pre = b.pre; q.arena = b.arena;
+    q.hdr = (SeqHeader*)c.seq_ws.p;
+    q.seq = (UnitSeq*)((u8*)c.seq_ws.p + 64);
+    q.recs = (PoolRun*)c.seq_recs.p; q.recs_cap = c.seq_recs.bytes / sizeof(PoolRun);
+    CU_OK(cudaMemsetAsync(q.hdr, 0, sizeof(SeqHeader), s));
+    lizard_token_parse_kernel<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(q);
+    g_launches++;
+    CU_OK(cudaGetLastError());
+    b.seq = q.seq; b.recs = q.recs;
+    return LIZARDB200_OK;
+}
+
 int launch_decode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* dSrcLen,
                   void* dDst, const u64* dDstOff, const u32* dDstCap, int* dResult, u32 n, cudaStream_t s,
                   const Progress* pg = nullptr)
@@ -193,6 +262,15 @@ int launch_decode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* d
     b.result = dResult; b.n_units = n;
     b.scratch = (u8*)c.dec_scratch.p;
     b.counter = next_counter(c, s);
+    b.pre = nullptr; b.arena = nullptr; b.seq = nullptr; b.recs = nullptr;
+    if ((c.dec_variant & 4) && pg == nullptr && n >= kPrepassMinUnits) {
+        int st = launch_prepass(c, b, s);
+        if (st != LIZARDB200_OK) return st;
+    }
+    if ((c.dec_variant & 8) && pg == nullptr && n >= kPrepassMinUnits) {
+        int st = launch_token_parse(c, b, s);
+        if (st != LIZARDB200_OK) return st;
+    }
     u32 warps_needed = n;
     int grid = (int)((warps_needed + kDecWarps - 1) / kDecWarps);
     if (grid > c.dec_grid) grid = c.dec_grid;
@@ -340,7 +418,7 @@ int LizardB200_setDecodeVariant(int variant)
     std::lock_guard<std::mutex> lk(c.mu);
     int st = ensure_context(c, g_device);
     if (st != LIZARDB200_OK) return st;
-    c.dec_variant = variant & 3;
+    c.dec_variant = variant & 15;
     return LIZARDB200_OK;
 }
 

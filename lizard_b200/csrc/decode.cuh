@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "lanes.cuh"
 #include "entropy_dec.cuh"
+#include "huf_expand.cuh"
 
 namespace lzb {
 
@@ -73,6 +74,10 @@ struct DecodeBatch {
     u8*        scratch;     // n_warps * kDecScratchPerWarp bytes (Huffman-expanded streams)
     u32*       counter;     // work queue head
     Progress   progress;
+    const UnitPre* pre;     // [n] streams expanded by the Huffman pre-pass (huf_expand.cuh), or null
+    const u8*  arena;       // the pre-pass's expansion arena
+    const UnitSeq* seq;     // [n] blocks parsed by the token pre-pass, or null
+    const PoolRun* recs;    // its sequence records
 };
 
 enum : u32 { kDecStreamScratch = kBlockSize + 64, kDecBigTableBytes = 2u << kHufTableLogMax,
@@ -175,6 +180,22 @@ LZ_HD_COLD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, co
     }
     while (p < count) out[p++] = (u8)hufx_sym(b, table, tl);
     return bits_done(b);
+}
+
+// segment k (0..3) of a stream prepared by huf_job_prepare: the pre-pass's unit of work (huf_expand.cuh).  `pay` = the
+// stream behind its weight header, `pc` its size.  Same split and same decoder as huf_decompress_lanes below.
+LZ_HD bool huf_job_segment(u8* dst, u32 n, const u8* pay, u32 pc, u32 k, const u16* table, u32 tl)
+{
+    const u32 l1 = rd_le16(pay), l2 = rd_le16(pay + 2), l3 = rd_le16(pay + 4);
+    const u32 l4 = pc - (l1 + l2 + l3 + 6);
+    const long seg = (long)((n + 3) / 4);
+    const u8* s = pay + 6 + (k > 0 ? l1 : 0) + (k > 1 ? l2 : 0) + (k > 2 ? l3 : 0);
+    const u32 len = k == 0 ? l1 : k == 1 ? l2 : k == 2 ? l3 : l4;
+    long cnt = k < 3 ? seg : (long)n - 3 * seg;
+    if (cnt < 0) cnt = 0;
+    int ierr = 0;
+    const bool good = huf_lane_segment(dst + (long)k * seg, cnt, s, len, table, tl, &ierr);
+    return good && ierr >= 0;
 }
 
 // HUF_decompress for one stream; all lanes return the same value (n or negative)
@@ -368,6 +389,159 @@ template <class W> LZ_HD int lizv1_serial(const Streams& s, u8* dst, long oend, 
         c.op += ml;
     }
     return 0;
+}
+
+// ---- token pre-pass: one lane parses one block (huf_expand.cuh, "token pre-pass") --------------------------------------
+// The reference's loops again, without the copies: every check of lz4_serial / lizv1_serial (plus the bounds the batch
+// path adds so that nothing outside a stream is ever read) must hold, otherwise the function returns false and the unit
+// is decoded by the in-kernel path, which reproduces the reference's verdict and error code.  Record = {a: literal run's
+// place in the literals stream, b: its length, c: match offset, d: match length}.
+LZ_HD void parse_prefetch(const u8* p)      // the walk is a chain of dependent loads: keep the lines ahead of it on their way
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
+LZ_HD bool parse_block_lz4(const Streams& s, u32 op0, u32 oend_u, PoolRun* out, u32* final_lp, u32* final_op)
+{
+    const long nl = (long)s.nlits, oend = (long)oend_u;
+    if (oend_u - op0 == 0) return false;
+    long lp = 0, op = op0;
+    for (u32 fp = 0; fp < s.nflags; ++fp) {
+        const u32 tok = s.flags[fp];
+        if (lp + 1024 < nl) parse_prefetch(s.lits + lp + 1024);
+        if ((fp & 63) == 0 && fp + 256 < s.nflags) parse_prefetch(s.flags + fp + 256);
+        u32 len = tok & 15;
+        if (len == 15) {
+            u32 v, sz;
+            if (lp > nl - 5 || !ext_field(s.lits, nl, lp, &v, &sz)) return false;
+            len = 15 + v; lp += sz;
+        }
+        if (op + len > oend - 16 || lp + len > nl - 18) return false;
+        PoolRun r; r.a = (u32)lp; r.b = len;
+        op += len; lp += len;
+        r.c = rd_le16(s.lits + lp); lp += 2;
+        if ((long)r.c > op) return false;
+        u32 ml = tok >> 4;
+        if (ml == 15) {
+            u32 v, sz;
+            if (lp > nl - 5 || !ext_field(s.lits, nl, lp, &v, &sz)) return false;
+            ml = 15 + v; lp += sz;
+        }
+        ml += kMinMatch;
+        if (op + ml > oend - 16) return false;
+        r.d = ml;
+        out[fp] = r;
+        op += ml;
+    }
+    const long rest = nl - lp;
+    if (rest < 0 || op + rest > oend) return false;
+    *final_lp = (u32)lp; *final_op = (u32)op;
+    return true;
+}
+
+LZ_HD bool parse_block_lizv1(const Streams& s, u32 op0, u32 oend_u, PoolRun* out, u32* final_lp, u32* final_op)
+{
+    const long nl = (long)s.nlits, oend = (long)oend_u;
+    if (oend_u - op0 == 0) return false;
+    long lp = 0, op = op0;
+    u32 p16 = 0, p24 = 0, last_off = 0;
+    for (u32 fp = 0; fp < s.nflags; ++fp) {
+        const u32 tok = s.flags[fp];
+        if (lp + 1024 < nl) parse_prefetch(s.lits + lp + 1024);
+        if ((fp & 63) == 0) {
+            if (fp + 256 < s.nflags) parse_prefetch(s.flags + fp + 256);
+            if (p16 + 512 < s.noff16) parse_prefetch(s.off16 + p16 + 512);
+        }
+        PoolRun r; r.a = (u32)lp; r.b = 0;
+        u32 ml;
+        if (tok >= 32) {
+            u32 len = tok & 7;
+            if (len == 7) {
+                u32 v, sz;
+                if (lp > nl - 1 || !ext_field(s.lits, nl, lp, &v, &sz)) return false;
+                len = 7 + v; lp += sz;
+            }
+            if (op + len > oend - 16 || lp > nl - 16 || lp + (long)len > nl) return false;
+            r.a = (u32)lp; r.b = len;
+            op += len; lp += len;
+            if ((tok >> 7) == 0) {
+                if (p16 + 2 > s.noff16) return false;
+                last_off = rd_le16(s.off16 + p16); p16 += 2;
+            } else if (p16 > s.noff16) return false;
+            ml = (tok >> 3) & 15;
+            if (ml == 15) {
+                u32 v, sz;
+                if (lp > nl - 1 || !ext_field(s.lits, nl, lp, &v, &sz)) return false;
+                ml = 15 + v; lp += sz;
+            }
+        } else {
+            if (tok < kLastLongOff) ml = tok + kMmLongOff;
+            else {
+                u32 v, sz;
+                if (lp > nl - 1 || !ext_field(s.lits, nl, lp, &v, &sz)) return false;
+                ml = v + kLastLongOff + kMmLongOff; lp += sz;
+            }
+            if ((long)p24 > (long)s.noff24 - 3) return false;
+            last_off = rd_le24(s.off24 + p24); p24 += 3;
+        }
+        if ((long)last_off > op) return false;
+        if (op + ml > oend - 16) return false;
+        r.c = last_off; r.d = ml;
+        out[fp] = r;
+        op += ml;
+    }
+    const long rest = nl - lp;
+    if (rest < 0 || op + rest > oend) return false;
+    *final_lp = (u32)lp; *final_op = (u32)op;
+    return true;
+}
+
+// Streams of the first inner block of a unit for the token pre-pass: raw streams in place, Huffman-coded ones from the
+// Huffman pre-pass's arena.  False when the block is not of the plain kind (stored block, damaged header, a coded stream
+// the pre-pass did not expand): decode_unit then does everything itself.  Mirrors decode_unit / read_stream.
+LZ_HD bool locate_first_block(const u8* src, u32 csize_u, const UnitPre* up, const u8* arena, Streams* st, int* lizv1)
+{
+    const long csize = (long)csize_u;
+    if (csize < 2) return false;
+    const int level = src[0];
+    if (level < (int)kMinLevel || level > (int)kMaxLevel) return false;
+    *lizv1 = level_is_lizv1(level);
+    long ip = 1;
+    const u32 hdr = src[ip++];
+    if (hdr == kFlagRaw || (hdr & kFlagLen)) return false;
+    if (ip > csize - 15) return false;
+    {
+        const long len_end = ip + 3 + (long)rd_le24(src + ip);
+        if (len_end > csize - 3) return false;
+        ip = len_end;
+    }
+    st->src_begin = src; st->src_end = src + csize;
+    const u32 bit[4] = { kFlagOff16, kFlagOff24, kFlagFlags, kFlagLiterals };
+    const u8* ptr[4]; u32 len[4];
+    for (int k = 0; k < 4; ++k) {
+        if (hdr & bit[k]) {
+            if (k < 2 || up == nullptr) return false;
+            if (ip > csize - 6) return false;
+            const u32 n = rd_le24(src + ip), c = rd_le24(src + ip + 3);
+            if (n > kBlockSize || ip + (long)c > csize - 6) return false;
+            const u32 slot = k == 3 ? kSlotLiterals : kSlotFlags;
+            if (up->state[slot] != kPreDone) return false;
+            ptr[k] = arena + up->off[slot]; len[k] = n;
+            ip += (long)c + 6;
+        } else {
+            if (ip > csize - 3) return false;
+            len[k] = rd_le24(src + ip);
+            ptr[k] = src + ip + 3;
+            ip += 3 + (long)len[k];
+        }
+    }
+    if (ip > csize) return false;
+    st->off16 = ptr[0]; st->noff16 = len[0]; st->off24 = ptr[1]; st->noff24 = len[1];
+    st->flags = ptr[2]; st->nflags = len[2]; st->lits = ptr[3]; st->nlits = len[3];
+    return true;
 }
 
 // ---- batch execution shared by both flavours: copy the literal runs, then resolve the matches in order ----
@@ -760,10 +934,35 @@ template <class W, int V> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* ds
     return (int)(c.op - (long)op0);
 }
 
+// Token loop of a block the token pre-pass has parsed: lane i of a batch loads record i, one scan gives the output
+// positions, the pooled sweeps move the bytes.  Every bound was checked when the records were written.
+template <class W> LZ_HD int decode_block_from_records(const Streams& s, u8* dst, u32 op0, const UnitSeq* us, const PoolRun* recs,
+                                                       DecWarpShared* sh)
+{
+    const u32 NL = W::lanes(), lane = W::lane();
+    const PoolRun* const mine = recs + us->off;
+    u32 op = op0;
+    for (u32 t = 0; t < us->nseq; t += NL) {
+        const u32 nb = us->nseq - t < NL ? us->nseq - t : NL;
+        PoolRun r; r.a = r.b = r.c = r.d = 0;
+        if (lane < nb) r = mine[t + lane];
+        if (lane < nb && (long)r.a + 2048 < (long)s.nlits) W::prefetch(s.lits + r.a + 2048);
+        u32 tot = 0;
+        const u32 O = W::excl_scan(r.b + r.d, &tot);
+        run_batch_copies_pool<W>(dst, s.lits, nb, r.a, r.b, op + O, r.c, r.d, sh->desc);
+        op += tot;
+    }
+    const u32 rest = s.nlits - us->final_lp;
+    if (rest >= kWideMinBytes) lanes_copy_wide<W>(dst + op, s.lits + us->final_lp, rest, false);
+    else lanes_copy<W>(dst + op, s.lits + us->final_lp, rest);
+    W::sync();
+    return (int)(op + rest - op0);
+}
+
 // One stream header.  Returns 1 on success, 0 on failure (Lizard_readStream, lizard_decompress.c:72-112).
 // `ip` is an offset into the unit.
 template <class W> LZ_HD int read_stream(bool huff, const u8* src, long csize, long& ip, u8* scratch, const u8** ptr, u32* len,
-                                        DecWarpShared* sh)
+                                        DecWarpShared* sh, const u8* expanded = nullptr)
 {
     if (!huff) {
         if (ip > csize - 3) return 0;
@@ -775,6 +974,7 @@ template <class W> LZ_HD int read_stream(bool huff, const u8* src, long csize, l
     if (ip > csize - 6) return 0;
     const u32 n = rd_le24(src + ip), c = rd_le24(src + ip + 3);
     if (n > kBlockSize || ip + (long)c > csize - 6) return 0;
+    if (expanded) { ip += (long)c + 6; *ptr = expanded; *len = n; return 1; }      // done by the pre-pass
     const int r = huf_decompress_lanes<W>(scratch, n, src + ip + 6, c, sh);
     if (r < 0 || (u32)r != n) return 0;
     ip += (long)c + 6;
@@ -783,7 +983,9 @@ template <class W> LZ_HD int read_stream(bool huff, const u8* src, long csize, l
 }
 
 // Lizard_decompress_safe for one unit; every lane returns the same value.
-template <class W, int V> LZ_HD int decode_unit(const u8* src, u32 csize_u, u8* dst, u32 cap, u8* scratch, DecWarpShared* sh)
+template <class W, int V> LZ_HD int decode_unit(const u8* src, u32 csize_u, u8* dst, u32 cap, u8* scratch, DecWarpShared* sh,
+                                                const UnitPre* up = nullptr, const u8* arena = nullptr,
+                                                const UnitSeq* us = nullptr, const PoolRun* recs = nullptr)
 {
     const long csize = (long)csize_u;
     if (csize < 1) return 0;
@@ -793,6 +995,7 @@ template <class W, int V> LZ_HD int decode_unit(const u8* src, u32 csize_u, u8* 
     long ip = 1;
     long op = 0;
     while (ip < csize) {
+        const long ip0 = ip;                   // 1 for the unit's first inner block
         const u32 hdr = src[ip++];
         if (hdr == kFlagRaw) {
             if (ip > csize - 3) return -1;
@@ -816,10 +1019,16 @@ template <class W, int V> LZ_HD int decode_unit(const u8* src, u32 csize_u, u8* 
         s.src_begin = src; s.src_end = src + csize;
         if (!read_stream<W>(hdr & kFlagOff16, src, csize, ip, scratch + 3 * kDecStreamScratch, &s.off16, &s.noff16, sh)) return -1;
         if (!read_stream<W>(hdr & kFlagOff24, src, csize, ip, scratch + 2 * kDecStreamScratch, &s.off24, &s.noff24, sh)) return -1;
-        if (!read_stream<W>(hdr & kFlagFlags, src, csize, ip, scratch + 1 * kDecStreamScratch, &s.flags, &s.nflags, sh)) return -1;
-        if (!read_stream<W>(hdr & kFlagLiterals, src, csize, ip, scratch, &s.lits, &s.nlits, sh)) return -1;
+        // streams of the unit's first inner block may have been expanded by the pre-pass already
+        const bool first = up != nullptr && ip0 == 1;
+        const u8* const pre_flags = (first && up->state[kSlotFlags] == kPreDone) ? arena + up->off[kSlotFlags] : nullptr;
+        const u8* const pre_lits = (first && up->state[kSlotLiterals] == kPreDone) ? arena + up->off[kSlotLiterals] : nullptr;
+        if (!read_stream<W>(hdr & kFlagFlags, src, csize, ip, scratch + 1 * kDecStreamScratch, &s.flags, &s.nflags, sh, pre_flags)) return -1;
+        if (!read_stream<W>(hdr & kFlagLiterals, src, csize, ip, scratch, &s.lits, &s.nlits, sh, pre_lits)) return -1;
         if (ip > csize) return -1;
-        const int res = lizv1 ? decode_tokens_lizv1<W, V>(s, dst, (u32)op, cap, sh) : decode_tokens_lz4<W, V>(s, dst, (u32)op, cap, sh);
+        int res;
+        if (us != nullptr && ip0 == 1 && us->state == kPreDone) res = decode_block_from_records<W>(s, dst, (u32)op, us, recs, sh);
+        else res = lizv1 ? decode_tokens_lizv1<W, V>(s, dst, (u32)op, cap, sh) : decode_tokens_lz4<W, V>(s, dst, (u32)op, cap, sh);
         if (res <= 0) return res;
         op += res;
     }

@@ -65,6 +65,37 @@ extern "C" int lzb_host_decompress(const unsigned char* src, int csize, unsigned
     return r;
 }
 
+// The Huffman pre-pass (huf_expand.cuh) as the device runs it, serially: plan the unit's first inner block, expand the
+// planned streams into an arena with the same per-segment function, hand the result to the token decoder.
+struct HostPre { lzb::UnitPre up; unsigned char* arena; int jobs; };
+static void host_prepass(const unsigned char* src, int csize, HostPre* hp, int sabotage)
+{
+    hp->up.state[0] = hp->up.state[1] = lzb::kPreNone; hp->up.off[0] = hp->up.off[1] = 0;
+    hp->arena = (unsigned char*)malloc(2 * (size_t)lzb::pre_slot_bytes(lzb::kBlockSize));
+    lzb::HufJob jobs[2];
+    const lzb::u32 nj = lzb::plan_unit(src, (lzb::u32)csize, jobs);
+    hp->jobs = (int)nj;
+    lzb::HufJobScratch* ws = (lzb::HufJobScratch*)malloc(sizeof(lzb::HufJobScratch));
+    lzb::u16* table = (lzb::u16*)malloc(sizeof(lzb::u16) << 11);
+    size_t cursor = 0;
+    for (lzb::u32 i = 0; i < nj; ++i) {
+        lzb::HufJob& j = jobs[i];
+        j.dst = cursor; cursor += (size_t)lzb::pre_slot_bytes(j.n);
+        lzb::u32 h = 0, tl = 0;
+        bool ok = lzb::huf_job_prepare(src + j.src, j.c, j.n, table, ws, &h, &tl);
+        for (lzb::u32 k = 0; ok && k < 4; ++k)
+            ok = lzb::huf_job_segment(hp->arena + j.dst, j.n, src + j.src + h, j.c - h, k, table, tl);
+        if (sabotage && ok) memset(hp->arena + j.dst, 0x5A, j.n);     // tests: proves the token decoder reads the arena
+        hp->up.off[j.slot] = j.dst;
+        hp->up.state[j.slot] = ok ? lzb::kPreDone : lzb::kPreNone;
+    }
+    free(ws); free(table);
+}
+// bit 0 of `mode`: 32 emulated lanes instead of one; bit 1: overwrite the expanded streams (negative control);
+// bit 2: also run the token pre-pass (one-lane parse of the first inner block into sequence records).
+// *jobs_done = streams the Huffman pre-pass expanded + 16 if the token pre-pass parsed the block.
+extern "C" int lzb_decompress_with_prepass(const unsigned char* src, int csize, unsigned char* dst, int cap, int mode, int* jobs_done);
+
 extern "C" void lzb_host_token_stats(unsigned long long* fast, unsigned long long* slow)
 {
 #if defined(LZB_STATS)
@@ -231,16 +262,17 @@ extern "C" int lzb_emu_compress(const unsigned char* src, int n, unsigned char* 
     return a.result;
 }
 
-struct EmuDecompressArgs { const unsigned char* src; int csize; unsigned char* dst; int cap; unsigned char* scratch; lzb::DecWarpShared* sh; int result; };
+struct EmuDecompressArgs { const unsigned char* src; int csize; unsigned char* dst; int cap; unsigned char* scratch; lzb::DecWarpShared* sh; int result;
+                           const lzb::UnitPre* up; const unsigned char* arena; const lzb::UnitSeq* us; const lzb::PoolRun* recs; };
 static void emu_decompress_body(void* p)
 {
     EmuDecompressArgs* a = (EmuDecompressArgs*)p;
     int r;
     switch (g_dec_variant & 3) {
-    case 0: r = lzb::decode_unit<EmuLanes, 0>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh); break;
-    case 1: r = lzb::decode_unit<EmuLanes, 1>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh); break;
-    case 2: r = lzb::decode_unit<EmuLanes, 2>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh); break;
-    default: r = lzb::decode_unit<EmuLanes, 3>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh); break;
+    case 0: r = lzb::decode_unit<EmuLanes, 0>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh, a->up, a->arena, a->us, a->recs); break;
+    case 1: r = lzb::decode_unit<EmuLanes, 1>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh, a->up, a->arena, a->us, a->recs); break;
+    case 2: r = lzb::decode_unit<EmuLanes, 2>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh, a->up, a->arena, a->us, a->recs); break;
+    default: r = lzb::decode_unit<EmuLanes, 3>(a->src, (lzb::u32)a->csize, a->dst, (lzb::u32)a->cap, a->scratch, a->sh, a->up, a->arena, a->us, a->recs); break;
     }
     if (EmuLanes::lane() == 0) a->result = r;
 }
@@ -251,11 +283,46 @@ extern "C" int lzb_emu_decompress(const unsigned char* src, int csize, unsigned 
     if (csize < 1) return 0;
     if (cap < 0) return -1;
     EmuDecompressArgs a;
-    a.src = src; a.csize = csize; a.dst = dst; a.cap = cap; a.result = -1;
+    a.src = src; a.csize = csize; a.dst = dst; a.cap = cap; a.result = -1; a.up = nullptr; a.arena = nullptr; a.us = nullptr; a.recs = nullptr;
     a.scratch = (unsigned char*)malloc(lzb::kDecScratchPerWarp);
     a.sh = (lzb::DecWarpShared*)malloc(sizeof(lzb::DecWarpShared));
     a.sh->big_table = (lzb::u16*)(a.scratch + 4 * lzb::kDecStreamScratch);
     emu::run(emu_decompress_body, &a);
     free(a.scratch); free(a.sh);
     return a.result;
+}
+
+extern "C" int lzb_decompress_with_prepass(const unsigned char* src, int csize, unsigned char* dst, int cap, int mode, int* jobs_done)
+{
+    if (csize < 1) return 0;
+    if (cap < 0) return -1;
+    HostPre hp;
+    host_prepass(src, csize, &hp, mode & 2);
+    if (jobs_done) *jobs_done = (hp.up.state[0] == lzb::kPreDone) + (hp.up.state[1] == lzb::kPreDone);
+    lzb::UnitSeq us; us.off = 0; us.nseq = 0; us.state = lzb::kPreNone; us.final_lp = us.final_op = 0;
+    lzb::PoolRun* recs = nullptr;
+    if (mode & 4) {
+        lzb::Streams st; int lizv1 = 0;
+        if (lzb::locate_first_block(src, (lzb::u32)csize, &hp.up, hp.arena, &st, &lizv1)) {
+            recs = (lzb::PoolRun*)malloc(sizeof(lzb::PoolRun) * (st.nflags + 1));
+            const bool ok = lizv1 ? lzb::parse_block_lizv1(st, 0, (lzb::u32)cap, recs, &us.final_lp, &us.final_op)
+                                  : lzb::parse_block_lz4(st, 0, (lzb::u32)cap, recs, &us.final_lp, &us.final_op);
+            if (ok) { us.nseq = st.nflags; us.state = lzb::kPreDone; if (jobs_done) *jobs_done += 16; }
+        }
+    }
+    unsigned char* scratch = (unsigned char*)malloc(lzb::kDecScratchPerWarp);
+    lzb::DecWarpShared* sh = (lzb::DecWarpShared*)malloc(sizeof(lzb::DecWarpShared));
+    sh->big_table = (lzb::u16*)(scratch + 4 * lzb::kDecStreamScratch);
+    int r;
+    if (mode & 1) {
+        EmuDecompressArgs a;
+        a.src = src; a.csize = csize; a.dst = dst; a.cap = cap; a.result = -1; a.up = &hp.up; a.arena = hp.arena;
+        a.us = (mode & 4) ? &us : nullptr; a.recs = recs;
+        a.scratch = scratch; a.sh = sh;
+        emu::run(emu_decompress_body, &a);
+        r = a.result;
+    } else r = lzb::decode_unit<lzb::HostLanes, 3>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, sh, &hp.up, hp.arena,
+                                                   (mode & 4) ? &us : nullptr, recs);
+    free(scratch); free(sh); free(hp.arena); free(recs);
+    return r;
 }

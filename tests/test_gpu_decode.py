@@ -106,3 +106,34 @@ def test_decode_corrupt_matches_reference(ref, data4m, level):
                 mism.append((idx, len(b), cap, "content"))
     assert not mism, (level, len(mism), mism[:10])
     assert n_cmp > 0
+
+
+def test_decode_schedules_and_prepass_agree(ref, data4m):
+    """Every decode configuration (token-loop schedules, with and without the Huffman pre-pass) returns the same
+    codes and bytes on a mixed batch: all levels side by side, damaged streams in between, a multi-inner-block unit."""
+    rnd = random.Random(77)
+    L = lz.lib()
+    L.LizardB200_setDecodeVariant.argtypes = [ctypes.c_int]
+    units, caps = [], []
+    for i in range(48):
+        level = [41, 30, 10, 21, 45, 37][i % 6]
+        blk = data4m[i * BS:(i + 1) * BS] if i % 5 else data4m[i * BS:i * BS + rnd.randrange(1, BS)]
+        k = refs.ref_compress(ref, blk, level)
+        units.append(k); caps.append(len(blk))
+        b = bytearray(k)
+        for _ in range(rnd.randrange(1, 4)):
+            b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        units.append(bytes(b)); caps.append(len(blk))
+    big = data4m[: 3 * BS + 555]
+    units.append(refs.ref_compress(ref, big, 41)); caps.append(len(big))
+    want = [refs.ref_decompress(ref, u, c) for u, c in zip(units, caps)]
+    try:
+        for variant in (15, 7, 11, 3, 12, 0, 5, 6):
+            assert L.LizardB200_setDecodeVariant(variant) == 0
+            got = lz.decompress_batch(units, caps)
+            for i, ((r, o), (rr, ro)) in enumerate(zip(got, want)):
+                assert r == rr, (variant, i, r, rr)
+                if rr > 0 and refs.stream_obeys_min_offset(units[i], caps[i]):
+                    assert o == ro, (variant, i)
+    finally:
+        L.LizardB200_setDecodeVariant(15)

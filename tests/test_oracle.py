@@ -325,6 +325,54 @@ def test_emulated_decoder_full_blocks_all_schedules(ref, shim, level):
     shim.lzb_emu_lane_order(0)
 
 
+def test_prepasses_match_reference(ref, shim):
+    """The decoder's two pre-passes run serially on the host -- Huffman pre-pass (plan the first inner block, expand the
+    planned streams segment by segment) and token pre-pass (one-lane parse of the block into sequence records, mode bit
+    4) -- feeding the 1-lane and the 32-lane token decoder: same return codes and bytes as the reference on valid and
+    damaged streams, and the token decoder really consumes the pre-expanded bytes (negative control)."""
+    shim.lzb_decompress_with_prepass.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.POINTER(ctypes.c_int)]
+
+    def dec(comp, cap, mode):
+        buf = ctypes.create_string_buffer(cap + 64)
+        jd = ctypes.c_int(0)
+        r = shim.lzb_decompress_with_prepass(comp, len(comp), buf, cap, mode, ctypes.byref(jd))
+        return r, buf.raw[:max(r, 0)], jd.value
+
+    rnd = random.Random(3)
+    data = lz.datagen(3 * BS)
+    expanded = 0
+    for level in (41, 30, 45, 10, 37):
+        for blk in (data[:BS], data[BS:2 * BS + 999], data[:20000]):
+            comp = refs.ref_compress(ref, blk, level)
+            for mode in (0, 1, 4, 5):                             # one lane / 32 emulated lanes, without / with token pre-pass
+                r, out, jd = dec(comp, len(blk), mode)
+                assert r == len(blk) and out == blk, (level, len(blk), mode, r)
+                if mode & 4:
+                    assert jd & 16, (level, len(blk), mode)           # the block was parsed into records
+            expanded += jd & 15
+            if level >= 30 and len(blk) >= BS:
+                assert (jd & 15) >= 1, (level, jd)
+                assert dec(comp, len(blk), 2)[1] != blk           # expanded streams overwritten -> output must change
+            for _ in range(25):
+                bad = bytearray(comp)
+                m = rnd.randrange(3)
+                if m == 0:
+                    bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+                elif m == 1:
+                    bad = bad[: rnd.randrange(0, len(bad) + 1)]
+                else:
+                    bad[rnd.randrange(min(60, len(bad)))] = rnd.randrange(256)
+                bad = bytes(bad)
+                cap = rnd.choice([len(blk), len(blk) - 1, len(blk) + 50])
+                rr, ro = refs.ref_decompress(ref, bad, cap)
+                r, out, _ = dec(bad, cap, rnd.choice([0, 4, 5]))
+                assert r == rr, (level, len(blk), len(bad), cap, r, rr)
+                if rr > 0 and refs.stream_obeys_min_offset(bad, cap):
+                    assert out == ro
+    assert expanded > 0
+
+
 def test_huffman_stage_parity(ref, oracle, shim):
     spd = refs.ref_speed()
     spd.HUF_compress.restype = ctypes.c_size_t

@@ -2,7 +2,8 @@
 """dec_bench.py -- kernel-only timing of the decode (and encode) kernel on device-resident data, several levels and both
 decode schedules in one process.  A development tool: bench.py is the contract bench.  One JSON line per case.
 
-  python tools/dec_bench.py [--size-mib 1024] [--levels 10,21,41] [--iters 5] [--variants 1,0] [--encode]
+  python tools/dec_bench.py [--size-mib 1024] [--levels 10,21,41] [--iters 5] [--variants 15,7,3] [--encode]
+  variant bits: 1 pooled copy sweeps, 2 compact extension chain, 4 Huffman pre-pass, 8 token pre-pass (LizardB200_setDecodeVariant)
 """
 import argparse
 import ctypes
@@ -19,7 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size-mib", type=int, default=1024)
     ap.add_argument("--levels", default="10,21,41")
-    ap.add_argument("--variants", default="1,0")
+    ap.add_argument("--variants", default="15,7,3")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--encode", action="store_true")
     args = ap.parse_args()
@@ -87,7 +88,7 @@ def main():
             print(json.dumps({"kernel": "decode", "variant": v, "level": level, "ms_best": round(best, 3), "ms_avg": round(avg, 3),
                               "MBps": round(nbytes / 1e6 / (avg / 1e3), 1), "algo_GBps": round(algo / 1e9 / (avg / 1e3), 1),
                               "frac_of_6560": round(algo / 1e9 / (avg / 1e3) / 6560.6, 4), "round_trip_ok": ok}), flush=True)
-        L.LizardB200_setDecodeVariant(1)
+        L.LizardB200_setDecodeVariant(15)
 
 
 if __name__ == "__main__":
