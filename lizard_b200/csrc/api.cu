@@ -96,7 +96,7 @@ struct Context {
     bool ready = false, failed = false;
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // compute / H2D / D2H
-    int dec_grid = 0, dec_variant = 15;       // bits 0-1: schedule of the token loops, bit 2: Huffman pre-pass, bit 3: token pre-pass
+    int dec_grid = 0, dec_variant = 7;        // bits 0-1: schedule of the token loops, bit 2: Huffman pre-pass, bit 3: token pre-pass
     DeviceBuffer pre_ws, pre_arena, pre_scratch, seq_ws, seq_recs;
     DeviceBuffer dec_scratch, enc_scratch, counters;
     u32 counter_slot = 0;

@@ -136,4 +136,4 @@ def test_decode_schedules_and_prepass_agree(ref, data4m):
                 if rr > 0 and refs.stream_obeys_min_offset(units[i], caps[i]):
                     assert o == ro, (variant, i)
     finally:
-        L.LizardB200_setDecodeVariant(15)
+        L.LizardB200_setDecodeVariant(7)
