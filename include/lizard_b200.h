@@ -163,7 +163,7 @@ int LizardB200_compress_device(const void* dSrc, const uint64_t* dSrcOff, const 
 /* number of kernel launches issued by this library since load (bench.py reports it as gpu_launches) */
 unsigned long long LizardB200_launchCount(void);
 /* diagnostics: how this thread's device decodes, four bits: 1 = pooled copy sweeps, 2 = compact length-extension chain,
- * 4 = Huffman pre-pass kernels, 8 = token pre-pass kernel ahead of the token kernel (default 15).  Results are identical
+ * 4 = Huffman pre-pass kernels, 8 = token pre-pass kernel ahead of the token kernel (default 7).  Results are identical
  * for every value; tools/dec_bench.py times them against each other. */
 int LizardB200_setDecodeVariant(int variant);
 

@@ -150,7 +150,19 @@ int ensure_context(Context& c, int device)
     }
     const size_t dec_smem = sizeof(DecWarpShared) * kDecWarps;
     if (const char* v = getenv("LIZARDB200_DEC_VARIANT")) c.dec_variant = atoi(v) & 15;
+    // Shared memory and L1 share one 256 KB array per SM.  Left alone, the driver sizes the carve-out for as many CTAs as
+    // the kernel's registers would allow, which leaves these kernels -- whose grids are sized by hand -- a 28 KB L1 for
+    // hundreds of byte streams; ask for exactly what the resident CTAs use.
+    auto carveout = [&](size_t smem_per_sm, const char* env) {
+        if (const char* v = getenv(env)) return atoi(v);
+        const size_t total = prop.sharedMemPerMultiprocessor;
+        const size_t pct = (smem_per_sm * 100 + total - 1) / total;
+        return (int)(pct > 100 ? 100 : pct);
+    };
     e = cudaFuncSetAttribute(lizard_huf_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ExpWarpShared) * kExpWarps));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(lizard_huf_expand_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 carveout(sizeof(ExpWarpShared) * kExpWarps + 1024, "LIZARDB200_EXP_CARVEOUT"));
     if (e != cudaSuccess) { c.failed = true; fail("cudaFuncSetAttribute(expand)", e); return LIZARDB200_ERR_CUDA; }
     e = cudaSuccess;
     for (int v = 0; v < 4 && e == cudaSuccess; ++v)
@@ -163,7 +175,14 @@ int ensure_context(Context& c, int device)
         if (v == 0 || p < per_sm) per_sm = p;
     }
     if (per_sm < 1) per_sm = 1;
+    if (const char* v = getenv("LIZARDB200_DEC_CTAS_PER_SM")) {     // diagnostics: fewer units in flight (L2 residency sweeps)
+        const int want = atoi(v);
+        if (want >= 1 && want < per_sm) per_sm = want;
+    }
     c.dec_grid = c.sm_count * per_sm;
+    for (int v = 0; v < 4; ++v)
+        cudaFuncSetAttribute(decode_kernel(v), cudaFuncAttributePreferredSharedMemoryCarveout,
+                             carveout((size_t)per_sm * (dec_smem + 1024), "LIZARDB200_DEC_CARVEOUT"));
     if ((e = c.dec_scratch.reserve((size_t)c.dec_grid * kDecWarps * kDecScratchPerWarp)) != cudaSuccess) {
         c.failed = true; fail("cudaMalloc(decode scratch)", e); return LIZARDB200_ERR_MEMORY;
     }

@@ -82,14 +82,14 @@ struct DecodeBatch {
 
 enum : u32 { kDecStreamScratch = kBlockSize + 64, kDecBigTableBytes = 2u << kHufTableLogMax,
              kDecScratchPerWarp = 4 * kDecStreamScratch + kDecBigTableBytes };
-enum : u32 { kDecSmemTableLog = 11 };    // Lizard's encoder never exceeds 11 (HUF_TABLELOG_DEFAULT); 12 is legal input
 
 typedef PoolRun SeqDesc;                          // 16-byte sequence descriptor (see run_batch_copies)
 
 struct DecWarpShared {             // per-warp shared memory
     SeqDesc desc[64];              // literal-run and match descriptors of the current token batch
-    u16 table[1u << kDecSmemTableLog];
-    u16* big_table;                // 2^12-entry table in the warp's global scratch, used only for tableLog 12
+    u16* big_table;                // single-symbol table of the in-kernel Huffman expansion: 2^12 entries in the warp's
+                                   // global scratch (the pre-pass expands the streams of real batches; keeping 4 KiB per
+                                   // warp in shared memory for the rest would cost the token loops their L1)
     union {
         HufStatsScratch stats;                       // while a Huffman header is being read
         struct { u32 ent[32]; u32 epre[32]; } chain; // during the token loops: length-extension chain of a batch
@@ -129,8 +129,15 @@ LZ_HD u64 ld64_any(const u8* p)          // unaligned 8-byte little-endian load 
     return rd_le64(p);
 #endif
 }
-// own function on the device: its loop must not share a register allocation with the token loops
-LZ_HD_COLD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u16* table, u32 tl, int* init_err)
+template <class T> LZ_HD u32 huf_step(BitReader& b, const T& tab)          // single-symbol step (HUF_decodeSymbolX2)
+{
+    const u32 e = tab.look((u32)((b.win << (b.used & 63)) >> 32));
+    b.used += e >> 8;
+    return e & 255;
+}
+
+// one segment, one lane; true when the bitstream ended exactly
+template <class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* src, u32 len, const T& tab, int* init_err)
 {
     BitReader b;
     int e = bits_init(b, src, len);
@@ -143,7 +150,7 @@ LZ_HD_COLD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, co
     if (len >= 24) {
         while (p < count && ((size_t)(out + p) & 3) != 0 && b.ptr >= b.start + 16) {
             if (bits_reload(b) != kBitsUnfinished) break;
-            out[p++] = (u8)hufx_sym(b, table, tl);
+            out[p++] = (u8)huf_step(b, tab);
         }
         while (p + 4 <= count && b.ptr >= b.start + 16 && b.used <= 64 && ((size_t)(out + p) & 3) == 0) {
             b.ptr -= b.used >> 3;                          // bits_reload, "ptr >= start + 8" case
@@ -154,19 +161,18 @@ LZ_HD_COLD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, co
             // four table steps on a 2 x 32-bit copy of the window kept left-aligned (<= 7 + 4*12 bits leave it)
             u32 hi = (u32)(b.win >> 32), lo = (u32)b.win;
             hi = __funnelshift_l(lo, hi, b.used); lo <<= b.used;
-            const u32 down = 32 - tl;
-            u32 e = table[hi >> down], n = e >> 8, word = e & 255, used = b.used + n;
+            u32 e = tab.look(hi), n = e >> 8, word = e & 255, used = b.used + n;
             hi = __funnelshift_l(lo, hi, n); lo <<= n;
-            e = table[hi >> down]; n = e >> 8; word |= (e & 255) << 8; used += n;
+            e = tab.look(hi); n = e >> 8; word |= (e & 255) << 8; used += n;
             hi = __funnelshift_l(lo, hi, n); lo <<= n;
-            e = table[hi >> down]; n = e >> 8; word |= (e & 255) << 16; used += n;
+            e = tab.look(hi); n = e >> 8; word |= (e & 255) << 16; used += n;
             hi = __funnelshift_l(lo, hi, n);
-            e = table[hi >> down]; word |= e << 24; used += e >> 8;
+            e = tab.look(hi); word |= e << 24; used += e >> 8;
             b.used = used;
             *reinterpret_cast<u32*>(out + p) = word;
 #else
-            const u32 s0 = hufx_sym(b, table, tl), s1 = hufx_sym(b, table, tl);
-            const u32 s2 = hufx_sym(b, table, tl), s3 = hufx_sym(b, table, tl);
+            const u32 s0 = huf_step(b, tab), s1 = huf_step(b, tab);
+            const u32 s2 = huf_step(b, tab), s3 = huf_step(b, tab);
             *reinterpret_cast<u32*>(out + p) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
 #endif
             p += 4;
@@ -176,15 +182,21 @@ LZ_HD_COLD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, co
         if (bits_reload(b) != kBitsUnfinished) break;
         long k = count - p; if (k > 4) k = 4;
         if (k <= 0) break;
-        for (long j = 0; j < k; ++j) out[p++] = (u8)hufx_sym(b, table, tl);
+        for (long j = 0; j < k; ++j) out[p++] = (u8)huf_step(b, tab);
     }
-    while (p < count) out[p++] = (u8)hufx_sym(b, table, tl);
+    while (p < count) out[p++] = (u8)huf_step(b, tab);
     return bits_done(b);
+}
+// own function on the device: its loop must not share a register allocation with the token loops
+LZ_HD_COLD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u16* table, u32 tl, int* init_err)
+{
+    HufFull tab; tab.t = table; tab.down = 32 - tl;
+    return huf_lane_segment_t(out, count, src, len, tab, init_err);
 }
 
 // segment k (0..3) of a stream prepared by huf_job_prepare: the pre-pass's unit of work (huf_expand.cuh).  `pay` = the
-// stream behind its weight header, `pc` its size.  Same split and same decoder as huf_decompress_lanes below.
-LZ_HD bool huf_job_segment(u8* dst, u32 n, const u8* pay, u32 pc, u32 k, const u16* table, u32 tl)
+// stream behind its weight header, `pc` its size.  Same split and same walk as huf_decompress_lanes below.
+LZ_HD bool huf_job_segment(u8* dst, u32 n, const u8* pay, u32 pc, u32 k, const HufCompact& table)
 {
     const u32 l1 = rd_le16(pay), l2 = rd_le16(pay + 2), l3 = rd_le16(pay + 4);
     const u32 l4 = pc - (l1 + l2 + l3 + 6);
@@ -194,7 +206,7 @@ LZ_HD bool huf_job_segment(u8* dst, u32 n, const u8* pay, u32 pc, u32 k, const u
     long cnt = k < 3 ? seg : (long)n - 3 * seg;
     if (cnt < 0) cnt = 0;
     int ierr = 0;
-    const bool good = huf_lane_segment(dst + (long)k * seg, cnt, s, len, table, tl, &ierr);
+    const bool good = huf_lane_segment_t(dst + (long)k * seg, cnt, s, len, huf_view(&table), &ierr);
     return good && ierr >= 0;
 }
 
@@ -211,11 +223,11 @@ template <class W> LZ_HD int huf_decompress_lanes(u8* dst, u32 n, const u8* src,
     if (lane == 0) {
         u32 nsym = 0;
         h = huf_read_stats(sh->weights, sh->rank, &nsym, &tl, src, c, &sh->stats);
-        if (h >= 0) huf_fill_dtable(tl <= kDecSmemTableLog ? sh->table : sh->big_table, sh->weights, sh->rank, nsym, tl);
+        if (h >= 0) huf_fill_dtable(sh->big_table, sh->weights, sh->rank, nsym, tl);
     }
     h = W::bcast(h);
     tl = (u32)W::bcast((int)tl);
-    const u16* const table = tl <= kDecSmemTableLog ? sh->table : sh->big_table;
+    const u16* const table = sh->big_table;
     if (h < 0) return h;
     if ((u32)h >= c) return kErrSrcSize;
     W::sync();

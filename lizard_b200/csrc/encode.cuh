@@ -212,14 +212,18 @@ inline EncodeShape encode_shape(const LevelParams& lp)
     EncodeShape sh;
     sh.table_bytes = lp.hashLog <= 14 ? hash_packed_bytes(lp.hashLog) : 0;
     sh.hist_bytes = lp.huffman ? 4096 : 0;
-    const size_t sm_bytes = 228 * 1024, cta_reserved = 1024, cta_max = 227 * 1024;
-    // Three shapes, picked from measurements (profiles/: shape sweep):
-    //   A. 2 CTAs x 14 warps when at least 12 of the 14 get a shared-memory table (level 10/20-style small tables),
+    const size_t sm_max = 228 * 1024, cta_reserved = 1024, cta_max = 227 * 1024;
+    // Shared memory and L1 are one 256 KB array per SM, and the 14-warp shapes do better when they do not take all of it:
+    // their tables are sized for the 196 KB carve-out step, which leaves the L1 60 KB for the input and the match
+    // candidates (B200, 1 GiB, explicit carve-out: level 10 14,11,2 9.24 ms against 10.88 ms for 14,13,2, 9.43 for 14,9,2;
+    // level 21 14,2,2 32.4 ms against 47.5 for 14,3,2 and 35.0 for 14,1,2; profiles/r01_SUMMARY.md section 8).
+    const size_t sm_pref = 196 * 1024;
+    // Three shapes, picked from measurements (profiles/: shape sweeps):
+    //   A. 2 CTAs x 14 warps when at least 12 of the 14 could get a shared-memory table (level 10-style small tables),
     //      or when there is no shared-memory table at all (hashLog 18: everything global anyway);
     //   B. one warp per CTA, every warp on a shared-memory table, when that keeps >= 16 warps resident;
-    //   C. otherwise 2 CTAs x 14 warps with as many shared-memory tables as fit (large tables: 24.4 GB/s at level 41
-    //      against 18.2 with 2 x 8 warps and 11.6 with 5 single-warp CTAs; level 21: 22.7 / 24.3 / 16.4).
-    auto tabs_for = [&](int warps, int ctas) -> int {
+    //   C. otherwise 2 CTAs x 14 warps with as many shared-memory tables as fit the preferred carve-out.
+    auto tabs_for = [&](int warps, int ctas, size_t sm_bytes) -> int {
         const size_t budget = sm_bytes / ctas < cta_max + cta_reserved ? sm_bytes / ctas - cta_reserved : cta_max;
         const size_t hist = (size_t)warps * sh.hist_bytes;
         if (hist > budget) return -1;
@@ -232,10 +236,12 @@ inline EncodeShape encode_shape(const LevelParams& lp)
         best.warps = warps; best.smem_tables = tabs; best.ctas_per_sm = ctas;
         best.smem = (size_t)tabs * sh.table_bytes + (size_t)warps * sh.hist_bytes;
     };
-    const int tabs14 = tabs_for(kEncWarpsPerCta, kEncCtasPerSM);
+    const int fit14 = tabs_for(kEncWarpsPerCta, kEncCtasPerSM, sm_max);       // tables that fit at all
+    int tabs14 = tabs_for(kEncWarpsPerCta, kEncCtasPerSM, sm_pref);           // tables we give the 14-warp shapes
+    if (tabs14 < 0) tabs14 = fit14 < 0 ? -1 : 0;
     int solo = 0;                                                   // shape B: resident single-warp CTAs
-    for (int ctas = kEncMaxWarpsPerSM; ctas >= 1; --ctas) if (tabs_for(1, ctas) >= (sh.table_bytes ? 1 : 0)) { solo = ctas; break; }
-    if (!sh.table_bytes || tabs14 >= 12) set(kEncWarpsPerCta, tabs14 < 0 ? 0 : tabs14, kEncCtasPerSM);
+    for (int ctas = kEncMaxWarpsPerSM; ctas >= 1; --ctas) if (tabs_for(1, ctas, sm_max) >= (sh.table_bytes ? 1 : 0)) { solo = ctas; break; }
+    if (!sh.table_bytes || fit14 >= 12) set(kEncWarpsPerCta, tabs14 < 0 ? 0 : tabs14, kEncCtasPerSM);
     else if (solo >= 16) set(1, 1, solo);
     else if (tabs14 >= 0) set(kEncWarpsPerCta, tabs14, kEncCtasPerSM);
     else set(1, 1, solo >= 1 ? solo : 1);
@@ -263,6 +269,12 @@ inline cudaError_t encode_launch(const EncodeConfig& c, const EncodeBatch& b, cu
     const size_t need = (b.n_units + sh.warps - 1) / sh.warps;
     if (grid > need) grid = need;
     if (grid * sh.warps * per_warp > c.scratch_bytes) grid = c.scratch_bytes / (per_warp * sh.warps);
+    {   // shared memory and L1 share one array: ask for the carve-out the resident CTAs use, no more (see api.cu)
+        const size_t total = 228 * 1024, use = (size_t)per_sm * (sh.smem + 1024);
+        int pct = (int)((use * 100 + total - 1) / total);
+        if (pct > 100) pct = 100;
+        cudaFuncSetAttribute(lizard_encode_units_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     lizard_encode_units_kernel<<<(unsigned)grid, 32 * sh.warps, sh.smem, s>>>(b, (u32)sh.smem_tables, (u32)sh.table_bytes,
                                                                             (u32)sh.hist_bytes, per_warp);
     *launches = 1;

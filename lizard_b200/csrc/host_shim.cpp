@@ -76,21 +76,43 @@ static void host_prepass(const unsigned char* src, int csize, HostPre* hp, int s
     const lzb::u32 nj = lzb::plan_unit(src, (lzb::u32)csize, jobs);
     hp->jobs = (int)nj;
     lzb::HufJobScratch* ws = (lzb::HufJobScratch*)malloc(sizeof(lzb::HufJobScratch));
-    lzb::u16* table = (lzb::u16*)malloc(sizeof(lzb::u16) << 11);
+    lzb::HufCompact* table = (lzb::HufCompact*)malloc(sizeof(lzb::HufCompact));
     size_t cursor = 0;
     for (lzb::u32 i = 0; i < nj; ++i) {
         lzb::HufJob& j = jobs[i];
         j.dst = cursor; cursor += (size_t)lzb::pre_slot_bytes(j.n);
-        lzb::u32 h = 0, tl = 0;
-        bool ok = lzb::huf_job_prepare(src + j.src, j.c, j.n, table, ws, &h, &tl);
+        lzb::u32 h = 0;
+        bool ok = lzb::huf_job_prepare(src + j.src, j.c, j.n, table, ws, &h);
         for (lzb::u32 k = 0; ok && k < 4; ++k)
-            ok = lzb::huf_job_segment(hp->arena + j.dst, j.n, src + j.src + h, j.c - h, k, table, tl);
+            ok = lzb::huf_job_segment(hp->arena + j.dst, j.n, src + j.src + h, j.c - h, k, *table);
         if (sabotage && ok) memset(hp->arena + j.dst, 0x5A, j.n);     // tests: proves the token decoder reads the arena
         hp->up.off[j.slot] = j.dst;
         hp->up.state[j.slot] = ok ? lzb::kPreDone : lzb::kPreNone;
     }
     free(ws); free(table);
 }
+// HufCompact (two-level table of the Huffman pre-pass) against the reference-layout table built from the same weights:
+// number of indices (all 1 << tl, three fillings of the bits below the index) whose lookup differs.
+extern "C" int lzb_huf_compact_check(const unsigned char* weights, int nsym, int tl)
+{
+    lzb::u32 rank_a[lzb::kHufTableLogMax + 1] = {0}, rank_b[lzb::kHufTableLogMax + 1] = {0};
+    for (int s = 0; s < nsym; ++s) { rank_a[weights[s]]++; rank_b[weights[s]]++; }
+    lzb::u16* full = (lzb::u16*)malloc(sizeof(lzb::u16) << tl);
+    lzb::HufCompact* c = (lzb::HufCompact*)malloc(sizeof(lzb::HufCompact));
+    lzb::huf_fill_dtable(full, weights, rank_a, (lzb::u32)nsym, (lzb::u32)tl);
+    lzb::huf_fill_compact(c, weights, rank_b, (lzb::u32)nsym, (lzb::u32)tl);
+    lzb::HufFull f; f.t = full; f.down = 32u - (lzb::u32)tl;
+    int bad = 0;
+    const lzb::u32 low[3] = { 0u, 0xFFFFFFFFu, 0x5A5A5A5Au };
+    for (lzb::u32 idx = 0; idx < (1u << tl); ++idx)
+        for (int k = 0; k < 3; ++k) {
+            const lzb::u32 hi = (idx << (32 - tl)) | (low[k] >> tl);
+            if (f.look(hi) != lzb::huf_view(c).look(hi)) ++bad;
+        }
+    free(full); free(c);
+    return bad;
+}
+
 // bit 0 of `mode`: 32 emulated lanes instead of one; bit 1: overwrite the expanded streams (negative control);
 // bit 2: also run the token pre-pass (one-lane parse of the first inner block into sequence records).
 // *jobs_done = streams the Huffman pre-pass expanded + 16 if the token pre-pass parsed the block.

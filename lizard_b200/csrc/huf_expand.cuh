@@ -8,7 +8,8 @@
 //                read_stream do (lizard_decompress.c:115-264, :72-112) and appends one job per Huffman-coded literals /
 //                flags stream: {payload, c, n, slot in the expansion arena};
 //   2. expand -- a warp takes 8 jobs: lanes 0-7 read the weight headers and fill 8 single-symbol tables in shared memory
-//                (HUF_readStats / HUF_readDTableX2), then lane l decodes segment l%4 of job l/4: 32 lanes busy;
+//                (HUF_readStats / HUF_readDTableX2; two-level form, HufCompact), then lane l decodes segment l%4 of
+//                job l/4: 32 lanes busy;
 //   3. the token kernel finds `state == kPreDone` for the stream and uses the expanded bytes from the arena.
 // A job is only marked done when the stream decoded the regular way (all four bitstreams end exactly).  Anything else
 // -- stored / RLE streams, damaged headers, tableLog 12, arena exhausted, later inner blocks of a multi-block unit --
@@ -105,10 +106,10 @@ struct HufJobScratch {      // per table-building lane; lives in global memory (
     u32 pad[3];
 };
 
-// Weight header -> table (2^11 entries of symbol | nbBits << 8).  True when the stream is of the regular kind the
-// pre-pass handles; *hdr_len = bytes of weight header, *tl = table log.  Same conditions, in the same order, as the
-// regular path of huf_decompress_lanes (decode.cuh) / HUF_decompress4X2 (huf_decompress.c:231-351).
-LZ_HD bool huf_job_prepare(const u8* src, u32 c, u32 n, u16* table, HufJobScratch* ws, u32* hdr_len, u32* tl_out)
+// Weight header -> two-level table (HufCompact, decode.cuh).  True when the stream is of the regular kind the
+// pre-pass handles; *hdr_len = bytes of weight header.  Same conditions, in the same order, as the regular path of
+// huf_decompress_lanes (decode.cuh) / HUF_decompress4X2 (huf_decompress.c:231-351).
+LZ_HD bool huf_job_prepare(const u8* src, u32 c, u32 n, HufCompact* table, HufJobScratch* ws, u32* hdr_len)
 {
     if (n == 0 || c >= n || c == 1) return false;       // error / stored / RLE: the in-kernel path deals with them
     u32 nsym = 0, tl = 0;
@@ -118,8 +119,8 @@ LZ_HD bool huf_job_prepare(const u8* src, u32 c, u32 n, u16* table, HufJobScratc
     if (pc < 10) return false;
     const u8* pay = src + h;
     if (rd_le16(pay) + rd_le16(pay + 2) + rd_le16(pay + 4) + 6 > pc) return false;
-    huf_fill_dtable(table, ws->weights, ws->rank, nsym, tl);
-    *hdr_len = (u32)h; *tl_out = tl;
+    huf_fill_compact(table, ws->weights, ws->rank, nsym, tl);
+    *hdr_len = (u32)h;
     return true;
 }
 

@@ -17,12 +17,14 @@ struct PrepassBatch {
     HufJobScratch* scratch;     // [expand grid warps][kExpJobs]
 };
 
-enum : u32 { kExpWarps = 7, kExpJobs = 8 };      // warps per CTA (one CTA per SM: 7 x 8 tables of 4 KiB), jobs per warp round
+// warps per CTA, jobs per warp round.  One CTA per SM: 1 GiB of 128 KiB blocks is 32768 literals segments = 1024 warps,
+// 7 x 148 warps take them in a single wave; 7 x 8 two-level tables are 74 KB, the rest of the SM's 256 KB stays L1 for
+// the 224 bitstreams read at once.
+enum : u32 { kExpWarps = 7, kExpJobs = 8 };
 
 struct ExpWarpShared {
-    u16 table[kExpJobs][1u << 11];
-    u32 hdr_len[kExpJobs], tl[kExpJobs], ok[kExpJobs];
-    u32 pad[8];
+    HufCompact table[kExpJobs];
+    u32 hdr_len[kExpJobs], ok[kExpJobs];
 };
 
 struct SeqBatch {
@@ -110,9 +112,9 @@ lizard_huf_expand_kernel(PrepassBatch b)
             const u32 nj = total - first < kExpJobs ? total - first : kExpJobs;
             if (lane < nj) {                                          // weight headers and tables, one lane per job
                 const HufJob j = list[first + lane];
-                u32 h = 0, tl = 0;
-                const bool ok = huf_job_prepare(b.src_base + j.src, j.c, j.n, sh->table[lane], ws, &h, &tl);
-                sh->hdr_len[lane] = h; sh->tl[lane] = tl; sh->ok[lane] = ok ? 1u : 0u;
+                u32 h = 0;
+                const bool ok = huf_job_prepare(b.src_base + j.src, j.c, j.n, &sh->table[lane], ws, &h);
+                sh->hdr_len[lane] = h; sh->ok[lane] = ok ? 1u : 0u;
             }
             __syncwarp();
             const u32 jj = lane >> 2, k = lane & 3;                   // lane -> (job, segment)
@@ -122,7 +124,7 @@ lizard_huf_expand_kernel(PrepassBatch b)
                 j = list[first + jj];
                 if (sh->ok[jj]) {
                     const u32 h = sh->hdr_len[jj];
-                    good = huf_job_segment(b.arena + j.dst, j.n, b.src_base + j.src + h, j.c - h, k, sh->table[jj], sh->tl[jj]);
+                    good = huf_job_segment(b.arena + j.dst, j.n, b.src_base + j.src + h, j.c - h, k, sh->table[jj]);
                 }
             }
             const u32 g = __ballot_sync(LZB_FULL, good);

@@ -373,6 +373,35 @@ def test_prepasses_match_reference(ref, shim):
     assert expanded > 0
 
 
+def test_huffman_two_level_table_equals_reference_layout(shim):
+    """The pre-pass's two-level decode table (HufCompact) answers every lookup like the 1 << tableLog table of
+    HUF_readDTableX2 (huf_decompress.c:87-133), for random complete codes of every table log."""
+    rnd = random.Random(5)
+    shim.lzb_huf_compact_check.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    seen = set()
+    for trial in range(400):
+        max_depth = rnd.randrange(1, 12)
+        leaves = [1, 1]
+        want = rnd.randrange(2, 257)
+        while len(leaves) < want:
+            cand = [i for i, d in enumerate(leaves) if d < max_depth]
+            if not cand:
+                break
+            # prefer deep leaves now and then so that long codes (the second level) are well populated
+            i = max(cand, key=lambda k: leaves[k]) if rnd.random() < 0.3 else rnd.choice(cand)
+            d = leaves.pop(i)
+            leaves += [d + 1, d + 1]
+        tl = max(leaves)
+        syms = rnd.sample(range(256), len(leaves))
+        weights = bytearray(256)
+        for s, d in zip(syms, leaves):
+            weights[s] = tl + 1 - d
+        nsym = max(syms) + 1
+        assert shim.lzb_huf_compact_check(bytes(weights), nsym, tl) == 0, (trial, tl, len(leaves))
+        seen.add(tl)
+    assert seen >= set(range(2, 12))
+
+
 def test_huffman_stage_parity(ref, oracle, shim):
     spd = refs.ref_speed()
     spd.HUF_compress.restype = ctypes.c_size_t

@@ -23,6 +23,9 @@ def main():
     ap.add_argument("--variants", default="15,7,3")
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--encode", action="store_true")
+    ap.add_argument("--enc-shapes", default="", help="encode launch shapes to time, 'warps,tables,ctas' separated by ';' "
+                    "(LIZARDB200_ENC_SHAPE is read at every launch); implies --encode")
+    ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
     import torch
     import lizard_b200 as lz
@@ -75,12 +78,19 @@ def main():
         torch.cuda.synchronize()
         ctot = int(d_csize.sum())
         algo = nbytes + ctot
-        if args.encode:
+        shapes = [x for x in args.enc_shapes.split(";") if x] or ([""] if args.encode else [])
+        for shape in shapes:
+            if shape:
+                os.environ["LIZARDB200_ENC_SHAPE"] = shape
             best, avg = timed(compress, args.iters)
-            print(json.dumps({"kernel": "encode", "level": level, "ms_best": round(best, 3), "ms_avg": round(avg, 3),
-                              "MBps": round(nbytes / 1e6 / (avg / 1e3), 1), "algo_GBps": round(algo / 1e9 / (avg / 1e3), 1),
-                              "compressed": ctot}), flush=True)
-        for v in [int(x) for x in args.variants.split(",")]:
+            print(json.dumps({"kernel": "encode", "level": level, "shape": shape or "default", "ms_best": round(best, 3),
+                              "ms_avg": round(avg, 3), "MBps": round(nbytes / 1e6 / (avg / 1e3), 1),
+                              "algo_GBps": round(algo / 1e9 / (avg / 1e3), 1), "compressed": int(d_csize.sum())}), flush=True)
+        os.environ.pop("LIZARDB200_ENC_SHAPE", None)
+        if shapes:
+            compress()                                  # leave the default shape's output for the decode runs
+            torch.cuda.synchronize()
+        for v in ([] if args.no_decode else [int(x) for x in args.variants.split(",")]):
             assert L.LizardB200_setDecodeVariant(v) == 0
             d_back.zero_()
             best, avg = timed(decompress, args.iters)
