@@ -148,6 +148,12 @@ struct EncodeConfig {
     size_t scratch_bytes = 0;
 };
 
+// the fast parsers keep candidate tags next to the packed entries (encode_core.cuh: tag8)
+#if !defined(LZB_ENC_TAGS)
+#define LZB_ENC_TAGS 1
+#endif
+LZ_HD bool enc_tagged(const LevelParams& lp) { return LZB_ENC_TAGS && (lp.parser == kParserFastSmall || lp.parser == kParserFast); }
+
 constexpr u32 kEncBigTableBytes = 4u << 18;          // plain 32-bit table for hashLog 18 or multi-inner-block units
 // Residency: registers allow 28 warps per SM (72 registers/thread), shared memory 26 packed level-10 tables
 // (8.5 KiB each).  The grid therefore runs CTAs of 14 warps, two per SM, where 13 warps keep their hash table in
@@ -167,10 +173,12 @@ lizard_encode_units_kernel(EncodeBatch b, u32 smem_tables, u32 table_bytes, u32 
     const bool packed_ok = wic < smem_tables;
     u8* tab = enc_smem + (size_t)wic * table_bytes;
     u32* seg_hist = reinterpret_cast<u32*>(enc_smem + (size_t)smem_tables * table_bytes + (size_t)wic * hist_bytes);
+    const bool tagged = enc_tagged(klp);
     HashTable packed, plain;
     packed.t32 = nullptr; packed.lo = reinterpret_cast<u16*>(tab);
     packed.hi = reinterpret_cast<u32*>(tab + ((size_t)2 << klp.hashLog));
-    plain.t32 = reinterpret_cast<u32*>(my + sizeof(EncWork)); plain.lo = nullptr; plain.hi = nullptr;
+    packed.tag = tagged ? tab + hash_packed_bytes(klp.hashLog, false) : nullptr; packed.tagged = 0;
+    plain.t32 = reinterpret_cast<u32*>(my + sizeof(EncWork)); plain.lo = nullptr; plain.hi = nullptr; plain.tag = nullptr;
     if (lane == 0) work->huf.seg_count = reinterpret_cast<u32 (*)[256]>(seg_hist);
     __syncwarp();
     for (;;) {
@@ -181,6 +189,7 @@ lizard_encode_units_kernel(EncodeBatch b, u32 smem_tables, u32 table_bytes, u32 
         progress_wait(b.progress, unit, lane);
         const u32 len = b.src_len[unit];
         // 17-bit packed entries need every position of the unit below 2^17
+        plain.tagged = (tagged && len <= kBlockSize) ? 1u : 0u;      // 7 spare bits per entry when positions stay below 2^17
         const HashTable& T = (packed_ok && len <= kBlockSize) ? packed : plain;
         const int r = encode_unit<WarpLanes>(b.src_base + b.src_off[unit], len,
                                              b.dst_base + b.dst_off[unit], b.dst_cap[unit], b.level, T, work);
@@ -210,7 +219,7 @@ struct EncodeShape { int warps, smem_tables; size_t table_bytes, hist_bytes, sme
 inline EncodeShape encode_shape(const LevelParams& lp)
 {
     EncodeShape sh;
-    sh.table_bytes = lp.hashLog <= 14 ? hash_packed_bytes(lp.hashLog) : 0;
+    sh.table_bytes = lp.hashLog <= 14 ? hash_packed_bytes(lp.hashLog, enc_tagged(lp)) : 0;
     sh.hist_bytes = lp.huffman ? 4096 : 0;
     const size_t sm_max = 228 * 1024, cta_reserved = 1024, cta_max = 227 * 1024;
     // Shared memory and L1 are one 256 KB array per SM, and the 14-warp shapes do better when they do not take all of it:
@@ -219,7 +228,7 @@ inline EncodeShape encode_shape(const LevelParams& lp)
     // level 21 14,2,2 32.4 ms against 47.5 for 14,3,2 and 35.0 for 14,1,2; profiles/r01_SUMMARY.md section 8).
     const size_t sm_pref = 196 * 1024;
     // Three shapes, picked from measurements (profiles/: shape sweeps):
-    //   A. 2 CTAs x 14 warps when at least 12 of the 14 could get a shared-memory table (level 10-style small tables),
+    //   A. 2 CTAs x 14 warps when at least 8 of the 14 could get a shared-memory table (level 10-style small tables),
     //      or when there is no shared-memory table at all (hashLog 18: everything global anyway);
     //   B. one warp per CTA, every warp on a shared-memory table, when that keeps >= 16 warps resident;
     //   C. otherwise 2 CTAs x 14 warps with as many shared-memory tables as fit the preferred carve-out.
@@ -241,7 +250,7 @@ inline EncodeShape encode_shape(const LevelParams& lp)
     if (tabs14 < 0) tabs14 = fit14 < 0 ? -1 : 0;
     int solo = 0;                                                   // shape B: resident single-warp CTAs
     for (int ctas = kEncMaxWarpsPerSM; ctas >= 1; --ctas) if (tabs_for(1, ctas, sm_max) >= (sh.table_bytes ? 1 : 0)) { solo = ctas; break; }
-    if (!sh.table_bytes || fit14 >= 12) set(kEncWarpsPerCta, tabs14 < 0 ? 0 : tabs14, kEncCtasPerSM);
+    if (!sh.table_bytes || fit14 >= 8) set(kEncWarpsPerCta, tabs14 < 0 ? 0 : tabs14, kEncCtasPerSM);
     else if (solo >= 16) set(1, 1, solo);
     else if (tabs14 >= 0) set(kEncWarpsPerCta, tabs14, kEncCtasPerSM);
     else set(1, 1, solo >= 1 ? solo : 1);
@@ -261,6 +270,9 @@ inline cudaError_t encode_launch(const EncodeConfig& c, const EncodeBatch& b, cu
     }
     const size_t per_warp = c.per_warp_small;
     int per_sm = 0;
+    // the occupancy query honours the kernel's current carve-out preference, which the previous launch (possibly of
+    // another level) left behind: ask with the whole array available, then set what this launch uses
+    cudaFuncSetAttribute(lizard_encode_units_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lizard_encode_units_kernel, 32 * sh.warps, sh.smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;

@@ -247,16 +247,37 @@ template <class W> LZ_HD void emit_streams(const EncStreams& s, const u8* src, b
 // position 65535 and from then on bits are only ever set; `pos_hint` (a position not below anything inserted so
 // far) lets the first half of a block skip the bitmap altogether.
 // Larger units (several dependent inner blocks) use plain 32-bit entries in global memory.
+// Candidate tags (fastSmall / fast parsers).  On datagen -P50 a 128 KiB block makes ~60 000 probes and finds ~1000
+// matches: once the table has filled, nearly every probe finds an in-range candidate, reads its four bytes -- a 32-byte
+// sector somewhere in the last 64 KiB of one of 4000 blocks in flight, i.e. mostly DRAM -- and throws it away.  An entry
+// therefore also carries a few hash bits of the four bytes at its position (tag8; independent of the bucket hash), and a
+// probe only reads the candidate when the tags agree.  A differing tag proves the bytes differ, so the parse is unchanged.
+// Only the fast parsers keep tags up to date (set_t) and consult them (get_t / maybe); the others use get / set and never
+// look at them.
+LZ_HD u32 tag8(u32 v4) { return (v4 * 0x9E3779B1u) >> 24; }
+enum : u32 { kNoTag = 0x100u };
+
 struct HashTable {       // runtime descriptor handed to encode_unit
     u32* t32;            // plain form (global memory), or null
     u16* lo;             // packed form
     u32* hi;
+    u8*  tag;            // packed form: one tag byte per entry, or null
+    u32  tagged;         // plain form: every position of the unit is below 2^17, bits 25..31 of an entry hold a tag
 };
 struct PlainTable {
-    u32* t32;
-    LZ_HDM explicit PlainTable(const HashTable& d) : t32(d.t32) {}
-    LZ_HDM u32 get(u32 h, u32) const { return t32[h]; }
+    u32* t32; u32 tagged;
+    LZ_HDM explicit PlainTable(const HashTable& d) : t32(d.t32), tagged(d.tagged) {}
+    LZ_HDM u32 get(u32 h, u32) const { const u32 e = t32[h]; return tagged ? e & 0x1FFFFFFu : e; }
     LZ_HDM void set(u32 h, u32 abs_index) const { t32[h] = abs_index; }
+    LZ_HDM u32 get_t(u32 h, u32, u32* tag) const
+    {
+        const u32 e = t32[h];
+        if (!tagged) { *tag = kNoTag; return e; }
+        *tag = e >> 25;
+        return e & 0x1FFFFFFu;
+    }
+    LZ_HDM void set_t(u32 h, u32 abs_index, u32 tag) const { t32[h] = tagged ? abs_index | (tag >> 1) << 25 : abs_index; }
+    LZ_HDM bool maybe(u32 stored, u32 mine) const { return stored == kNoTag || stored == (mine >> 1); }
     template <class W> LZ_HDM void clear(u32 hash_log) const
     {
         const u32 n = 1u << hash_log;
@@ -265,8 +286,8 @@ struct PlainTable {
     }
 };
 struct PackedTable {
-    u16* lo; u32* hi;
-    LZ_HDM explicit PackedTable(const HashTable& d) : lo(d.lo), hi(d.hi) {}
+    u16* lo; u32* hi; u8* tag;
+    LZ_HDM explicit PackedTable(const HashTable& d) : lo(d.lo), hi(d.hi), tag(d.tag) {}
     LZ_HDM u32 get(u32 h, u32 pos_hint) const
     {
         u32 p = lo[h];
@@ -285,16 +306,23 @@ struct PackedTable {
         else if (hi[h >> 5] & bit) abort();        // insertion order assumption violated
 #endif
     }
+    LZ_HDM u32 get_t(u32 h, u32 pos_hint, u32* t) const { *t = tag ? (u32)tag[h] : (u32)kNoTag; return get(h, pos_hint); }
+    LZ_HDM void set_t(u32 h, u32 abs_index, u32 t) const { set(h, abs_index); if (tag) tag[h] = (u8)t; }
+    LZ_HDM bool maybe(u32 stored, u32 mine) const { return stored == kNoTag || stored == mine; }
     template <class W> LZ_HDM void clear(u32 hash_log) const
     {
         const u32 n = 1u << hash_log;
         u32* lo32 = reinterpret_cast<u32*>(lo);
         for (u32 i = W::lane(); i < n / 2; i += W::lanes()) lo32[i] = 0;
         for (u32 i = W::lane(); i < n / 32; i += W::lanes()) hi[i] = 0;
-        W::sync();
+        W::sync();                                  // tags of empty entries are never looked at
     }
 };
-LZ_HD size_t hash_packed_bytes(u32 hash_log) { return ((size_t)2 << hash_log) + ((size_t)1 << hash_log) / 8; }
+// bytes of a packed table: 16-bit entries + the bit plane (+ one tag byte per entry for the fast parsers)
+LZ_HD size_t hash_packed_bytes(u32 hash_log, bool tagged)
+{
+    return ((size_t)2 << hash_log) + ((size_t)1 << hash_log) / 8 + (tagged ? (size_t)1 << hash_log : 0);
+}
 
 // ---- parser state shared by the inner blocks of one unit -----------------------------------------------
 template <class TT> struct ParseCtx {
@@ -380,7 +408,7 @@ template <class W, class TT> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u3
     {
         const u32 mflimit = b1 - kMfLimit;
         const u8* const matchlimit = src + b1 - kLastLiterals;
-        if (wr) T.set(hash5(ld5(src + ip), hl), ip + bias);
+        if (wr) { const u64 v0 = ld5(src + ip); T.set_t(hash5(v0, hl), ip + bias, tag8((u32)v0)); }
         W::sync();
         ip++;
         for (;;) {
@@ -406,10 +434,11 @@ template <class W, class TT> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u3
                     const u32 pl = below ? highbit32(below) : lane;
                     const u32 prevP = W::shfl(P, pl);
                     const u32 cur = P + bias;
-                    u32 cand = 0;
-                    if (valid) cand = below ? prevP + bias : T.get(h, P);
+                    u32 cand = 0, ctag = kNoTag;
+                    if (valid) cand = below ? prevP + bias : T.get_t(h, P, &ctag);
                     bool hit = false;
-                    if (valid && cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset)
+                    if (valid && cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset &&
+                        T.maybe(ctag, tag8((u32)v)))
                         hit = ld32(src + (cand - bias)) == (u32)v;
                     const u32 hits = W::ballot(hit);
                     const u32 term = W::ballot(!valid);
@@ -423,7 +452,7 @@ template <class W, class TT> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u3
                     W::sync();
                     if ((commit >> lane) & 1) {
                         const u32 grp = peers & commit;
-                        if (highbit32(grp) == lane) T.set(h, cur);
+                        if (highbit32(grp) == lane) T.set_t(h, cur, tag8((u32)v));
                     }
                     W::sync();
                     if (matched) { ip = W::shfl(P, w_lane); mpos = W::shfl(cand, w_lane) - bias; break; }
@@ -439,16 +468,18 @@ template <class W, class TT> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u3
                 ip += ml + kMinMatch;
                 anchor = ip;
                 if (ip > mflimit) goto last_literals;
-                if (wr) T.set(hash5(ld5(src + ip - 2), hl), ip - 2 + bias);
+                if (wr) { const u64 v2 = ld5(src + ip - 2); T.set_t(hash5(v2, hl), ip - 2 + bias, tag8((u32)v2)); }
                 W::sync();
                 const u64 v = ld5(src + ip);
                 const u32 h = hash5(v, hl);
-                const u32 cand = T.get(h, ip);
+                u32 ctag = kNoTag;
+                const u32 cand = T.get_t(h, ip, &ctag);
                 W::sync();
-                if (wr) T.set(h, ip + bias);
+                if (wr) T.set_t(h, ip + bias, tag8((u32)v));
                 W::sync();
                 const u32 cur = ip + bias;
-                if (cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset) {
+                if (cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset &&
+                    T.maybe(ctag, tag8((u32)v))) {
                     mpos = cand - bias;
                     if (ld32(src + mpos) == (u32)v) {
                         ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
@@ -511,11 +542,13 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
             if (P + 384 < b1) W::prefetch(src + P + 384);          // the input is walked once, front to back
             const u32 same = W::match_any(h);
             const u32 below = same & lt_mask;
-            const u32 tv = ld_ok ? T.get(h, P) : 0u;
+            const u32 mytag = tag8((u32)v);
+            u32 ttag = kNoTag;
+            const u32 tv = ld_ok ? T.get_t(h, P, &ttag) : 0u;
             bool hit_t = false;
             {
                 const u32 cur = P + bias;
-                if (ld_ok && tv >= low_limit && tv < cur && tv + max_dist >= cur && cur - tv >= kMinOffset)
+                if (ld_ok && tv >= low_limit && tv < cur && tv + max_dist >= cur && cur - tv >= kMinOffset && T.maybe(ttag, mytag))
                     hit_t = ld32(src + (tv - bias)) == (u32)v;
             }
             // ---- replay the reference's walk over the window ----
@@ -562,7 +595,7 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
             W::sync();
             if ((committed >> lane) & 1) {
                 const u32 grp = same & committed;
-                if (highbit32(grp) == lane) T.set(h, P + bias);
+                if (highbit32(grp) == lane) T.set_t(h, P + bias, mytag);
             }
             W::sync();
             if (finished) break;
@@ -584,12 +617,15 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
                     const u32 blw = peers & lt_mask;
                     const u32 plj = blw ? highbit32(blw) : lane;
                     const u32 prevP = W::shfl(Pj, plj);
+                    const u32 prevV = W::shfl((u32)vj, plj);         // the four bytes at prevP
                     const u32 cur = Pj + bias;
-                    u32 cand = 0;
-                    if (valid) cand = blw ? prevP + bias : T.get(hj, Pj);
+                    u32 cand = 0, ctag = kNoTag;
+                    if (valid) cand = blw ? prevP + bias : T.get_t(hj, Pj, &ctag);
                     bool hit = false;
-                    if (valid && cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset)
-                        hit = ld32(src + (cand - bias)) == (u32)vj;
+                    if (valid && cand >= low_limit && cand < cur && cand + max_dist >= cur && cur - cand >= kMinOffset) {
+                        if (blw) hit = prevV == (u32)vj;
+                        else if (T.maybe(ctag, tag8((u32)vj))) hit = ld32(src + (cand - bias)) == (u32)vj;
+                    }
                     const u32 hits = W::ballot(hit);
                     const u32 term = W::ballot(!valid);
                     const u32 w_lane = hits ? ctz32(hits) : 32;
@@ -601,7 +637,7 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
                     W::sync();
                     if ((commit >> lane) & 1) {
                         const u32 grp = peers & commit;
-                        if (highbit32(grp) == lane) T.set(hj, cur);
+                        if (highbit32(grp) == lane) T.set_t(hj, cur, tag8((u32)vj));
                     }
                     W::sync();
                     if (matched) { ip = W::shfl(Pj, w_lane); mpos = W::shfl(cand, w_lane) - bias; break; }

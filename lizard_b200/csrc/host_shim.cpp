@@ -21,8 +21,11 @@ extern "C" int lzb_host_huf_decompress(unsigned char* dst, unsigned n, const uns
 static lzb::HashTable make_table(lzb::u32* buf, int n, lzb::u32 hash_log)
 {
     lzb::HashTable T;
-    if ((lzb::u32)n <= lzb::kBlockSize && hash_log <= 14) { T.t32 = nullptr; T.lo = (lzb::u16*)buf; T.hi = buf + ((size_t)1 << hash_log) / 2; }
-    else { T.t32 = buf; T.lo = nullptr; T.hi = nullptr; }
+    const bool single = (lzb::u32)n <= lzb::kBlockSize;
+    if (single && hash_log <= 14) {
+        T.t32 = nullptr; T.lo = (lzb::u16*)buf; T.hi = buf + ((size_t)1 << hash_log) / 2;
+        T.tag = (lzb::u8*)buf + lzb::hash_packed_bytes(hash_log, false); T.tagged = 0;     // 3.125 of the buffer's 4 bytes per entry
+    } else { T.t32 = buf; T.lo = nullptr; T.hi = nullptr; T.tag = nullptr; T.tagged = single ? 1u : 0u; }
     return T;
 }
 
