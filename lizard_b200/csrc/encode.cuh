@@ -148,12 +148,6 @@ struct EncodeConfig {
     size_t scratch_bytes = 0;
 };
 
-// the fast parsers keep candidate tags next to the packed entries (encode_core.cuh: tag8)
-#if !defined(LZB_ENC_TAGS)
-#define LZB_ENC_TAGS 1
-#endif
-LZ_HD bool enc_tagged(const LevelParams& lp) { return LZB_ENC_TAGS && (lp.parser == kParserFastSmall || lp.parser == kParserFast); }
-
 constexpr u32 kEncBigTableBytes = 4u << 18;          // plain 32-bit table for hashLog 18 or multi-inner-block units
 // Residency: registers allow 28 warps per SM (72 registers/thread), shared memory 26 packed level-10 tables
 // (8.5 KiB each).  The grid therefore runs CTAs of 14 warps, two per SM, where 13 warps keep their hash table in
@@ -173,7 +167,7 @@ lizard_encode_units_kernel(EncodeBatch b, u32 smem_tables, u32 table_bytes, u32 
     const bool packed_ok = wic < smem_tables;
     u8* tab = enc_smem + (size_t)wic * table_bytes;
     u32* seg_hist = reinterpret_cast<u32*>(enc_smem + (size_t)smem_tables * table_bytes + (size_t)wic * hist_bytes);
-    const bool tagged = enc_tagged(klp);
+    const bool tagged = enc_tagged(klp), tagged_plain = enc_tagged_plain(klp);
     HashTable packed, plain;
     packed.t32 = nullptr; packed.lo = reinterpret_cast<u16*>(tab);
     packed.hi = reinterpret_cast<u32*>(tab + ((size_t)2 << klp.hashLog));
@@ -189,7 +183,7 @@ lizard_encode_units_kernel(EncodeBatch b, u32 smem_tables, u32 table_bytes, u32 
         progress_wait(b.progress, unit, lane);
         const u32 len = b.src_len[unit];
         // 17-bit packed entries need every position of the unit below 2^17
-        plain.tagged = (tagged && len <= kBlockSize) ? 1u : 0u;      // 7 spare bits per entry when positions stay below 2^17
+        plain.tagged = (tagged_plain && len <= kBlockSize) ? 1u : 0u;      // 7 spare bits per entry when positions stay below 2^17
         const HashTable& T = (packed_ok && len <= kBlockSize) ? packed : plain;
         const int r = encode_unit<WarpLanes>(b.src_base + b.src_off[unit], len,
                                              b.dst_base + b.dst_off[unit], b.dst_cap[unit], b.level, T, work);

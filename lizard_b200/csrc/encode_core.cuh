@@ -318,6 +318,15 @@ struct PackedTable {
         W::sync();                                  // tags of empty entries are never looked at
     }
 };
+// Which tables carry tags: the plain table has the bits to spare (fast parsers and priceFast use them; single-block units
+// only); a packed table pays a byte per entry, which the small level-10/30 tables of the fast parsers are given and the
+// 34 KiB priceFast tables are not.
+#if !defined(LZB_ENC_TAGS)
+#define LZB_ENC_TAGS 1
+#endif
+LZ_HD bool enc_tagged(const LevelParams& lp) { return LZB_ENC_TAGS && (lp.parser == kParserFastSmall || lp.parser == kParserFast); }
+LZ_HD bool enc_tagged_plain(const LevelParams& lp) { return LZB_ENC_TAGS && (enc_tagged(lp) || lp.parser == kParserPriceFast); }
+
 // bytes of a packed table: 16-bit entries + the bit plane (+ one tag byte per entry for the fast parsers)
 LZ_HD size_t hash_packed_bytes(u32 hash_log, bool tagged)
 {
@@ -884,25 +893,38 @@ template <class W, class TT> LZ_HD void parse_price_fast_par(const ParseCtx<TT>&
             }
             const u32 peers = W::match_any(h);
             u32 below = peers & ((1u << lane) - 1);
-            u32 seen = valid ? T.get(h, P) : 0;
+            const u32 mytag = tag8((u32)v);
+            u32 ttag = kNoTag;
+            u32 seen = valid ? T.get_t(h, P, &ttag) : 0;
+            u32 seen_lane = NL;                               // whose position `seen` is: an earlier lane's, or the table's (NL)
             while (below) {                                   // replay earlier same-bucket lanes, in order
                 const u32 bl = ctz32(below); below &= below - 1;
                 const u32 pb = ip + bl + bias;
-                if (seen >= pb || pb >= seen + kMinOffset) seen = pb;
+                if (seen >= pb || pb >= seen + kMinOffset) { seen = pb; seen_lane = bl; }
             }
+            // the four bytes at an earlier lane's position are that lane's own bytes: no memory access for those
+            const u32 seen_v = W::shfl((u32)v, seen_lane < NL ? seen_lane : lane);
             bool rep_hit = false, hash_hit = false;
             if (valid) {
                 if (last_off >= kMinOffset && last_off <= P && cur - last_off >= low)
                     rep_hit = ld32(src + (P - last_off)) == (u32)v;
                 if (!rep_hit && seen < cur && seen >= low) {
                     const u32 m = seen - bias;
-                    if (P - m >= kMinOffset && ld32(src + m) == (u32)v) {
+                    bool eq4 = false;
+                    if (P - m >= kMinOffset) {
+                        if (seen_lane < NL) eq4 = seen_v == (u32)v;
+                        else if (T.maybe(ttag, mytag)) eq4 = ld32(src + m) == (u32)v;
+                    }
+                    if (eq4) {
                         if (P - m < kMax16BitOffset) hash_hit = true;
                         else hash_hit = count_match(src + P + kMinMatch, src + m + kMinMatch, matchlimit) + kMinMatch >= min_match_long;
                     }
                 }
             }
-            const u32 newval = (seen >= cur || cur >= seen + kMinOffset) ? cur : seen;
+            const bool take = seen >= cur || cur >= seen + kMinOffset;
+            const u32 newval = take ? cur : seen;
+            const u32 new_lane = take ? lane : seen_lane;      // NL: the bucket keeps the table's entry, nothing to write
+            const u32 new_tag = W::shfl(mytag, new_lane < NL ? new_lane : lane);
             const u32 hits = W::ballot(rep_hit || hash_hit);
             const u32 vmask = W::ballot(valid);
             const u32 w_lane = hits ? ctz32(hits) : 32;
@@ -910,7 +932,7 @@ template <class W, class TT> LZ_HD void parse_price_fast_par(const ParseCtx<TT>&
             W::sync();
             if ((commit >> lane) & 1) {
                 const u32 grp = peers & commit;
-                if (highbit32(grp) == lane) T.set(h, newval);
+                if (highbit32(grp) == lane && new_lane < NL) T.set_t(h, newval, new_tag);
             }
             W::sync();
             if (w_lane == 32) { ip += NL; continue; }
@@ -935,15 +957,16 @@ template <class W, class TT> LZ_HD void parse_price_fast_par(const ParseCtx<TT>&
                         const u32 low2 = (bias + max_dist >= cur2) ? bias : cur2 - max_dist;
                         const u64 v2 = ld5(src + start2);
                         const u32 h2 = hash5(v2, hl);
-                        const u32 cand2 = T.get(h2, start2);
+                        u32 tag2 = kNoTag;
+                        const u32 cand2 = T.get_t(h2, start2, &tag2);
                         ml2 = 0;
                         bool ok = false; u32 m = 0;
                         if (cand2 < cur2 && cand2 >= low2) {
                             m = cand2 - bias;
-                            ok = start2 - m >= kMinOffset && ld32(src + m) == (u32)v2;
+                            ok = start2 - m >= kMinOffset && T.maybe(tag2, tag8((u32)v2)) && ld32(src + m) == (u32)v2;
                         }
                         W::sync();
-                        if (wr && (cand2 >= cur2 || cur2 >= cand2 + kMinOffset)) T.set(h2, cur2);   // lizard_parser_pricefast.h:190
+                        if (wr && (cand2 >= cur2 || cur2 >= cand2 + kMinOffset)) T.set_t(h2, cur2, tag8((u32)v2));   // lizard_parser_pricefast.h:190
                         W::sync();
                         if (ok) {
                             const u32 mlt = count_match_par<W>(src + start2 + kMinMatch, src + m + kMinMatch, matchlimit) + kMinMatch;

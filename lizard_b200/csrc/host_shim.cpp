@@ -18,14 +18,21 @@ extern "C" int lzb_host_huf_decompress(unsigned char* dst, unsigned n, const uns
 
 // same choice as the device kernel: packed 17-bit entries when the unit is a single inner block and the table
 // would live in shared memory, plain 32-bit entries otherwise (the buffer is big enough for either form)
-static lzb::HashTable make_table(lzb::u32* buf, int n, lzb::u32 hash_log)
+// tests: 1 = plain 32-bit entries even where the packed form would do (on the device the warps of a CTA that have no
+// shared-memory table run small-table levels on the plain form, with its in-entry tags)
+static int g_force_plain = 0;
+extern "C" void lzb_force_plain_table(int on) { g_force_plain = on; }
+
+static lzb::HashTable make_table(lzb::u32* buf, int n, const lzb::LevelParams& lp)
 {
+    const lzb::u32 hash_log = lp.hashLog;
     lzb::HashTable T;
     const bool single = (lzb::u32)n <= lzb::kBlockSize;
-    if (single && hash_log <= 14) {
+    if (single && hash_log <= 14 && !g_force_plain) {
         T.t32 = nullptr; T.lo = (lzb::u16*)buf; T.hi = buf + ((size_t)1 << hash_log) / 2;
-        T.tag = (lzb::u8*)buf + lzb::hash_packed_bytes(hash_log, false); T.tagged = 0;     // 3.125 of the buffer's 4 bytes per entry
-    } else { T.t32 = buf; T.lo = nullptr; T.hi = nullptr; T.tag = nullptr; T.tagged = single ? 1u : 0u; }
+        T.tag = lzb::enc_tagged(lp) ? (lzb::u8*)buf + lzb::hash_packed_bytes(hash_log, false) : nullptr;   // 3.125 of the buffer's 4 bytes per entry
+        T.tagged = 0;
+    } else { T.t32 = buf; T.lo = nullptr; T.hi = nullptr; T.tag = nullptr; T.tagged = (single && lzb::enc_tagged_plain(lp)) ? 1u : 0u; }
     return T;
 }
 
@@ -39,7 +46,7 @@ extern "C" int lzb_host_compress(const unsigned char* src, int n, unsigned char*
     lzb::u32* table = (lzb::u32*)malloc(sizeof(lzb::u32) << lp.hashLog);
     lzb::EncWork* work = (lzb::EncWork*)malloc(sizeof(lzb::EncWork));
     work->huf.seg_count = (lzb::u32 (*)[256])malloc(4 * 256 * sizeof(lzb::u32));
-    lzb::HashTable T = make_table(table, n, lp.hashLog);
+    lzb::HashTable T = make_table(table, n, lp);
     int r = lzb::encode_unit<lzb::HostLanes>(src, (lzb::u32)n, dst, (lzb::u32)cap, level, T, work);
     free(work->huf.seg_count); free(table); free(work);
     return r;
@@ -279,7 +286,7 @@ extern "C" int lzb_emu_compress(const unsigned char* src, int n, unsigned char* 
     EmuCompressArgs a;
     a.src = src; a.n = n; a.dst = dst; a.cap = cap; a.level = level; a.result = 0;
     lzb::u32* table = (lzb::u32*)malloc(sizeof(lzb::u32) << lp.hashLog);
-    a.T = make_table(table, n, lp.hashLog);
+    a.T = make_table(table, n, lp);
     a.work = (lzb::EncWork*)malloc(sizeof(lzb::EncWork));
     a.work->huf.seg_count = (lzb::u32 (*)[256])malloc(4 * 256 * sizeof(lzb::u32));
     emu::run(emu_compress_body, &a);

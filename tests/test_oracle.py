@@ -219,6 +219,31 @@ def test_warp_emulated_device_path_bit_exact(ref, shim, level):
         assert emu_compress(shim, d, level, cap) == refs.ref_compress(ref, d, level, cap), (level, len(d), cap)
 
 
+@pytest.mark.parametrize("level", [10, 30, 21, 41, 22])
+def test_plain_table_with_entry_tags_bit_exact(ref, shim, level):
+    """On the device the warps of a CTA that have no shared-memory table run these levels on the plain 32-bit table,
+    whose entries carry a 7-bit candidate tag while every position of the unit is below 2^17.  Same bytes as the
+    reference, one lane and 32 emulated lanes, single-block units (tagged) and a two-block unit (untagged)."""
+    rnd = random.Random(1000 + level)
+    shim.lzb_force_plain_table(1)
+    try:
+        data = lz.datagen(2 * BS + 777, 50, level)
+        for blk in (data[:BS], data[BS:2 * BS], data[:70000]):
+            want = refs.ref_compress(ref, blk, level, BS - 1)
+            assert shim_compress(shim, blk, level, BS - 1) == want, (level, len(blk))
+            assert emu_compress(shim, blk, level, BS - 1) == want, (level, len(blk))
+        want = refs.ref_compress(ref, data, level)
+        assert shim_compress(shim, data, level) == want
+        assert emu_compress(shim, data, level) == want
+        for d in _inputs(200 + level, 12):
+            cap = rnd.choice([lz_bound(len(d)), max(len(d) - 1, 1)])
+            want = refs.ref_compress(ref, d, level, cap)
+            assert shim_compress(shim, d, level, cap) == want, (level, len(d), cap)
+            assert emu_compress(shim, d, level, cap) == want, (level, len(d), cap)
+    finally:
+        shim.lzb_force_plain_table(0)
+
+
 def test_decompress_parity_valid_and_corrupt(ref, oracle):
     rnd = random.Random(9)
     for data in _inputs(9, 120):
