@@ -1,0 +1,74 @@
+"""The C-ABI boundary without a GPU: liblizard_b200.so loads, exports every function include/lizard_b200.h declares, and
+every entry point of the product path FAILS (no CPU fallback) when there is no B200 -- loudly through the batch API
+(negative status + message), with the reference's own failure value through the drop-in symbols.  Pure host helpers
+(Lizard_compressBound, LizardF_compressFrameBound, error names) answer like the reference's."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import lizard_b200 as lz
+from tests import refs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lizard_b200.h")
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)              # the header's comments cite symbols it replaces
+    text = re.sub(r"//[^\n]*", " ", text)
+    names = set(re.findall(r"\b((?:Lizard|LizardF|LizardB200)_\w+)\s*\(", text))
+    names -= {n for n in names if re.search(r"typedef[^;]*\b%s\b" % re.escape(n), text)}
+    return sorted(names)
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+def test_header_declares_the_reference_surface():
+    names = _declared_functions()
+    for must in ("Lizard_compress", "Lizard_compress_extState", "Lizard_compressBound", "Lizard_sizeofState",
+                 "Lizard_decompress_safe", "LizardF_compressFrame", "LizardF_compressFrameBound", "LizardF_compressBegin",
+                 "LizardF_compressUpdate", "LizardF_flush", "LizardF_compressEnd", "LizardF_decompress",
+                 "LizardF_getFrameInfo", "LizardF_isError", "LizardF_getErrorName", "LizardB200_compress_batch",
+                 "LizardB200_decompress_batch", "LizardB200_compress_device", "LizardB200_decompress_device"):
+        assert must in names, must
+
+
+def test_library_exports_every_declared_symbol():
+    L = lz.lib()
+    missing = [n for n in _declared_functions() if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_host_only_helpers_match_the_reference():
+    L = lz.lib()
+    ref = refs.ref_parity()
+    for n in (0, 1, 20, 131071, 131072, 131073, 1 << 20, 0x7E000000, 0x7E000001):
+        want = ref.Lizard_compressBound(n) if ref else (0 if n > 0x7E000000 else n + 2 + (n // 131072 + 1) * 4)
+        assert L.Lizard_compressBound(n) == want, n
+    assert L.Lizard_versionNumber() > 0
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="checks the behaviour of a box WITHOUT a GPU")
+def test_product_path_fails_without_a_gpu_instead_of_falling_back():
+    L = lz.lib()
+    assert L.LizardB200_available() == 0
+    src = b"abcdefgh" * 4096
+    dst = ctypes.create_string_buffer(len(src) + 64)
+    # drop-in symbols: the reference's own failure values (0 = compression failed, negative = decode error)
+    assert L.Lizard_compress(src, dst, len(src), len(dst), 10) == 0
+    assert L.Lizard_decompress_safe(b"\x0a\x80\x01\x00\x00a", dst, 6, 64) < 0
+    # batch API: negative status and a message
+    with pytest.raises(lz.LizardB200Error):
+        lz.compress_batch([src], 10)
+    with pytest.raises(lz.LizardB200Error):
+        lz.decompress_batch([b"\x0a\x80\x01\x00\x00a"], [64])
+    assert L.LizardB200_lastError()
