@@ -78,3 +78,52 @@ def gather_stream(my_bytes, all_sizes, n_blocks: int, device, group=None):
             out[pos:pos + nbytes].copy_(tmp)
         pos += nbytes
     return out
+
+
+def scatter_stream(stream, all_sizes, n_blocks: int, device, group=None):
+    """Inverse of gather_stream: rank 0 holds the concatenated compressed blocks (`stream`) and `all_sizes`; every rank
+    returns (its slice of the stream, the sizes of its blocks, lo, hi).  The sizes travel by broadcast."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    sizes = all_sizes.to(device=device, dtype=torch.int64) if rank == 0 else torch.empty(n_blocks, dtype=torch.int64, device=device)
+    dist.broadcast(sizes, src=0, group=group)
+    lo, hi = block_range(n_blocks, rank, world)
+    my_bytes = int(sizes[lo:hi].sum())
+    mine = torch.empty(my_bytes, dtype=torch.uint8, device=device)
+    if rank == 0:
+        reqs, pos = [], 0
+        for r in range(world):
+            rlo, rhi = block_range(n_blocks, r, world)
+            nbytes = int(sizes[rlo:rhi].sum())
+            if r == 0:
+                mine.copy_(stream[pos:pos + nbytes])
+            elif nbytes:
+                reqs.append(dist.isend(stream[pos:pos + nbytes].contiguous(), dst=r, group=group))
+            pos += nbytes
+        for q in reqs:
+            q.wait()
+    elif my_bytes:
+        dist.recv(mine, src=0, group=group)
+    return mine, sizes[lo:hi], lo, hi
+
+
+def gather_blocks(my_out, total_bytes: int, block: int, device, group=None):
+    """Collect the decoded blocks (fixed size except the last one) on rank 0, in block order."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n_blocks = (total_bytes + block - 1) // block
+    if rank != 0:
+        if my_out.numel():
+            dist.send(my_out.contiguous(), dst=0, group=group)
+        return None
+    out = torch.empty(total_bytes, dtype=torch.uint8, device=device)
+    for r in range(world):
+        lo, hi = block_range(n_blocks, r, world)
+        a, b = lo * block, min(hi * block, total_bytes)
+        if b <= a:
+            continue
+        if r == 0:
+            out[a:b].copy_(my_out[: b - a])
+        else:
+            tmp = torch.empty(b - a, dtype=torch.uint8, device=device)
+            dist.recv(tmp, src=r, group=group)
+            out[a:b].copy_(tmp)
+    return out

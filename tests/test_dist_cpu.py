@@ -1,5 +1,5 @@
 """world_size-2 gloo test of the multi-GPU host logic (lizard_b200/dist.py): scatter input block ranges,
-exchange compressed sizes, gather the concatenated stream.  The per-rank codec is the CPU oracle here (this
+exchange compressed sizes, gather the concatenated stream, and the way back (scatter the stream, decode, gather blocks).  The per-rank codec is the CPU oracle here (this
 test runs without a GPU); on the GPU box the same functions run over NCCL with the CUDA codec (bench.py)."""
 import ctypes
 import os
@@ -25,6 +25,15 @@ def _oracle_compress(block: bytes, level: int) -> bytes:
     return dst.raw[:n]
 
 
+def _oracle_decompress(comp: bytes, cap: int) -> bytes:
+    L = ctypes.CDLL(os.path.join(refs.ROOT, "oracle", "liboracle.so"))
+    L.oracle_Lizard_decompress_safe.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+    dst = ctypes.create_string_buffer(max(cap, 1))
+    r = L.oracle_Lizard_decompress_safe(comp, dst, len(comp), cap)
+    assert r >= 0, r
+    return dst.raw[:r]
+
+
 def _worker(rank, world, port, total, level, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -41,8 +50,18 @@ def _worker(rank, world, port, total, level, q):
         all_sizes, my_off = lzdist.exchange_sizes(sizes, n_blocks)
         blob = torch.frombuffer(bytearray(b"".join(comp)), dtype=torch.uint8) if comp else torch.empty(0, dtype=torch.uint8)
         stream = lzdist.gather_stream(blob, all_sizes, n_blocks, "cpu")
+        # and back: rank 0 owns the stream, every rank decodes its range, rank 0 collects the blocks
+        part, my_sizes, lo2, hi2 = lzdist.scatter_stream(stream, all_sizes if rank == 0 else None, n_blocks, "cpu")
+        assert (lo2, hi2) == (lo, hi) and my_sizes.tolist() == sizes.tolist()
+        pb, pos, outs = part.numpy().tobytes(), 0, []
+        for i, k in enumerate(my_sizes.tolist()):
+            cap = min(BS, total - (lo + i) * BS)
+            outs.append(_oracle_decompress(pb[pos:pos + k], cap))
+            pos += k
+        mine_out = torch.frombuffer(bytearray(b"".join(outs)), dtype=torch.uint8) if outs else torch.empty(0, dtype=torch.uint8)
+        back = lzdist.gather_blocks(mine_out, total, BS, "cpu")
         if rank == 0:
-            q.put((all_sizes.tolist(), stream.numpy().tobytes(), my_off))
+            q.put((all_sizes.tolist(), stream.numpy().tobytes(), my_off, back.numpy().tobytes()))
         else:
             q.put((lo, hi, my_off))
     finally:
@@ -70,6 +89,7 @@ def test_scatter_exchange_gather_world2(total):
     r1 = [g for g in got if not isinstance(g[0], list)][0]
     assert r0[0] == [len(w) for w in want]
     assert r0[1] == b"".join(want)
+    assert r0[3] == data                                  # scatter_stream -> decode per rank -> gather_blocks
     lo, hi, off = r1
     assert (lo, hi) == lzdist.block_range(len(want), 1, 2)
     assert off == sum(len(w) for w in want[:lo])
