@@ -72,3 +72,27 @@ def test_product_path_fails_without_a_gpu_instead_of_falling_back():
     with pytest.raises(lz.LizardB200Error):
         lz.decompress_batch([b"\x0a\x80\x01\x00\x00a"], [64])
     assert L.LizardB200_lastError()
+
+
+def build_c_host(tmp_path):
+    """Compile examples/frame_roundtrip.c as strict C99 against include/lizard_b200.h and link it to the library."""
+    import subprocess
+    exe = os.path.join(str(tmp_path), "frame_roundtrip")
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-O2", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "frame_roundtrip.c"), os.path.join(ROOT, "lizard_b200", "csrc", "datagen.c"),
+           "-L" + os.path.join(ROOT, "lizard_b200"), "-llizard_b200", "-Wl,-rpath," + os.path.join(ROOT, "lizard_b200"),
+           "-lm", "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_c_host_compiles_as_c99_and_fails_loudly_without_a_gpu(tmp_path):
+    """The north_star keeps the host side in C: the header must be valid C (not only C++), and a C program written like
+    the reference's own callers links against the library with nothing but that header."""
+    import subprocess
+    lz.lib()                                              # built
+    exe = build_c_host(tmp_path)
+    if _no_gpu():
+        r = subprocess.run([exe, "1", "10"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 1 and "LizardF_compressFrame" in r.stderr, (r.returncode, r.stderr)
