@@ -69,6 +69,32 @@ int Lizard_compress_extState(void* state, const char* src, char* dst, int srcSiz
 int Lizard_decompress_safe(const char* src, char* dst, int compressedSize, int maxDecompressedSize);
 
 /* ---------------------------------------------------------------------------------------------
+ * (1a) the rest of the reference's export list (lib/dll/liblizard.def:3-19), so that its own callers link:
+ *      lib/lizard_frame.c and the sources under programs/ reference every one of these.
+ *      Stream objects are functional: lib/lizard_frame.c:379-401 creates one per compression context and hands it to
+ *      Lizard_compress_extState.  The streaming / dictionary family (linked blocks, cross-call windows;
+ *      lib/lizard_compress.h:178-198, lib/lizard_decompress.h:89-145) is OUT OF SCOPE and fails with the reference's
+ *      failure values: 0 from Lizard_loadDict / Lizard_saveDict / Lizard_compress_continue, -1 from
+ *      Lizard_decompress_safe_continue / _partial; Lizard_decompress_safe_usingDict is Lizard_decompress_safe when
+ *      dictSize == 0 (lib/lizard_decompress.c:353-355) and -1 with a dictionary.  No CPU code path behind any of them.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct Lizard_stream_s Lizard_stream_t;                 /* lib/lizard_compress.h:72 */
+typedef struct Lizard_streamDecode_s Lizard_streamDecode_t;     /* lib/lizard_decompress.h:100 */
+Lizard_stream_t* Lizard_createStream(int compressionLevel);
+int              Lizard_freeStream(Lizard_stream_t* streamPtr);
+Lizard_stream_t* Lizard_resetStream(Lizard_stream_t* streamPtr, int compressionLevel);
+int Lizard_loadDict(Lizard_stream_t* streamPtr, const char* dictionary, int dictSize);
+int Lizard_saveDict(Lizard_stream_t* streamPtr, char* safeBuffer, int dictSize);
+int Lizard_compress_continue(Lizard_stream_t* streamPtr, const char* src, char* dst, int srcSize, int maxDstSize);
+int Lizard_decompress_safe_partial(const char* source, char* dest, int compressedSize, int targetOutputSize, int maxDecompressedSize);
+Lizard_streamDecode_t* Lizard_createStreamDecode(void);
+int Lizard_freeStreamDecode(Lizard_streamDecode_t* streamPtr);
+int Lizard_setStreamDecode(Lizard_streamDecode_t* streamPtr, const char* dictionary, int dictSize);
+int Lizard_decompress_safe_continue(Lizard_streamDecode_t* streamPtr, const char* source, char* dest, int compressedSize, int maxDecompressedSize);
+int Lizard_decompress_safe_usingDict(const char* source, char* dest, int compressedSize, int maxDecompressedSize,
+                                     const char* dictStart, int dictSize);
+
+/* ---------------------------------------------------------------------------------------------
  * (1b) drop-in frame layer: same names, types and error values as lib/lizard_frame.h:57-297 and
  *      lib/lizard_frame_static.h:56-67.  Frame format: doc/lizard_Frame_format.md (magic 0x184D2206).
  *      All full blocks handed to one LizardF_compressUpdate / LizardF_compressFrame / LizardF_decompress

@@ -579,6 +579,60 @@ int Lizard_compress_extState(void* state, const char* src, char* dst, int srcSiz
     return Lizard_compress(src, dst, srcSize, maxDstSize, level);
 }
 
+// ---- the rest of lib/dll/liblizard.def: what callers of the block API link against -------------------------------------
+// Stream OBJECTS are functional (the reference's frame layer creates one per context and hands it to
+// Lizard_compress_extState, lib/lizard_frame.c:379-401, 436-451); the device keeps the real state, so the object only
+// records its level.  The streaming / dictionary FAMILY (linked blocks, cross-call windows) is out of scope (SURVEY.md
+// section 2): those entry points exist so that the reference's own callers link, and they fail with the reference's
+// failure values -- 0 from the compress side, a negative value from the decode side -- never with a CPU code path.
+struct Lizard_stream_s { size_t allocatedMemory; int compressionLevel; };
+struct Lizard_streamDecode_s { const char* dict; int dictSize; };
+static const char* const kNoStreaming = "streaming / dictionary API (linked blocks) is not implemented on the GPU path";
+
+Lizard_stream_t* Lizard_createStream(int level)            // lib/lizard_compress.c:392-397
+{
+    if (level > (int)kMaxLevel) level = kMaxLevel;
+    if (level < (int)kMinLevel) level = kDefaultLevel;
+    Lizard_stream_t* p = (Lizard_stream_t*)malloc(sizeof(Lizard_stream_t));
+    if (p) { p->allocatedMemory = sizeof(Lizard_stream_t); p->compressionLevel = level; }
+    return p;
+}
+int Lizard_freeStream(Lizard_stream_t* p) { free(p); return 0; }              // :417-423
+Lizard_stream_t* Lizard_resetStream(Lizard_stream_t* p, int level)            // :401-414
+{
+    if (!p) return Lizard_createStream(level);
+    if (level > (int)kMaxLevel) level = kMaxLevel;
+    if (level < (int)kMinLevel) level = kDefaultLevel;
+    p->compressionLevel = level;
+    return p;
+}
+int Lizard_loadDict(Lizard_stream_t*, const char*, int) { g_last_error = kNoStreaming; return 0; }
+int Lizard_saveDict(Lizard_stream_t*, char*, int) { g_last_error = kNoStreaming; return 0; }
+int Lizard_compress_continue(Lizard_stream_t*, const char*, char*, int, int) { g_last_error = kNoStreaming; return 0; }
+
+Lizard_streamDecode_t* Lizard_createStreamDecode(void) { return (Lizard_streamDecode_t*)calloc(1, sizeof(Lizard_streamDecode_t)); }
+int Lizard_freeStreamDecode(Lizard_streamDecode_t* p) { free(p); return 0; }
+int Lizard_setStreamDecode(Lizard_streamDecode_t* p, const char* dict, int dictSize)   // lib/lizard_decompress.c:303-319
+{
+    if (p) { p->dict = dict; p->dictSize = dictSize; }
+    return 1;
+}
+int Lizard_decompress_safe_continue(Lizard_streamDecode_t*, const char*, char*, int, int) { g_last_error = kNoStreaming; return -1; }
+int Lizard_decompress_safe_partial(const char*, char*, int, int, int)
+{
+    g_last_error = "Lizard_decompress_safe_partial is not implemented on the GPU path";
+    return -1;
+}
+int Lizard_decompress_safe_usingDict(const char* src, char* dst, int compressedSize, int maxDecompressedSize,
+                                     const char* dictStart, int dictSize)
+{
+    // lib/lizard_decompress.c:353-355: without a dictionary this is Lizard_decompress_safe
+    if (dictSize == 0) return Lizard_decompress_safe(src, dst, compressedSize, maxDecompressedSize);
+    (void)dictStart;
+    g_last_error = kNoStreaming;
+    return -1;
+}
+
 }  // extern "C"
 
 #include "frame.inl"

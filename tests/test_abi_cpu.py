@@ -96,3 +96,24 @@ def test_c_host_compiles_as_c99_and_fails_loudly_without_a_gpu(tmp_path):
     if _no_gpu():
         r = subprocess.run([exe, "1", "10"], capture_output=True, text=True, timeout=120)
         assert r.returncode == 1 and "LizardF_compressFrame" in r.stderr, (r.returncode, r.stderr)
+
+
+def test_reference_frame_layer_relinks_against_the_library(tmp_path):
+    """the reference's unmodified lizard_frame.c links against the library (every symbol of
+    lib/dll/liblizard.def it references is exported) and runs.  Without a GPU our block codec reports failure (0), which
+    the reference's frame layer answers by storing every block raw (lizard_frame.c:462-466): a valid frame that the pure
+    reference decodes -- still no CPU codec behind the drop-in symbols."""
+    import subprocess
+    exe = os.path.join(refs.REF_DIR, "relinked_frame")
+    ref = refs.ref_parity()
+    if ref is None or not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built")
+    out = os.path.join(str(tmp_path), "f.liz")
+    r = subprocess.run([exe, "10", "1", out, "1"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    frame = open(out, "rb").read()
+    lz.bind_frame_api(ref)
+    res, back = lz.frame_decompress(ref, frame, 1 << 20)
+    assert res == 0 and back == lz.datagen(1 << 20)
+    if _no_gpu():
+        assert "8 blocks, 8 stored raw" in r.stdout, r.stdout
