@@ -59,6 +59,24 @@ def test_decode_edge_sizes(ref):
             assert r == rr, (level, len(c), r, rr)
 
 
+def test_input_one_byte_short_or_long_matches_reference(ref):
+    """Fuzzer property of the reference (tests/fuzzer.c:417-427): a compressed block with one byte missing or one byte
+    (or a few) appended must not decode like the original; whatever the reference returns, we return."""
+    rnd = random.Random(9)
+    units, caps = [], []
+    for level in (10, 21, 41, 30, 17):
+        for blk in (lz.datagen(BS, 50, level), lz.datagen(5000, 50, level), lz.datagen(BS + 777, 50, level), b"", b"a" * 100):
+            comp = refs.ref_compress(ref, blk, level)
+            for c in (comp[:-1], comp + b"\x00", comp + b"\x80", comp + b"\xff", comp + bytes([rnd.randrange(256)]),
+                      comp + bytes(4)):
+                for cap in (len(blk), len(blk) + 64):
+                    units.append(c); caps.append(cap)
+    got = lz.decompress_batch(units, caps)
+    for i, ((r, _), u, cap) in enumerate(zip(got, units, caps)):
+        rr, _ = refs.ref_decompress(ref, u, cap)
+        assert r == rr, (i, len(u), cap, r, rr)
+
+
 def _content_is_defined(ref, comp, cap):
     # The reference copies matches in 8-byte granules, so for offsets < 8 (never produced by any Lizard
     # encoder) its output depends on stale bytes of dst; only compare contents when decoding into two

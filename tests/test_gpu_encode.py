@@ -72,6 +72,21 @@ def test_edge_inputs_and_capacities(ref, level):
         assert r == len(want) and o == want, (level, len(c), cap, r, len(want))
 
 
+@pytest.mark.parametrize("level", [10, 21, 41, 30, 17])
+def test_compress_into_exact_and_short_capacity(ref, level):
+    """tests/fuzzer.c:442-481 of the reference: exactly `compressedSize` bytes of room give the same bytes, one byte less
+    gives what the reference gives (0)."""
+    units, caps = [], []
+    for blk in (lz.datagen(BS, 50, level), lz.datagen(70000, 30, level + 1), lz.datagen(3000, 50, 7), bytes(5000)):
+        full = refs.ref_compress(ref, blk, level)
+        for cap in (len(full), len(full) - 1, len(full) // 2):
+            units.append(blk); caps.append(cap)
+    out = lz.compress_batch(units, level, caps)
+    for blk, cap, (r, o) in zip(units, caps, out):
+        want = refs.ref_compress(ref, blk, level, cap)
+        assert r == len(want) and o == want, (level, len(blk), cap, r, len(want))
+
+
 def test_unsupported_level_fails_loudly():
     with pytest.raises(lz.LizardB200Error):
         lz.compress_batch([b"x" * 1000], 12)

@@ -285,6 +285,40 @@ def _content_is_defined(ref, comp, cap):
     return outs[0] == outs[1]
 
 
+@pytest.mark.parametrize("level", [10, 21, 41, 30, 17])
+def test_compress_into_exact_and_short_capacity(ref, oracle, shim, level):
+    """tests/fuzzer.c:442-481 of the reference: compressing into exactly `compressedSize` bytes succeeds with the same
+    bytes, one byte less returns what the reference returns (0), and nothing is written behind the capacity."""
+    for blk in (lz.datagen(BS, 50, level), lz.datagen(70000, 30, level + 1), lz.datagen(3000, 50, 7), bytes(5000)):
+        full = refs.ref_compress(ref, blk, level)
+        for cap in (len(full), len(full) - 1, len(full) // 2):
+            want = refs.ref_compress(ref, blk, level, cap)
+            assert (want == full) == (cap == len(full))
+            assert o_compress(oracle, blk, level, cap) == want, (level, len(blk), cap)
+            for fn in (shim.lzb_host_compress, shim.lzb_emu_compress):
+                dst = ctypes.create_string_buffer(b"\xA5" * (cap + 64), cap + 64)
+                n = fn(blk, len(blk), dst, cap, level)
+                assert dst.raw[:n] == want, (level, len(blk), cap, n, len(want))
+                assert dst.raw[cap:] == b"\xA5" * 64, "wrote behind the capacity"
+
+
+def test_input_one_byte_short_or_long_matches_reference(ref, oracle, shim):
+    """tests/fuzzer.c:417-427 of the reference: compressed input with one byte missing / extra bytes appended.  Oracle
+    restatement and the host build of the device decoder return what the reference returns."""
+    rnd = random.Random(9)
+    shim.lzb_host_decompress.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    for level in (10, 21, 41, 30, 17):
+        for blk in (lz.datagen(BS, 50, level), lz.datagen(5000, 50, level), lz.datagen(BS + 777, 50, level), b"", b"a" * 100):
+            comp = refs.ref_compress(ref, blk, level)
+            for c in (comp[:-1], comp + b"\x00", comp + b"\x80", comp + b"\xff", comp + bytes([rnd.randrange(256)]),
+                      comp + bytes(4)):
+                for cap in (len(blk), len(blk) + 64):
+                    rr, _ = refs.ref_decompress(ref, c, cap)
+                    assert o_decompress(oracle, c, cap)[0] == rr, (level, len(blk), len(c), cap)
+                    buf = ctypes.create_string_buffer(max(cap, 1) + 64)
+                    assert shim.lzb_host_decompress(c, len(c), buf, cap) == rr, (level, len(blk), len(c), cap)
+
+
 @pytest.mark.parametrize("fn,count,variant,order", [("lzb_host_decompress", 90, 3, 0), ("lzb_host_decompress", 40, 0, 0),
                                                     ("lzb_emu_decompress", 14, 3, 0), ("lzb_emu_decompress", 14, 3, 2),
                                                     ("lzb_emu_decompress", 10, 3, 1), ("lzb_emu_decompress", 8, 0, 2),
