@@ -33,7 +33,10 @@ def ref_compress(L, data: bytes, level: int, cap: int = None) -> bytes:
 
 
 def ref_decompress(L, comp: bytes, cap: int):
-    dst = ctypes.create_string_buffer(max(cap, 1))
+    # twice the capacity: the reference does not charge a raw inner block against maxDecompressedSize
+    # (lib/lizard_decompress.c:164-180 never reduces outputSize), so a compressed inner block behind a raw one may write up
+    # to the raw block's size past the capacity; a result > cap tells the caller that this happened
+    dst = ctypes.create_string_buffer(2 * max(cap, 1) + 64)
     r = L.Lizard_decompress_safe(comp, dst, len(comp), cap)
     return r, (dst.raw[:r] if r > 0 else b"")
 

@@ -302,6 +302,33 @@ def test_compress_into_exact_and_short_capacity(ref, oracle, shim, level):
                 assert dst.raw[cap:] == b"\xA5" * 64, "wrote behind the capacity"
 
 
+def test_reference_overrun_behind_a_raw_inner_block_is_refused(ref, oracle, shim):
+    """Found by tools/fuzz_parity.py.  A unit whose first inner block is stored raw and whose second is compressed, decoded
+    with maxDecompressedSize one byte (or 100) short: the reference does not charge the raw block against the capacity
+    (lib/lizard_decompress.c:164-180), decodes the second block past the end of `dst` and reports success.  The oracle
+    restates that; the device decoder (host build, one lane and 32 emulated lanes) refuses and writes nothing behind the
+    capacity.  Everything agrees again as soon as the capacity is the real size."""
+    rng = np.random.default_rng(1)
+    data = rng.integers(0, 256, BS, dtype=np.uint8).tobytes() + lz.datagen(40000)
+    shim.lzb_host_decompress.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    shim.lzb_emu_decompress.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int]
+    for level in (10, 21, 41):
+        comp = refs.ref_compress(ref, data, level)
+        assert comp[1] == 0x80                                   # first inner block raw
+        for cap in (len(data), len(data) - 1, len(data) - 100):
+            rr, _ = refs.ref_decompress(ref, comp, cap)
+            assert rr == len(data)                                  # the reference "succeeds" in all three cases
+            assert o_decompress(oracle, comp, cap)[0] == rr if cap == len(data) else True
+            for fn in (shim.lzb_host_decompress, shim.lzb_emu_decompress):
+                dst = ctypes.create_string_buffer(b"\xA5" * (len(data) + 64), len(data) + 64)
+                r = fn(comp, len(comp), dst, cap)
+                assert dst.raw[cap:] == b"\xA5" * (len(data) + 64 - cap), "wrote behind the capacity"
+                if cap == len(data):
+                    assert r == len(data) and dst.raw[:r] == data
+                else:
+                    assert r < 0, (level, cap, r)
+
+
 def test_input_one_byte_short_or_long_matches_reference(ref, oracle, shim):
     """tests/fuzzer.c:417-427 of the reference: compressed input with one byte missing / extra bytes appended.  Oracle
     restatement and the host build of the device decoder return what the reference returns."""
