@@ -292,8 +292,8 @@ struct HufFull {                 // the reference's layout: 1 << tableLog entrie
     const u16* t; u32 down;      // down = 32 - tableLog
     LZ_HDM u32 look(u32 hi) const { return t[hi >> down]; }
 };
-// Two-level form of the same table, 1.3 KiB instead of 4 KiB at tableLog 11 (the pre-pass keeps 56 tables per SM in
-// shared memory; with full tables they leave the L1 too small for the 224 bitstreams an SM reads at once).
+// Two-level form of the same table: 2.3 KiB instead of 4 KiB at tableLog 11 with the 10-bit first level used.  The pre-pass
+// keeps 56 tables per SM in shared memory; full tables would leave the L1 28 KB for the 224 bitstreams an SM reads at once.
 // HUF_readDTableX2 lays the symbols out by ascending weight, i.e. the longest codes sit at the lowest indices, and the
 // region of weight w starts at a multiple of 1 << (w-1) -- even 1 << w, because everything above it is a multiple of that
 // and the total is 1 << tableLog.  So with drop = tableLog - kHufL1Bits: an index's top kHufL1Bits bits select either one

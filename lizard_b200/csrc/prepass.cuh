@@ -18,7 +18,7 @@ struct PrepassBatch {
 };
 
 // warps per CTA, jobs per warp round.  One CTA per SM: 1 GiB of 128 KiB blocks is 32768 literals segments = 1024 warps,
-// 7 x 148 warps take them in a single wave; 7 x 8 two-level tables are 74 KB, the rest of the SM's 256 KB stays L1 for
+// 7 x 148 warps take them in a single wave; 7 x 8 two-level tables are 130 KB, the rest of the SM's 256 KB stays L1 for
 // the 224 bitstreams read at once.
 enum : u32 { kExpWarps = 7, kExpJobs = 8 };
 
