@@ -186,6 +186,10 @@ int LizardB200_decompress_device(const void* dSrc, const uint64_t* dSrcOff, cons
 int LizardB200_compress_device(const void* dSrc, const uint64_t* dSrcOff, const uint32_t* dSrcLen,
                                void* dDst, const uint64_t* dDstOff, const uint32_t* dDstCap,
                                int* dResult, unsigned nUnits, int compressionLevel, void* cudaStream);
+/* diagnostics: default launch shape of the encode kernel for a level (no device needed): warps per CTA, how many of them
+ * keep their hash table in shared memory, CTAs per SM, dynamic shared memory per CTA.  LIZARDB200_ERR_LEVEL for levels
+ * whose parser is not implemented. */
+int LizardB200_encodeShape(int compressionLevel, int* warpsPerCta, int* smemTables, int* ctasPerSM, int* smemBytes);
 /* number of kernel launches issued by this library since load (bench.py reports it as gpu_launches) */
 unsigned long long LizardB200_launchCount(void);
 /* diagnostics: how this thread's device decodes, four bits: 1 = pooled copy sweeps, 2 = compact length-extension chain,

@@ -117,3 +117,17 @@ def test_reference_frame_layer_relinks_against_the_library(tmp_path):
     assert res == 0 and back == lz.datagen(1 << 20)
     if _no_gpu():
         assert "8 blocks, 8 stored raw" in r.stdout, r.stdout
+
+
+def test_encoder_launch_shapes_are_the_measured_ones():
+    """The per-level launch shapes were picked from sweeps on the B200 (profiles/r01_SUMMARY.md section 8); a refactoring of
+    encode_shape() must not move them silently.  (warps per CTA, shared-memory tables per CTA, CTAs per SM)"""
+    L = lz.lib()
+    want = {10: (14, 7, 2), 30: (14, 3, 2), 11: (14, 0, 2), 31: (14, 0, 2), 21: (14, 2, 2), 22: (14, 0, 2), 41: (14, 1, 2),
+            13: (14, 0, 2), 17: (14, 0, 2), 34: (14, 0, 2)}
+    for level, shape in want.items():
+        w, t, k, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert L.LizardB200_encodeShape(level, ctypes.byref(w), ctypes.byref(t), ctypes.byref(k), ctypes.byref(b)) == 0
+        assert (w.value, t.value, k.value) == shape, (level, w.value, t.value, k.value)
+        assert 2 * (b.value + 1024) <= 196 * 1024          # two CTAs inside the 196 KB carve-out step
+    assert L.LizardB200_encodeShape(12, None, None, None, None) < 0
