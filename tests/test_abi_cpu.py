@@ -74,12 +74,12 @@ def test_product_path_fails_without_a_gpu_instead_of_falling_back():
     assert L.LizardB200_lastError()
 
 
-def build_c_host(tmp_path):
-    """Compile examples/frame_roundtrip.c as strict C99 against include/lizard_b200.h and link it to the library."""
+def build_c_host(tmp_path, name="frame_roundtrip"):
+    """Compile examples/<name>.c as strict C99 against include/lizard_b200.h and link it to the library."""
     import subprocess
-    exe = os.path.join(str(tmp_path), "frame_roundtrip")
+    exe = os.path.join(str(tmp_path), name)
     cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-O2", "-I" + os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "examples", "frame_roundtrip.c"), os.path.join(ROOT, "lizard_b200", "csrc", "datagen.c"),
+           os.path.join(ROOT, "examples", name + ".c"), os.path.join(ROOT, "lizard_b200", "csrc", "datagen.c"),
            "-L" + os.path.join(ROOT, "lizard_b200"), "-llizard_b200", "-Wl,-rpath," + os.path.join(ROOT, "lizard_b200"),
            "-lm", "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -93,9 +93,12 @@ def test_c_host_compiles_as_c99_and_fails_loudly_without_a_gpu(tmp_path):
     import subprocess
     lz.lib()                                              # built
     exe = build_c_host(tmp_path)
+    bench = build_c_host(tmp_path, "block_bench")
     if _no_gpu():
         r = subprocess.run([exe, "1", "10"], capture_output=True, text=True, timeout=120)
         assert r.returncode == 1 and "LizardF_compressFrame" in r.stderr, (r.returncode, r.stderr)
+        r = subprocess.run([bench, "10", "1", "1"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 1 and "LizardB200_compress_blocks" in r.stderr, (r.returncode, r.stderr)
 
 
 def test_reference_frame_layer_relinks_against_the_library(tmp_path):
