@@ -4,7 +4,7 @@
  * result verified.  Plain C99 host code over include/lizard_b200.h; buffers are ordinary host memory, so the numbers
  * include both PCIe directions (bench.py's `e2e` measures the same thing through the frame API with pinned memory).
  *
- *   gcc -std=c99 -O2 -Iinclude examples/block_bench.c lizard_b200/csrc/datagen.c \
+ *   gcc -std=c99 -O2 -Iinclude examples/block_bench.c tools/datagen.c \
  *       -Llizard_b200 -llizard_b200 -Wl,-rpath,$PWD/lizard_b200 -lm -o block_bench
  *   ./block_bench [level=10] [MiB=256] [loops=3]
  *

@@ -3,7 +3,7 @@
  * decode it with LizardF_decompress, compare.  Only include/lizard_b200.h is needed; all buffers are ordinary host memory,
  * the library moves them to the B200 and back.
  *
- *   gcc -std=c99 -O2 -Iinclude examples/frame_roundtrip.c lizard_b200/csrc/datagen.c \
+ *   gcc -std=c99 -O2 -Iinclude examples/frame_roundtrip.c tools/datagen.c \
  *       -Llizard_b200 -llizard_b200 -Wl,-rpath,$PWD/lizard_b200 -lm -o frame_roundtrip
  *   ./frame_roundtrip [MiB=64] [level=10]
  *
@@ -16,7 +16,7 @@
 #include <time.h>
 #include "lizard_b200.h"
 
-/* synthetic input, same generator as the reference's `datagen -P50` (lizard_b200/csrc/datagen.c) */
+/* synthetic input, same generator as the reference's `datagen -P50` (tools/datagen.c) */
 int lizb200_datagen(void* out, unsigned long long size, double match_pct, double lit_pct, unsigned seed);
 
 static double now_ms(void)

@@ -14,7 +14,7 @@
  *        lib/lizard_decompress.h:73  Lizard_decompress_safe   lib/lizard_decompress.c:267-270
  *      Compression output is byte-identical to the reference built with -DLIZARD_RESET_MEM
  *      (hash table empty at the start of every call), for the levels whose parsers are implemented on
- *      the GPU: 10, 11, 30, 31 (fastSmall / fast) and 21, 22, 41, 42 (priceFast).  Any other level
+ *      the GPU: 10, 11, 30, 31 (fastSmall / fast), 13-17, 34-38 (hashChain) and 21, 22, 41, 42 (priceFast).  Any other level
  *      makes the compress entry points return 0 ("failed"), never a CPU fallback.
  *      Decompression accepts every level 10..49 (the block format only has two codeword flavours).
  *
@@ -186,6 +186,12 @@ int LizardB200_decompress_device(const void* dSrc, const uint64_t* dSrcOff, cons
 int LizardB200_compress_device(const void* dSrc, const uint64_t* dSrcOff, const uint32_t* dSrcLen,
                                void* dDst, const uint64_t* dDstOff, const uint32_t* dDstCap,
                                int* dResult, unsigned nUnits, int compressionLevel, void* cudaStream);
+/* Concatenation step of a block writer on the device (what lib/lizard_frame.c:544-549 does by advancing dstPtr block by
+ * block): segment i = dSrc + dSrcOff[i], dLen[i] bytes (entries <= 0 are skipped, e.g. failed units) is copied to
+ * dDst + dDstOff[i].  With dLen = the result array of LizardB200_compress_device and dDstOff = its exclusive prefix sum this
+ * packs the units of a batch back to back.  Enqueue-only, like the calls above. */
+int LizardB200_gather_device(const void* dSrc, const uint64_t* dSrcOff, const int* dLen,
+                             void* dDst, const uint64_t* dDstOff, unsigned nUnits, void* cudaStream);
 /* diagnostics: default launch shape of the encode kernel for a level (no device needed): warps per CTA, how many of them
  * keep their hash table in shared memory, CTAs per SM, dynamic shared memory per CTA.  LIZARDB200_ERR_LEVEL for levels
  * whose parser is not implemented. */

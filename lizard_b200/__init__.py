@@ -10,7 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblizard_b200.so")
-DATAGEN_PATH = os.path.join(_HERE, "libdatagen.so")
+DATAGEN_PATH = os.path.join(os.path.dirname(_HERE), "tools", "libdatagen.so")   # bench / test input generator, not product code
 
 BLOCK_SIZE = 1 << 17
 _lib = None
@@ -45,6 +45,7 @@ def lib():
         dev_args = [ctypes.c_void_p] * 7 + [ctypes.c_uint]
         L.LizardB200_decompress_device.argtypes = dev_args + [ctypes.c_void_p]
         L.LizardB200_compress_device.argtypes = dev_args + [ctypes.c_int, ctypes.c_void_p]
+        L.LizardB200_gather_device.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_uint, ctypes.c_void_p]
         L.LizardB200_compress_blocks.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
                                                  ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         L.LizardB200_decompress_blocks.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
@@ -124,7 +125,7 @@ def _load_dg():
 
 
 def datagen(size: int, match_pct: float = 50.0, seed: int = 0, lit_pct: float = 0.0) -> bytes:
-    """Bytes identical to the reference's `datagen -g<size> -P<match_pct> -s<seed>` (csrc/datagen.c)."""
+    """Bytes identical to the reference's `datagen -g<size> -P<match_pct> -s<seed>` (tools/datagen.c)."""
     buf = ctypes.create_string_buffer(max(size, 1))
     if _load_dg().lizb200_datagen(buf, size, match_pct, lit_pct, seed) != 0:
         raise LizardB200Error("datagen failed")

@@ -51,6 +51,26 @@ lizard_decode_units_kernel(DecodeBatch b)
     }
 }
 
+// Variable-length segments to their places in another arena (segment i: src_off[i], len[i] -> dst_off[i]): what the frame
+// layer's "payloads back to back" (lib/lizard_frame.c:544-549 writes each block behind the previous one) is on the device
+// when the units were produced at a fixed stride.  One CTA per segment, warps take 4 KiB tiles, destination-aligned 16-byte
+// stores (lanes_copy_wide).  Segments with len <= 0 (failed units) are skipped.
+__global__ void __launch_bounds__(256) lizard_gather_segments_kernel(const u8* src, const u64* src_off, const int* len,
+                                                                      u8* dst, const u64* dst_off, u32 n)
+{
+    const u32 warp = threadIdx.x >> 5;
+    for (u32 i = blockIdx.x; i < n; i += gridDim.x) {
+        const int L = len[i];
+        if (L <= 0) continue;
+        const u8* s = src + src_off[i];
+        u8* d = dst + dst_off[i];
+        for (u32 t = warp * 4096u; t < (u32)L; t += 8u * 4096u) {
+            const u32 part = (u32)L - t < 4096u ? (u32)L - t : 4096u;
+            lanes_copy_wide<WarpLanes, true, true>(d + t, s + t, part, false);
+        }
+    }
+}
+
 typedef void (*DecodeKernel)(DecodeBatch);
 DecodeKernel decode_kernel(int v)
 {
@@ -474,6 +494,23 @@ int LizardB200_compress_device(const void* dSrc, const uint64_t* dSrcOff, const 
     int st = ensure_context(c, g_device);
     if (st != LIZARDB200_OK) return st;
     return launch_encode(c, dSrc, (const u64*)dSrcOff, dSrcLen, dDst, (const u64*)dDstOff, dDstCap, dResult, nUnits, level, (cudaStream_t)stream);
+}
+
+int LizardB200_gather_device(const void* dSrc, const uint64_t* dSrcOff, const int* dLen,
+                             void* dDst, const uint64_t* dDstOff, unsigned nUnits, void* stream)
+{
+    if (nUnits == 0) return LIZARDB200_OK;
+    if (!dSrc || !dSrcOff || !dLen || !dDst || !dDstOff) return LIZARDB200_ERR_ARGUMENT;
+    Context& c = g_ctx[g_device];
+    std::lock_guard<std::mutex> lock(c.mu);
+    int st = ensure_context(c, g_device);
+    if (st != LIZARDB200_OK) return st;
+    const unsigned grid = nUnits < (unsigned)c.sm_count * 8u ? nUnits : (unsigned)c.sm_count * 8u;
+    lizard_gather_segments_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const u8*)dSrc, (const u64*)dSrcOff, dLen,
+                                                                            (u8*)dDst, (const u64*)dDstOff, nUnits);
+    g_launches++;
+    CU_OK(cudaGetLastError());
+    return LIZARDB200_OK;
 }
 
 int LizardB200_decompress_batch(const void* const* src, const int* cSize, void* const* dst, const int* dstCap,

@@ -1153,19 +1153,25 @@ int oracle_Lizard_compress(const char* source, char* dest, int src_size, int max
 }
 
 /* =====================================================================================================
- * pthread timing harness for the CPU baseline (bench.py).  Blocks are handed out through an atomic
- * counter; every pass is timed with CLOCK_MONOTONIC and the fastest pass is returned (the reference's
- * own bench keeps the fastest loop too, programs/bench.c:231-286).
+ * pthread timing harness for the CPU baseline (bench.py).  A pool of `threads` workers is created ONCE per
+ * call, outside every timed pass; a pass is bracketed by two pthread barriers and timed with CLOCK_MONOTONIC
+ * on the calling thread (which works as worker 0).  Blocks are handed out through an atomic counter.  The
+ * fastest pass is returned (the reference's own bench keeps the fastest loop too, programs/bench.c:231-286);
+ * the MEAN over the passes of the last call is available from oracle_time_last_mean(), so a caller can quote
+ * the same statistic as for the GPU arm.
  * =================================================================================================== */
 typedef struct {
     oracle_compress_fn cfn; oracle_decompress_fn dfn;
     const char* src; size_t src_size; int block; int level; char* dst; size_t stride; int* sizes;
-    const int* csizes; size_t nblocks; size_t next; pthread_mutex_t mu;
+    const int* csizes; size_t nblocks; size_t next;
+    pthread_barrier_t start, stop; pthread_mutex_t gate; int iters;
 } o_job;
 
-static void* o_worker(void* arg)
+static __thread double o_last_mean = 0.0;
+double oracle_time_last_mean(void) { return o_last_mean; }
+
+static void o_pass(o_job* j)
 {
-    o_job* j = (o_job*)arg;
     for (;;) {
         size_t i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
         if (i >= j->nblocks) break;
@@ -1176,23 +1182,47 @@ static void* o_worker(void* arg)
             j->sizes[i] = j->dfn(j->src + i * j->stride, j->dst + i * (size_t)j->block, j->csizes[i], j->block);
         }
     }
+}
+static void* o_worker(void* arg)
+{
+    o_job* j = (o_job*)arg;
+    pthread_mutex_lock(&j->gate); pthread_mutex_unlock(&j->gate);      /* the barriers exist once the gate opens */
+    for (int it = 0; it < j->iters; ++it) {
+        pthread_barrier_wait(&j->start);
+        o_pass(j);
+        pthread_barrier_wait(&j->stop);
+    }
     return 0;
 }
 static double o_run(o_job* j, int threads, int iters)
 {
-    double best = 1e30;
+    double best = 1e30, sum = 0.0;
     if (threads < 1) threads = 1;
+    if (iters < 1) iters = 1;
+    j->iters = iters;
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
+    pthread_mutex_init(&j->gate, 0);
+    pthread_mutex_lock(&j->gate);
+    int made = 1;
+    for (int t = 1; t < threads; ++t) { if (pthread_create(&th[made], 0, o_worker, j) != 0) break; made++; }
+    pthread_barrier_init(&j->start, 0, (unsigned)made);        /* sized for the workers that really exist */
+    pthread_barrier_init(&j->stop, 0, (unsigned)made);
+    pthread_mutex_unlock(&j->gate);
     for (int it = 0; it < iters; ++it) {
-        struct timespec a, b; j->next = 0;
+        struct timespec a, b;
+        j->next = 0;                                  /* workers are parked at `start`: nobody reads it yet */
         clock_gettime(CLOCK_MONOTONIC, &a);
-        for (int t = 1; t < threads; ++t) pthread_create(&th[t], 0, o_worker, j);
-        o_worker(j);
-        for (int t = 1; t < threads; ++t) pthread_join(th[t], 0);
+        pthread_barrier_wait(&j->start);
+        o_pass(j);
+        pthread_barrier_wait(&j->stop);
         clock_gettime(CLOCK_MONOTONIC, &b);
-        {   double s = (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec); if (s < best) best = s; }
+        {   double s = (double)(b.tv_sec - a.tv_sec) + 1e-9 * (double)(b.tv_nsec - a.tv_nsec); if (s < best) best = s; sum += s; }
     }
+    for (int t = 1; t < made; ++t) pthread_join(th[t], 0);
+    pthread_barrier_destroy(&j->start); pthread_barrier_destroy(&j->stop);
+    pthread_mutex_destroy(&j->gate);
     free(th);
+    o_last_mean = sum / iters;
     return best;
 }
 double oracle_time_compress(oracle_compress_fn fn, const char* src, size_t src_size, int block, int level,

@@ -34,6 +34,9 @@ double oracle_time_compress(oracle_compress_fn fn, const char* src, size_t srcSi
                             char* dst, size_t dstStride, int* outSizes, int threads, int iters);
 double oracle_time_decompress(oracle_decompress_fn fn, const char* comp, size_t compStride, const int* compSizes,
                               size_t nBlocks, char* dst, int blockSize, int threads, int iters);
+/* mean seconds per pass of the calling thread's last oracle_time_* call (the worker pool is created outside the timed
+ * passes, so best and mean both exclude thread creation) */
+double oracle_time_last_mean(void);
 
 #ifdef __cplusplus
 }

@@ -57,6 +57,18 @@ def test_host_only_helpers_match_the_reference():
     assert L.Lizard_versionNumber() > 0
 
 
+def test_sizeof_state_equals_the_reference_for_every_level():
+    """Lizard_sizeofState (lib/lizard_compress.c:311-323): callers malloc this many bytes for Lizard_compress_extState; the
+    device keeps its own state, but the figure must be the reference's (806045 at level 10, 17632409 at 21/41)."""
+    L = lz.lib()
+    ref = refs.ref_parity()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    for level in list(range(10, 50)) + [0, 5, 9, 50, 99, -3]:
+        assert L.Lizard_sizeofState(level) == ref.Lizard_sizeofState(level), level
+    assert L.Lizard_sizeofState(10) == 806045 and L.Lizard_sizeofState(21) == 17632409 == L.Lizard_sizeofState(41)
+
+
 @pytest.mark.skipif(not _no_gpu(), reason="checks the behaviour of a box WITHOUT a GPU")
 def test_product_path_fails_without_a_gpu_instead_of_falling_back():
     L = lz.lib()
@@ -79,7 +91,7 @@ def build_c_host(tmp_path, name="frame_roundtrip"):
     import subprocess
     exe = os.path.join(str(tmp_path), name)
     cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-O2", "-I" + os.path.join(ROOT, "include"),
-           os.path.join(ROOT, "examples", name + ".c"), os.path.join(ROOT, "lizard_b200", "csrc", "datagen.c"),
+           os.path.join(ROOT, "examples", name + ".c"), os.path.join(ROOT, "tools", "datagen.c"),
            "-L" + os.path.join(ROOT, "lizard_b200"), "-llizard_b200", "-Wl,-rpath," + os.path.join(ROOT, "lizard_b200"),
            "-lm", "-o", exe]
     r = subprocess.run(cmd, capture_output=True, text=True)
