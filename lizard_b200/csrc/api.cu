@@ -2,6 +2,7 @@
 // launches, host staging.  Host-side logic only; the codec lives in decode.cuh / encode.cuh.
 #include "../../include/lizard_b200.h"
 #include "decode.cuh"
+#include "decode2.cuh"
 #include "prepass.cuh"
 #include "encode.cuh"
 
@@ -71,7 +72,47 @@ __global__ void __launch_bounds__(256) lizard_gather_segments_kernel(const u8* s
     }
 }
 
+// Second generation (decode2.cuh): one CTA of two warps per unit -- warp 0 parses (tokens -> records, literals stream staged
+// through shared memory by TMA bulk copies), warp 1 copies (records -> output tile -> coalesced 16-byte stores).
+// kStages = stages of 2 KiB in the literals ring.
+template <u32 kStages> __global__ void __launch_bounds__(64, kStages >= 8 ? 9 : 14)
+lizard_decode2_units_kernel(DecodeBatch b)
+{
+    __shared__ PairShared<kStages> ps;
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (u32 i = 0; i < kStages; ++i) mbar_init(&ps.full_bar[i], 1);
+        for (u32 i = 0; i < kBatchSlots; ++i) { mbar_init(&ps.pub_bar[i], 1); mbar_init(&ps.free_bar[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) { copier_loop<kStages>(&ps); return; }
+    u8* scratch = b.scratch + (size_t)blockIdx.x * kDecScratchPerWarp;
+    if (lane == 0) ps.dws.big_table = reinterpret_cast<u16*>(scratch + 4 * kDecStreamScratch);
+    __syncwarp();
+    PairSink<kStages> sk;
+    sk.init(&ps);
+    for (;;) {
+        u32 unit = 0;
+        if (lane == 0) unit = atomicAdd(b.counter, 1u);
+        unit = __shfl_sync(LZB_FULL, unit, 0);
+        if (unit >= b.n_units) break;
+        progress_wait(b.progress, unit, lane);
+        u8* const dst = b.dst_base + b.dst_off[unit];
+        sk.begin_unit(dst);
+        const int r = decode_unit2<WarpLanes>(b.src_base + b.src_off[unit], b.src_len[unit], dst, b.dst_cap[unit], scratch,
+                                              &ps.dws, sk, b.pre ? b.pre + unit : nullptr, b.arena);
+        sk.drain();
+        if (lane == 0) b.result[unit] = r;
+        __syncwarp();
+        progress_done(b.progress, unit, lane);
+    }
+    sk.finish_stream();
+    sk.exit_copier();
+}
+
 typedef void (*DecodeKernel)(DecodeBatch);
+DecodeKernel decode2_kernel(int stages) { return stages >= 8 ? lizard_decode2_units_kernel<8> : lizard_decode2_units_kernel<4>; }
 DecodeKernel decode_kernel(int v)
 {
     switch (v & 3) {
@@ -116,7 +157,9 @@ struct Context {
     bool ready = false, failed = false;
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // compute / H2D / D2H
-    int dec_grid = 0, dec_variant = 7;        // bits 0-1: schedule of the token loops, bit 2: Huffman pre-pass, bit 3: token pre-pass
+    int dec_grid = 0, dec_variant = 23;       // bits 0-1: schedule of the token loops, bit 2: Huffman pre-pass, bit 3: token pre-pass,
+                                              // bit 4: second-generation kernel (parser + copier warp per unit)
+    int dec2_grid = 0, dec2_stages = 4;
     DeviceBuffer pre_ws, pre_arena, pre_scratch, seq_ws, seq_recs;
     DeviceBuffer dec_scratch, enc_scratch, counters;
     u32 counter_slot = 0;
@@ -169,7 +212,7 @@ int ensure_context(Context& c, int device)
         c.failed = true; fail("cudaStreamCreate", e); return LIZARDB200_ERR_CUDA;
     }
     const size_t dec_smem = sizeof(DecWarpShared) * kDecWarps;
-    if (const char* v = getenv("LIZARDB200_DEC_VARIANT")) c.dec_variant = atoi(v) & 15;
+    if (const char* v = getenv("LIZARDB200_DEC_VARIANT")) c.dec_variant = atoi(v) & 31;
     // Shared memory and L1 share one 256 KB array per SM.  Left alone, the driver sizes the carve-out for as many CTAs as
     // the kernel's registers would allow, which leaves these kernels -- whose grids are sized by hand -- a 28 KB L1 for
     // hundreds of byte streams; ask for exactly what the resident CTAs use.
@@ -203,7 +246,21 @@ int ensure_context(Context& c, int device)
     for (int v = 0; v < 4; ++v)
         cudaFuncSetAttribute(decode_kernel(v), cudaFuncAttributePreferredSharedMemoryCarveout,
                              carveout((size_t)per_sm * (dec_smem + 1024), "LIZARDB200_DEC_CARVEOUT"));
-    if ((e = c.dec_scratch.reserve((size_t)c.dec_grid * kDecWarps * kDecScratchPerWarp)) != cudaSuccess) {
+    {   // second generation: CTAs of two warps, static shared memory; as many per SM as fit (LIZARDB200_DEC2_CTAS_PER_SM caps it)
+        if (const char* v = getenv("LIZARDB200_DEC2_STAGES")) c.dec2_stages = atoi(v) >= 8 ? 8 : 4;
+        cudaFuncAttributes fa;
+        int p2 = 0;
+        if ((e = cudaFuncGetAttributes(&fa, decode2_kernel(c.dec2_stages))) != cudaSuccess) { c.failed = true; fail("cudaFuncGetAttributes(decode2)", e); return LIZARDB200_ERR_CUDA; }
+        cudaFuncSetAttribute(decode2_kernel(c.dec2_stages), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, decode2_kernel(c.dec2_stages), 64, 0);
+        if (p2 < 1) p2 = 1;
+        if (const char* v = getenv("LIZARDB200_DEC2_CTAS_PER_SM")) { const int want = atoi(v); if (want >= 1 && want < p2) p2 = want; }
+        c.dec2_grid = c.sm_count * p2;
+        cudaFuncSetAttribute(decode2_kernel(c.dec2_stages), cudaFuncAttributePreferredSharedMemoryCarveout,
+                             carveout((size_t)p2 * (fa.sharedSizeBytes + 1024), "LIZARDB200_DEC2_CARVEOUT"));
+    }
+    const size_t dec_scratch_units = (size_t)c.dec_grid * kDecWarps > (size_t)c.dec2_grid ? (size_t)c.dec_grid * kDecWarps : (size_t)c.dec2_grid;
+    if ((e = c.dec_scratch.reserve(dec_scratch_units * kDecScratchPerWarp)) != cudaSuccess) {
         c.failed = true; fail("cudaMalloc(decode scratch)", e); return LIZARDB200_ERR_MEMORY;
     }
     if ((e = c.counters.reserve(kCounterSlots * sizeof(u32))) != cudaSuccess) {
@@ -306,9 +363,16 @@ int launch_decode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* d
         int st = launch_prepass(c, b, s);
         if (st != LIZARDB200_OK) return st;
     }
-    if ((c.dec_variant & 8) && pg == nullptr && n >= kPrepassMinUnits) {
+    if ((c.dec_variant & 8) && !(c.dec_variant & 16) && pg == nullptr && n >= kPrepassMinUnits) {
         int st = launch_token_parse(c, b, s);
         if (st != LIZARDB200_OK) return st;
+    }
+    if (c.dec_variant & 16) {
+        const int grid2 = (int)n < c.dec2_grid ? (int)n : c.dec2_grid;
+        decode2_kernel(c.dec2_stages)<<<grid2, 64, 0, s>>>(b);
+        g_launches++;
+        CU_OK(cudaGetLastError());
+        return LIZARDB200_OK;
     }
     u32 warps_needed = n;
     int grid = (int)((warps_needed + kDecWarps - 1) / kDecWarps);
@@ -471,7 +535,7 @@ int LizardB200_setDecodeVariant(int variant)
     std::lock_guard<std::mutex> lk(c.mu);
     int st = ensure_context(c, g_device);
     if (st != LIZARDB200_OK) return st;
-    c.dec_variant = variant & 15;
+    c.dec_variant = variant & 31;
     return LIZARDB200_OK;
 }
 

@@ -85,8 +85,7 @@ enum : u32 { kDecStreamScratch = kBlockSize + 64, kDecBigTableBytes = 2u << kHuf
 
 typedef PoolRun SeqDesc;                          // 16-byte sequence descriptor (see run_batch_copies)
 
-struct DecWarpShared {             // per-warp shared memory
-    SeqDesc desc[64];              // literal-run and match descriptors of the current token batch
+struct DecWarpCore {               // per-warp shared memory every decoder generation needs
     u16* big_table;                // single-symbol table of the in-kernel Huffman expansion: 2^12 entries in the warp's
                                    // global scratch (the pre-pass expands the streams of real batches; keeping 4 KiB per
                                    // warp in shared memory for the rest would cost the token loops their L1)
@@ -97,6 +96,9 @@ struct DecWarpShared {             // per-warp shared memory
     u8  weights[256];
     u32 rank[kHufTableLogMax + 1];
     u32 pad[3];
+};
+struct DecWarpShared : DecWarpCore {   // first generation (decode_tokens_*): plus the batch's copy descriptors
+    SeqDesc desc[64];              // literal-run and match descriptors of the current token batch
 };
 
 // ---- lane-cooperative byte movers --------------------------------------------------------------
@@ -112,6 +114,8 @@ template <class W> LZ_HD void lanes_match(u8* dst, long op, u32 off, u32 len)
     u8* d = dst + op;
     if (off >= len) { for (u32 i = W::lane(); i < len; i += W::lanes()) d[i] = s[i]; }
     else if (off != 0) { for (u32 i = W::lane(); i < len; i += W::lanes()) d[i] = s[i % off]; }
+    else { for (u32 i = W::lane(); i < len; i += W::lanes()) d[i] = 0; }     // offset 0 (no encoder emits it; the reference copies
+                                                                              // whatever dst held): defined output, nothing stale leaks
 }
 
 // ---- Huffman stream expansion -----------------------------------------------------------------
@@ -211,7 +215,7 @@ LZ_HD bool huf_job_segment(u8* dst, u32 n, const u8* pay, u32 pc, u32 k, const H
 }
 
 // HUF_decompress for one stream; all lanes return the same value (n or negative)
-template <class W> LZ_HD int huf_decompress_lanes(u8* dst, u32 n, const u8* src, u32 c, DecWarpShared* sh)
+template <class W> LZ_HD int huf_decompress_lanes(u8* dst, u32 n, const u8* src, u32 c, DecWarpCore* sh)
 {
     const u32 lane = W::lane();
     if (n == 0) return kErrDstSmall;
@@ -974,7 +978,7 @@ template <class W> LZ_HD int decode_block_from_records(const Streams& s, u8* dst
 // One stream header.  Returns 1 on success, 0 on failure (Lizard_readStream, lizard_decompress.c:72-112).
 // `ip` is an offset into the unit.
 template <class W> LZ_HD int read_stream(bool huff, const u8* src, long csize, long& ip, u8* scratch, const u8** ptr, u32* len,
-                                        DecWarpShared* sh, const u8* expanded = nullptr)
+                                        DecWarpCore* sh, const u8* expanded = nullptr)
 {
     if (!huff) {
         if (ip > csize - 3) return 0;

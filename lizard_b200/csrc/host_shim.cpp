@@ -6,6 +6,7 @@
 #include "entropy_dec.cuh"
 #include "encode_core.cuh"
 #include "decode.cuh"
+#include "decode2.cuh"
 #include <stdlib.h>
 
 extern "C" int lzb_host_huf_decompress(unsigned char* dst, unsigned n, const unsigned char* src, unsigned c)
@@ -356,5 +357,49 @@ extern "C" int lzb_decompress_with_prepass(const unsigned char* src, int csize, 
     } else r = lzb::decode_unit<lzb::HostLanes, 3>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, sh, &hp.up, hp.arena,
                                                    (mode & 4) ? &us : nullptr, recs);
     free(scratch); free(sh); free(hp.arena); free(recs);
+    return r;
+}
+
+
+// ---- second-generation decoder (decode2.cuh): parser + copier through the in-line sink -------------------------------
+// mode bit 0: 32 emulated lanes instead of one.  `span` = most literals-stream bytes per published batch (the device uses
+// ~4 KB; tests also run tiny values to exercise the prefix / split paths).  `dst` may be unaligned: the copier works in the
+// aligned space of dst & ~15 and must not touch a byte outside [dst, dst + result).
+template <class W> static int decode2_run(const unsigned char* src, int csize, unsigned char* dst, int cap, unsigned span,
+                                          unsigned char* scratch, lzb::DecWarpCore* core, lzb::CopyShared* cs)
+{
+    lzb::InlineSink<W> sk;
+    sk.cs = cs; sk.lits.p = nullptr; sk.nrec_total = 0; sk.span_limit = span; sk.out_pos = 0;
+    sk.st.unit_lo = (lzb::u32)((size_t)dst & 15);
+    sk.st.dst_al = dst - sk.st.unit_lo;
+    sk.st.T0 = 0;
+    sk.resync(sk.st.unit_lo);
+    return lzb::decode_unit2<W>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, core, sk);
+}
+struct EmuDecode2Args { const unsigned char* src; int csize; unsigned char* dst; int cap; unsigned span; unsigned char* scratch;
+                        lzb::DecWarpCore* core; lzb::CopyShared* cs; int result; };
+static void emu_decode2_body(void* p)
+{
+    EmuDecode2Args* a = (EmuDecode2Args*)p;
+    const int r = decode2_run<EmuLanes>(a->src, a->csize, a->dst, a->cap, a->span, a->scratch, a->core, a->cs);
+    if (EmuLanes::lane() == 0) a->result = r;
+}
+extern "C" int lzb_host_decompress2(const unsigned char* src, int csize, unsigned char* dst, int cap, int mode, unsigned span)
+{
+    if (csize < 1) return 0;
+    if (cap < 0) return -1;
+    unsigned char* scratch = (unsigned char*)malloc(lzb::kDecScratchPerWarp);
+    lzb::DecWarpCore* core = (lzb::DecWarpCore*)malloc(sizeof(lzb::DecWarpCore));
+    lzb::CopyShared* cs = (lzb::CopyShared*)malloc(sizeof(lzb::CopyShared));
+    memset(cs, 0xA5, sizeof *cs);
+    core->big_table = (lzb::u16*)(scratch + 4 * lzb::kDecStreamScratch);
+    int r;
+    if (mode & 1) {
+        EmuDecode2Args a; a.src = src; a.csize = csize; a.dst = dst; a.cap = cap; a.span = span; a.scratch = scratch; a.core = core;
+        a.cs = cs; a.result = -1;
+        emu::run(emu_decode2_body, &a);
+        r = a.result;
+    } else r = decode2_run<lzb::HostLanes>(src, csize, dst, cap, span, scratch, core, cs);
+    free(scratch); free(core); free(cs);
     return r;
 }

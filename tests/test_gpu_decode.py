@@ -9,6 +9,7 @@ from tests import refs
 
 pytestmark = pytest.mark.gpu
 BS = lz.BLOCK_SIZE
+DEFAULT_VARIANT = 23         # the library's default (api.cu Context::dec_variant)
 
 
 @pytest.fixture(scope="module")
@@ -22,6 +23,17 @@ def ref():
 @pytest.fixture(scope="module")
 def data4m():
     return lz.datagen(4 << 20)
+
+
+@pytest.fixture(params=[7, 23], autouse=True, ids=["gen1", "gen2"])
+def decode_generation(request):
+    """Every test of this file runs on both decode kernels: 7 = first generation (one warp per unit, Huffman pre-pass on),
+    23 = second generation (parser + copier warp per unit, TMA-staged literals ring; decode2.cuh)."""
+    L = lz.lib()
+    L.LizardB200_setDecodeVariant.argtypes = [ctypes.c_int]
+    assert L.LizardB200_setDecodeVariant(request.param) == 0
+    yield request.param
+    L.LizardB200_setDecodeVariant(DEFAULT_VARIANT)
 
 
 @pytest.mark.parametrize("level", [10, 21, 41, 30, 11, 17, 24, 45])
@@ -146,7 +158,7 @@ def test_decode_schedules_and_prepass_agree(ref, data4m):
     units.append(refs.ref_compress(ref, big, 41)); caps.append(len(big))
     want = [refs.ref_decompress(ref, u, c) for u, c in zip(units, caps)]
     try:
-        for variant in (15, 7, 11, 3, 12, 0, 5, 6):
+        for variant in (15, 7, 11, 3, 12, 0, 5, 6, 23, 19, 16):
             assert L.LizardB200_setDecodeVariant(variant) == 0
             got = lz.decompress_batch(units, caps)
             for i, ((r, o), (rr, ro)) in enumerate(zip(got, want)):
@@ -154,4 +166,46 @@ def test_decode_schedules_and_prepass_agree(ref, data4m):
                 if rr > 0 and refs.stream_obeys_min_offset(units[i], caps[i]):
                     assert o == ro, (variant, i)
     finally:
-        L.LizardB200_setDecodeVariant(7)
+        L.LizardB200_setDecodeVariant(DEFAULT_VARIANT)
+
+
+def test_device_api_unaligned_destinations(ref, data4m):
+    """LizardB200_decompress_device with units decoding to arbitrary byte offsets of a device buffer (the second-generation
+    copier works in the 16-byte aligned space of each destination and must not touch a byte outside [dst, dst + size))."""
+    import torch
+    L = lz.lib()
+    rnd = random.Random(3)
+    dev = torch.device("cuda", 0)
+    for level in (10, 21, 41):
+        blocks, comp = [], []
+        for i in range(24):
+            n = BS if i % 3 else rnd.randrange(1, BS)
+            blocks.append(data4m[i * BS:i * BS + n])
+            comp.append(refs.ref_compress(ref, blocks[-1], level))
+        src_off, dst_off, pos_s, pos_d = [], [], 0, 0
+        for b, c in zip(blocks, comp):
+            pos_s += rnd.randrange(0, 9)
+            pos_d += rnd.randrange(1, 40)
+            src_off.append(pos_s); dst_off.append(pos_d)
+            pos_s += len(c); pos_d += len(b)
+        h_src = bytearray(pos_s + 64)
+        for o, c in zip(src_off, comp):
+            h_src[o:o + len(c)] = c
+        d_src = torch.frombuffer(h_src, dtype=torch.uint8).to(dev)
+        d_dst = torch.full((pos_d + 64,), 0xEE, dtype=torch.uint8, device=dev)
+        t_so = torch.tensor(src_off, dtype=torch.int64, device=dev)
+        t_sl = torch.tensor([len(c) for c in comp], dtype=torch.int32, device=dev)
+        t_do = torch.tensor(dst_off, dtype=torch.int64, device=dev)
+        t_dc = torch.tensor([len(b) for b in blocks], dtype=torch.int32, device=dev)
+        t_res = torch.zeros(len(blocks), dtype=torch.int32, device=dev)
+        st = L.LizardB200_decompress_device(d_src.data_ptr(), t_so.data_ptr(), t_sl.data_ptr(), d_dst.data_ptr(), t_do.data_ptr(),
+                                            t_dc.data_ptr(), t_res.data_ptr(), len(blocks), None)
+        assert st == 0, L.LizardB200_lastError()
+        torch.cuda.synchronize()
+        out = bytes(d_dst.cpu().numpy())
+        res = t_res.cpu().tolist()
+        want = bytearray(b"\xEE" * len(out))
+        for o, b in zip(dst_off, blocks):
+            want[o:o + len(b)] = b
+        assert res == [len(b) for b in blocks], (level, res)
+        assert out == bytes(want), level
