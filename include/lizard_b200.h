@@ -179,7 +179,11 @@ int LizardB200_decompress_blocks(const void* src, size_t srcStride, const int* c
 
 /* Device-pointer variants: everything (payload, offset/size tables, results) already lives in device memory
  * of the current device; the call only enqueues kernels on `cudaStream` (a cudaStream_t, may be NULL) and
- * returns without synchronising.  Workspace is owned by the library and grown on demand. */
+ * returns without synchronising.  Workspace is owned by the library, shared by all calls on a device and grown on demand
+ * (growing it -- the first call, or a batch larger than any before -- is the one case in which these calls synchronise the
+ * stream and allocate; do not capture that call in a CUDA graph).  Calls on DIFFERENT streams are serialised against each
+ * other on the device (each launch waits for the previous launch's completion event when the stream changes), so results
+ * do not depend on how the caller spreads calls over streams; calls on one stream run in stream order. */
 int LizardB200_decompress_device(const void* dSrc, const uint64_t* dSrcOff, const uint32_t* dSrcLen,
                                  void* dDst, const uint64_t* dDstOff, const uint32_t* dDstCap,
                                  int* dResult, unsigned nUnits, void* cudaStream);

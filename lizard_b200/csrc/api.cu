@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) lizard_gather_segments_kernel(const u8* s
 // Second generation (decode2.cuh): one CTA of two warps per unit -- warp 0 parses (tokens -> records, literals stream staged
 // through shared memory by TMA bulk copies), warp 1 copies (records -> output tile -> coalesced 16-byte stores).
 // kStages = stages of 2 KiB in the literals ring.
-template <u32 kStages> __global__ void __launch_bounds__(64, kStages >= 8 ? 9 : 14)
+template <u32 kStages> __global__ void __launch_bounds__(64, kStages >= 8 ? 8 : 11)
 lizard_decode2_units_kernel(DecodeBatch b)
 {
     __shared__ PairShared<kStages> ps;
@@ -163,6 +163,10 @@ struct Context {
     DeviceBuffer pre_ws, pre_arena, pre_scratch, seq_ws, seq_recs;
     DeviceBuffer dec_scratch, enc_scratch, counters;
     u32 counter_slot = 0;
+    // The kernels of one device share the library-owned workspaces (scratch per grid warp, pre-pass arena, sequence list).
+    // Launches on ONE stream are ordered by the stream; a launch on a different stream than the previous one first waits
+    // for the previous launch's completion event, so two streams never run on the same scratch at once.
+    cudaEvent_t ws_done = nullptr; cudaStream_t ws_stream = nullptr; bool ws_used = false;
     // staging for the host-pointer entry points
     PinnedBuffer pin_in, pin_out, pin_tab, pin_flags;
     DeviceBuffer d_progress;
@@ -275,6 +279,18 @@ int ensure_context(Context& c, int device)
     return LIZARDB200_OK;
 }
 
+// workspace hand-over between streams (see Context::ws_done)
+void workspace_acquire(Context& c, cudaStream_t s)
+{
+    if (!c.ws_done) cudaEventCreateWithFlags(&c.ws_done, cudaEventDisableTiming);
+    if (c.ws_used && c.ws_stream != s && c.ws_done) cudaStreamWaitEvent(s, c.ws_done, 0);
+}
+void workspace_release(Context& c, cudaStream_t s)
+{
+    if (c.ws_done) cudaEventRecord(c.ws_done, s);
+    c.ws_stream = s; c.ws_used = true;
+}
+
 // a fresh zeroed work-queue counter for one launch
 u32* next_counter(Context& c, cudaStream_t s)
 {
@@ -288,18 +304,28 @@ u32* next_counter(Context& c, cudaStream_t s)
 // in-kernel expansion because their units arrive while the kernel is already running.
 constexpr u32 kPrepassMinUnits = 32;
 constexpr size_t kPrepassArenaPerUnit = 160u << 10;     // literals + flags of one 128 KiB block; overflow falls back in-kernel
+constexpr size_t kPrepassArenaMax = (size_t)3 << 30;    // never more than this, however many units a batch has: the plan kernel
+                                                        // hands out arena space by what the streams really need and leaves the
+                                                        // rest to the in-kernel expansion (a batch of a million 4 KiB units must
+                                                        // not ask for 160 KiB each)
 
 int launch_prepass(Context& c, DecodeBatch& b, cudaStream_t s)
 {
     const size_t n = b.n_units;
     const size_t ws_bytes = 256 + n * sizeof(UnitPre) + 2 * n * sizeof(HufJob);
-    const size_t arena_bytes = n * kPrepassArenaPerUnit;
+    size_t arena_bytes = n * kPrepassArenaPerUnit;
+    if (arena_bytes > kPrepassArenaMax) arena_bytes = kPrepassArenaMax;
     const size_t scratch_bytes = (size_t)c.sm_count * kExpWarps * kExpJobs * sizeof(HufJobScratch);
     if (ws_bytes > c.pre_ws.bytes || arena_bytes > c.pre_arena.bytes || scratch_bytes > c.pre_scratch.bytes) {
-        cudaStreamSynchronize(s);                       // an earlier launch may still be reading the buffers we are about to replace
-        CU_OK(c.pre_ws.reserve(ws_bytes));
-        CU_OK(c.pre_arena.reserve(arena_bytes));
-        CU_OK(c.pre_scratch.reserve(scratch_bytes));
+        // growing a workspace is the one place where an enqueue-only call synchronises (first call, or a larger batch than
+        // ever before): an earlier launch may still be reading the buffers that are about to be replaced
+        cudaStreamSynchronize(s);
+        if (c.pre_ws.reserve(ws_bytes) != cudaSuccess || c.pre_arena.reserve(arena_bytes) != cudaSuccess ||
+            c.pre_scratch.reserve(scratch_bytes) != cudaSuccess) {
+            cudaGetLastError();                          // no room for the pre-pass: the token kernel expands the streams itself
+            b.pre = nullptr; b.arena = nullptr;
+            return LIZARDB200_OK;
+        }
     }
     PrepassBatch p;
     p.src_base = b.src_base; p.src_off = b.src_off; p.src_len = b.src_len; p.n_units = b.n_units;
@@ -329,8 +355,11 @@ int launch_token_parse(Context& c, DecodeBatch& b, cudaStream_t s)
     if (rec_bytes < ((size_t)64 << 20)) rec_bytes = (size_t)64 << 20;
     if (ws_bytes > c.seq_ws.bytes || rec_bytes > c.seq_recs.bytes) {
         cudaStreamSynchronize(s);
-        CU_OK(c.seq_ws.reserve(ws_bytes));
-        CU_OK(c.seq_recs.reserve(rec_bytes));
+        if (c.seq_ws.reserve(ws_bytes) != cudaSuccess || c.seq_recs.reserve(rec_bytes) != cudaSuccess) {
+            cudaGetLastError();                          // optional pass: decode without it
+            b.seq = nullptr; b.recs = nullptr;
+            return LIZARDB200_OK;
+        }
     }
     SeqBatch q;
     q.src_base = b.src_base; q.src_off = b.src_off; q.src_len = b.src_len; q.dst_cap = b.dst_cap; q.n_units = b.n_units;
@@ -351,6 +380,8 @@ int launch_decode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* d
                   const Progress* pg = nullptr)
 {
     if (n == 0) return LIZARDB200_OK;
+    workspace_acquire(c, s);
+    struct Release { Context& c; cudaStream_t s; ~Release() { workspace_release(c, s); } } release_on_exit{c, s};
     DecodeBatch b;
     if (pg) b.progress = *pg; else memset(&b.progress, 0, sizeof b.progress);
     b.src_base = (const u8*)dSrc; b.src_off = dSrcOff; b.src_len = dSrcLen;
@@ -390,6 +421,8 @@ int launch_encode(Context& c, const void* dSrc, const u64* dSrcOff, const u32* d
     if (n == 0) return LIZARDB200_OK;
     LevelParams lp = level_params(level);
     if (lp.parser == kParserUnsupported) { g_last_error = "compression level not implemented on the GPU"; return LIZARDB200_ERR_LEVEL; }
+    workspace_acquire(c, s);
+    struct Release { Context& c; cudaStream_t s; ~Release() { workspace_release(c, s); } } release_on_exit{c, s};
     EncodeBatch b;
     if (pg) b.progress = *pg; else memset(&b.progress, 0, sizeof b.progress);
     if (fp) b.pack = *fp; else memset(&b.pack, 0, sizeof b.pack);

@@ -38,8 +38,10 @@ enum : u32 {
     kRecRing    = 128,          // records in the ring (4 batches of 32)
     kRecMask    = kRecRing - 1,
     kBatchSlots = 4,            // batches in flight between parser and copier
-    kTileBytes  = 2048,         // output tile of the copier
+    kTileBytes  = 6144,         // output window of the copier: one span = at most this many bytes
     kTileChunks = kTileBytes / 16,
+    kExtraCap   = 128,          // chunks waiting for the merge pass
+    kGroup      = 4,            // chunks a lane works on at once (all their loads in flight together)
 };
 
 struct CopyShared {                       // shared memory of one parser / copier pair
@@ -47,14 +49,13 @@ struct CopyShared {                       // shared memory of one parser / copie
     u32    pos[kRecRing];                 // opos of the records (the copier's search key); pos[n & mask] of the first unpublished
                                           // record holds the end of the published output
     alignas(16) u8 tile[kTileBytes];      // output bytes [T0, T0 + kTileBytes) under construction
-    u32    extras[kTileChunks];           // chunks of the current tile span that need the merge pass
-    u32    late_bits[kRecRing / 32];      // records whose match reads bytes of the current tile span
+    u32    extras[kExtraCap];             // chunks of the current span that need the merge pass
+    u32    late_bits[kRecRing / 32];      // records whose match reads bytes of the current span
 };
 
 struct CopyState {                        // registers of the copier
     u8* dst_al;                           // unit's dst rounded down to 16 bytes
     u32 unit_lo;                          // first aligned-space position that belongs to the unit (= dst & 15)
-    u32 T0;                               // aligned-space position of tile byte 0 (multiple of kTileBytes)
 };
 
 // ---- small pieces ---------------------------------------------------------------------------------------------------
@@ -108,33 +109,42 @@ LZ_HD Vec16 merge_from(const Vec16& acc, const Vec16& x, u32 lo)
     return r;
 }
 
+// A 16-byte source vector "in flight": the two aligned vectors that hold it and its byte phase.  Loading and realigning are
+// separate steps so that a lane can have the loads of several chunks outstanding before it touches any of the data.
+struct Raw16 { Vec16 v0, v1; u32 delta; };
+LZ_HD Vec16 raw_finish(const Raw16& r) { return realign16(r.v0, r.v1, r.delta); }
+LZ_HD Raw16 raw_none() { Raw16 r; r.v0 = vec16_zero(); r.v1 = r.v0; r.delta = 0; return r; }
+
 // 16 bytes X with X[i] = out[a + i] for i in [lo, hi), read from the already written output through aligned vectors.  Only
 // vectors that hold at least one needed byte are touched (a + lo >= 0 is the caller's bound check), so no access leaves the
 // 16-byte granules the needed bytes occupy.
-LZ_HD Vec16 fetch_out(const u8* dst_al, long a, u32 lo, u32 hi)
+LZ_HD Raw16 out_load(const u8* dst_al, long a, u32 lo, u32 hi)
 {
+    Raw16 r = raw_none();
 #if defined(__CUDA_ARCH__)
     const long a0 = a & ~15L;
-    Vec16 v0 = vec16_zero(), v1 = v0;
-    if (a + (long)lo < a0 + 16) v0 = ld_vec16(dst_al + a0);
-    if (a + (long)hi > a0 + 16) v1 = ld_vec16(dst_al + a0 + 16);
-    return realign16(v0, v1, (u32)(a & 15));
+    if (a + (long)lo < a0 + 16) r.v0 = ld_vec16(dst_al + a0);
+    if (a + (long)hi > a0 + 16) r.v1 = ld_vec16(dst_al + a0 + 16);
+    r.delta = (u32)(a & 15);
 #else
     u8 t[16] = {0};
     for (u32 i = lo; i < hi; ++i) t[i] = dst_al[a + (long)i];
-    Vec16 r; memcpy(&r, t, 16); return r;
+    memcpy(&r.v0, t, 16);
 #endif
+    return r;
 }
 
-// Literals stream as a plain pointer (host build, and the device when a stream is read in place)
+// Literals stream as a plain pointer (host build)
 struct LitPtr {
     const u8* p;
     LZ_HDM u32 byte(long pos) const { return p[pos]; }
-    LZ_HDM Vec16 chunk(long a, u32 lo, u32 hi) const
+    LZ_HDM Raw16 load(long a, u32 lo, u32 hi) const
     {
+        Raw16 r = raw_none();
         u8 t[16] = {0};
         for (u32 i = lo; i < hi; ++i) t[i] = p[a + (long)i];
-        Vec16 r; memcpy(&r, t, 16); return r;
+        memcpy(&r.v0, t, 16);
+        return r;
     }
 };
 
@@ -168,86 +178,125 @@ LZ_HD u32 rec_search(const u32* pos, u32 r0, u32 nrec, u32 top, u32 p)
 }
 
 // ---- the copier -----------------------------------------------------------------------------------------------------
-// One tile span: output positions [cur_begin, cur_end) of the tile at st.T0, covered by records [r0, r0 + nrec).
-// Invariant on entry and exit: every byte below cur_begin (on exit: below cur_end) is in global memory; the tile holds the
-// bytes of [T0, cur_begin) that share a chunk with cur_begin.
+// merge pass over the chunks listed in extras[0, nx): one lane per chunk walks the chunk's remaining pieces.  The walk
+// depends only on the records, so a lane first issues the loads of up to four pieces and then merges them in order.
+template <class W, class LV>
+LZ_HD void copy_merge_pass(CopyShared* cs, const LV& lv, const CopyState& st, u32 r0, u32 T0, u32 nx, u32 cur_begin, u32 cur_end)
+{
+    const u32 lane = W::lane(), L = W::lanes();
+    u8* const tile = cs->tile;
+    for (u32 base = 0; base < nx; base += L) {
+        const u32 i = base + lane;
+        if (i < nx) {
+            const u32 ex = cs->extras[i];
+            const u32 toff = (ex & 511u) << 4;
+            const u32 c0 = T0 + toff;
+            u32 s = (ex >> 9) & 127u;
+            u32 p = c0 + (ex >> 16);
+            const u32 cend = c0 + 16 < cur_end ? c0 + 16 : cur_end;
+            Vec16 acc = tile_load(tile, toff);
+            while (p < cend) {
+                Raw16 raw[4]; u32 lo[4]; bool have[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    have[k] = false; lo[k] = 0; raw[k] = raw_none();
+                    // skip what lies behind p: empty matches, empty literal runs
+                    while (p < cend && p >= cs->pos[(r0 + s + 1) & kRecMask]) ++s;
+                    if (p < cend) {
+                        const OutRec d = cs->rec[(r0 + s) & kRecMask];
+                        const u32 nxt = cs->pos[(r0 + s + 1) & kRecMask];
+                        lo[k] = p - c0;
+                        if (p < d.mdst) {
+                            const u32 e = d.mdst < cend ? d.mdst : cend;
+                            raw[k] = lv.load((long)d.lsrc + (long)c0 - (long)d.opos, p - c0, e - c0);
+                            have[k] = true; p = e;
+                        } else {
+                            const u32 e = nxt < cend ? nxt : cend;
+                            if (e - d.off > cur_begin) lanes_or_u32(&cs->late_bits[s >> 5], 1u << (s & 31));
+                            else { raw[k] = out_load(st.dst_al, (long)c0 - (long)d.off, p - c0, e - c0); have[k] = true; }
+                            p = e;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (have[k]) acc = merge_from(acc, raw_finish(raw[k]), lo[k]);
+            }
+            tile_store(tile, toff, acc);
+        }
+    }
+}
+
+// One span: output positions [cur_begin, cur_end), at most kTileBytes from cur_begin & ~15, covered by records [r0, r0 + nrec).
+// The tile holds aligned-space bytes from T0 = cur_begin & ~15 on; on entry its first chunk holds the bytes of [T0, cur_begin)
+// (left there by the previous span or by copy_resync).  Invariant on entry and exit: every byte below cur_begin (on exit:
+// below cur_end) is in global memory.
 template <class W, class LV>
 LZ_HD void copy_tile_span(CopyShared* cs, const LV& lv, const CopyState& st, u32 r0, u32 nrec, u32 cur_begin, u32 cur_end)
 {
     const u32 lane = W::lane(), L = W::lanes();
-    const u32 T0 = st.T0;
+    const u32 T0 = cur_begin & ~15u;
     u8* const tile = cs->tile;
-    const u32 cur0 = cur_begin & ~15u;
     u32 top = 0;
     if (nrec > 1) { top = 1; while (top * 2 < nrec) top *= 2; }
     if (lane < kRecRing / 32) cs->late_bits[lane] = 0;
     if (L < kRecRing / 32) for (u32 i = 0; i < kRecRing / 32; ++i) cs->late_bits[i] = 0;
     W::sync();
-    // ---- pass 1: the run a chunk starts in fills the chunk's vector; anything else in the chunk is left to pass 2
+    // ---- pass 1: the run a chunk starts in fills the chunk's vector; anything else in the chunk is left to the merge pass.
+    //      A lane takes kGroup chunks per step (L chunks apart, so that each load instruction of the warp covers consecutive
+    //      vectors): first all searches, then all loads, then the realignments and stores.
     u32 nx = 0;
-    for (u32 stepb = cur0; stepb < cur_end; stepb += 16 * L) {
-        const u32 c0 = stepb + 16 * lane;
-        u32 ex = 0; bool want = false;
-        if (c0 < cur_end) {
-            const u32 cend = c0 + 16 < cur_end ? c0 + 16 : cur_end;
-            if (c0 < cur_begin) {                 // partly filled by an earlier span: all new bytes go through the merge pass
-                const u32 s = rec_search(cs->pos, r0, nrec, top, cur_begin);
-                ex = ((c0 - T0) >> 4) | (s << 7) | ((cur_begin - c0) << 14); want = true;
-            } else {
-                const u32 s = rec_search(cs->pos, r0, nrec, top, c0);
+    for (u32 stepb = T0; stepb < cur_end; stepb += 16 * L * kGroup) {
+        u32 sI[kGroup], eI[kGroup]; Raw16 raw[kGroup];
+#pragma unroll
+        for (u32 k = 0; k < kGroup; ++k) {
+            const u32 c0 = stepb + 16 * (lane + L * k);
+            sI[k] = c0 < cur_end ? rec_search(cs->pos, r0, nrec, top, c0 < cur_begin ? cur_begin : c0) : 0u;
+        }
+#pragma unroll
+        for (u32 k = 0; k < kGroup; ++k) {
+            const u32 c0 = stepb + 16 * (lane + L * k);
+            raw[k] = raw_none(); eI[k] = c0;
+            if (c0 < cur_end && c0 >= cur_begin) {
+                const u32 cend = c0 + 16 < cur_end ? c0 + 16 : cur_end;
+                const u32 s = sI[k];
                 const OutRec d = cs->rec[(r0 + s) & kRecMask];
-                const u32 nxt = cs->pos[(r0 + s + 1) & kRecMask];
-                Vec16 X = vec16_zero();
-                u32 e;
                 if (c0 < d.mdst) {
-                    e = d.mdst < cend ? d.mdst : cend;
-                    X = lv.chunk((long)d.lsrc + (long)(c0 - d.opos), 0, e - c0);
+                    eI[k] = d.mdst < cend ? d.mdst : cend;
+                    raw[k] = lv.load((long)d.lsrc + (long)(c0 - d.opos), 0, eI[k] - c0);
                 } else {
-                    e = nxt < cend ? nxt : cend;
-                    if (e - d.off > cur_begin) lanes_or_u32(&cs->late_bits[s >> 5], 1u << (s & 31));
-                    else X = fetch_out(st.dst_al, (long)c0 - (long)d.off, 0, e - c0);
+                    const u32 nxt = cs->pos[(r0 + s + 1) & kRecMask];
+                    eI[k] = nxt < cend ? nxt : cend;
+                    if (eI[k] - d.off > cur_begin) lanes_or_u32(&cs->late_bits[s >> 5], 1u << (s & 31));
+                    else raw[k] = out_load(st.dst_al, (long)c0 - (long)d.off, 0, eI[k] - c0);
                 }
-                tile_store(tile, c0 - T0, X);
-                if (e < cend) { ex = ((c0 - T0) >> 4) | (s << 7) | ((e - c0) << 14); want = true; }
             }
         }
-        const u32 wm = W::ballot(want);
-        if (want) cs->extras[nx + popc32(wm & ((1u << lane) - 1))] = ex;
-        nx += popc32(wm);
+#pragma unroll
+        for (u32 k = 0; k < kGroup; ++k) {
+            const u32 c0 = stepb + 16 * (lane + L * k);
+            bool want = false; u32 ex = 0;
+            if (c0 < cur_end) {
+                const u32 cend = c0 + 16 < cur_end ? c0 + 16 : cur_end;
+                if (c0 >= cur_begin) tile_store(tile, c0 - T0, raw_finish(raw[k]));
+                // c0 < cur_begin: the span's first chunk, partly filled earlier -- all its new bytes go through the merge pass
+                if (eI[k] < cend || c0 < cur_begin) {
+                    const u32 p = c0 < cur_begin ? cur_begin : eI[k];
+                    ex = ((c0 - T0) >> 4) | (sI[k] << 9) | ((p - c0) << 16); want = true;
+                }
+            }
+            const u32 wm = W::ballot(want);
+            if (nx + popc32(wm) > kExtraCap) {               // list full: merge what is listed (those chunks are stored), start over
+                W::sync();
+                copy_merge_pass<W>(cs, lv, st, r0, T0, nx, cur_begin, cur_end);
+                W::sync();
+                nx = 0;
+            }
+            if (want) cs->extras[nx + popc32(wm & ((1u << lane) - 1))] = ex;
+            nx += popc32(wm);
+        }
     }
     W::sync();
-    // ---- pass 2: chunks with a run boundary, one lane each: walk the remaining pieces, merge in registers
-    for (u32 base = 0; base < nx; base += L) {
-        const u32 i = base + lane;
-        if (i < nx) {
-            const u32 ex = cs->extras[i];
-            const u32 toff = (ex & 127u) << 4;
-            const u32 c0 = T0 + toff;
-            u32 s = (ex >> 7) & 127u;
-            u32 p = c0 + (ex >> 14);
-            const u32 cend = c0 + 16 < cur_end ? c0 + 16 : cur_end;
-            Vec16 acc = tile_load(tile, toff);
-            while (p < cend) {
-                const OutRec d = cs->rec[(r0 + s) & kRecMask];
-                const u32 nxt = cs->pos[(r0 + s + 1) & kRecMask];
-                if (p < d.mdst) {
-                    const u32 e = d.mdst < cend ? d.mdst : cend;
-                    const Vec16 X = lv.chunk((long)d.lsrc + (long)c0 - (long)d.opos, p - c0, e - c0);
-                    acc = merge_from(acc, X, p - c0);
-                    p = e;
-                } else if (p < nxt) {
-                    const u32 e = nxt < cend ? nxt : cend;
-                    if (e - d.off > cur_begin) lanes_or_u32(&cs->late_bits[s >> 5], 1u << (s & 31));
-                    else {
-                        const Vec16 X = fetch_out(st.dst_al, (long)c0 - (long)d.off, p - c0, e - c0);
-                        acc = merge_from(acc, X, p - c0);
-                    }
-                    p = e;
-                } else ++s;
-            }
-            tile_store(tile, toff, acc);
-        }
-    }
+    copy_merge_pass<W>(cs, lv, st, r0, T0, nx, cur_begin, cur_end);
     W::sync();
     // ---- late matches, in record order (= output order): their source bytes are final by the time they are read
     for (u32 w = 0; w < kRecRing / 32; ++w) {
@@ -286,44 +335,60 @@ LZ_HD void copy_tile_span(CopyShared* cs, const LV& lv, const CopyState& st, u32
     }
     W::sync();
     // ---- flush: complete chunks as aligned 16-byte stores (consecutive lanes, consecutive vectors); the bytes of a trailing
-    //      partial chunk go out one by one so that the invariant holds (the whole chunk is stored again once it is complete)
+    //      partial chunk go out one by one so that the invariant holds, and the chunk itself moves to the front of the tile,
+    //      where the next span expects it
     const u32 fe = cur_end & ~15u;
-    for (u32 c = cur0 + 16 * lane; c < fe; c += 16 * L) {
-        if (c >= st.unit_lo) {
-            const Vec16 v = tile_load(tile, c - T0);
-            st_vec16(st.dst_al + c, v.w[0], v.w[1], v.w[2], v.w[3]);
-        } else {
-            for (u32 q = st.unit_lo; q < c + 16; ++q) st.dst_al[q] = tile[q - T0];     // the unit starts inside this chunk
+    for (u32 cb = T0; cb < fe; cb += 16 * L * kGroup) {
+        Vec16 v[kGroup];
+#pragma unroll
+        for (u32 k = 0; k < kGroup; ++k) {
+            const u32 c = cb + 16 * (lane + L * k);
+            if (c < fe) v[k] = tile_load(tile, c - T0);
+        }
+#pragma unroll
+        for (u32 k = 0; k < kGroup; ++k) {
+            const u32 c = cb + 16 * (lane + L * k);
+            if (c < fe) {
+                if (c >= st.unit_lo) st_vec16(st.dst_al + c, v[k].w[0], v[k].w[1], v[k].w[2], v[k].w[3]);
+                else for (u32 q = st.unit_lo; q < c + 16; ++q) st.dst_al[q] = tile[q - T0];     // the unit starts inside this chunk
+            }
         }
     }
     if (cur_end & 15u) {
         const u32 from = fe > st.unit_lo ? fe : st.unit_lo;
         for (u32 q = from + lane; q < cur_end; q += L) st.dst_al[q] = tile[q - T0];
+        W::sync();
+        if (fe != T0) {
+            u32 w = 0;
+            if (lane < 4) w = *reinterpret_cast<const u32*>(tile + (fe - T0) + 4 * lane);
+            if (L < 4) { Vec16 t = tile_load(tile, fe - T0); tile_store(tile, 0, t); }
+            W::sync();
+            if (lane < 4 && L >= 4) *reinterpret_cast<u32*>(tile + 4 * lane) = w;
+        }
     }
     W::sync();
 }
 
-// Published records [r0, r0 + nrec) produce output [B0, B1): tile by tile.
+// Published records [r0, r0 + nrec) produce output [B0, B1): in spans of at most one tile.
 template <class W, class LV>
 LZ_HD void copy_span(CopyShared* cs, const LV& lv, CopyState& st, u32 r0, u32 nrec, u32 B0, u32 B1)
 {
     u32 cur = B0;
     while (cur < B1) {
-        if (cur >= st.T0 + kTileBytes) st.T0 = cur & ~(kTileBytes - 1u);
-        const u32 tend = B1 < st.T0 + kTileBytes ? B1 : st.T0 + kTileBytes;
+        const u32 lim = (cur & ~15u) + kTileBytes;
+        const u32 tend = B1 < lim ? B1 : lim;
         copy_tile_span<W>(cs, lv, st, r0, nrec, cur, tend);
         cur = tend;
     }
 }
 
 // (Re)start of the copier at aligned-space position `apos` (start of a unit; after the parser has written output itself):
-// the bytes of apos's chunk that lie below apos are taken over from global memory.
+// the bytes of apos's chunk that lie below apos are taken over from global memory into the front of the tile.
 template <class W>
 LZ_HD void copy_resync(CopyShared* cs, CopyState& st, u32 apos)
 {
-    st.T0 = apos & ~(kTileBytes - 1u);
     const u32 c = apos & ~15u;
-    for (u32 q = c + W::lane(); q < apos; q += W::lanes()) cs->tile[q - st.T0] = q >= st.unit_lo ? st.dst_al[q] : (u8)0;
+    for (u32 q = c + W::lane(); q < apos; q += W::lanes()) cs->tile[q - c] = q >= st.unit_lo ? st.dst_al[q] : (u8)0;
     W::sync();
 }
 
@@ -371,13 +436,20 @@ template <class LV> LZ_HD bool ext_field_lv(const LV& lv, long nl, long p, u32* 
     *size = sz;
     return true;
 }
+// `limit`: fields that begin more than this many bytes behind lp are not read (the staged part of the stream ends there);
+// their tokens get positions far outside every bound, so that the caller sees them as "do not fit this batch".
 template <class W, class LV> LZ_HD bool ext_chain_lv(const LV& lv, long nl, long lp, u32 npend, const u32* ent, u32* epre,
-                                                     u32 lbias, long room, u32 gap, u32* total)
+                                                     u32 lbias, long room, u32 gap, u32 limit, u32* total)
 {
     u32 E = 0;
     for (u32 j = 0; j < npend; ++j) {
         const u32 e = ent[j];
         const long base = lp + (long)(e & 0xffffu) + (long)E;
+        if (base - lp > (long)limit) {
+            if (W::lane() == 0) for (u32 i = j; i < npend; ++i) epre[i] = 0x40000000u;
+            *total = 0x40000000u;
+            return true;
+        }
         if (W::lane() == 0) epre[j] = E;
         long pm;
         if (e & (1u << 24)) {
@@ -431,7 +503,7 @@ LZ_HD int parse_tokens_lz4(const Streams& s, const LV& lv, SK& sk, u8* dst, u32 
         if (need || needm) sh->chain.ent[myidx] = A | (litn << 16) | (need ? 1u << 24 : 0u) | (needm ? 1u << 25 : 0u);
         W::sync();
         u32 tot_ext = 0;
-        bool slow = !ext_chain_lv<W>(lv, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, 15, 5, 2, &tot_ext);
+        bool slow = !ext_chain_lv<W>(lv, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, 15, 5, 2, sk.span(), &tot_ext);
         bool taken = false;
         if (!slow) {
             W::sync();
@@ -472,7 +544,7 @@ LZ_HD int parse_tokens_lz4(const Streams& s, const LV& lv, SK& sk, u8* dst, u32 
             if (nfit > 0 && W::ballot(bad) == 0) {
                 OutRec r;
                 r.opos = (u32)opos + skew; r.lsrc = (u32)lit_src; r.mdst = (u32)opos + lit_len + skew; r.off = off;
-                const long lp_end = nfit == nb ? c.lp + (long)tot_adv + (long)tot_ext : (long)W::shfl((u32)tokpos, nfit & (NL - 1));
+                const long lp_end = (long)W::shfl((u32)tok_end, nfit - 1);      // first stream byte behind the last token taken
                 sk.publish(mine, r, nfit, (u32)(c.op + (long)tot_out) + skew, (u32)c.lp);
                 c.fp += nfit; c.lp = lp_end; c.op += (long)tot_out;
                 taken = true;
@@ -522,7 +594,7 @@ LZ_HD int parse_tokens_lizv1(const Streams& s, const LV& lv, SK& sk, u8* dst, u3
         if (need || mlext) sh->chain.ent[myidx] = A | (litn << 16) | (need ? 1u << 24 : 0u) | (mlext ? 1u << 25 : 0u);
         W::sync();
         u32 tot_ext = 0;
-        bool slow = !ext_chain_lv<W>(lv, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, 7, 1, 0, &tot_ext);
+        bool slow = !ext_chain_lv<W>(lv, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, 7, 1, 0, sk.span(), &tot_ext);
         bool taken = false;
         if (!slow) {
             W::sync();
@@ -576,7 +648,7 @@ LZ_HD int parse_tokens_lizv1(const Streams& s, const LV& lv, SK& sk, u8* dst, u3
                 OutRec r;
                 r.opos = (u32)opos + skew; r.lsrc = (u32)lit_src; r.mdst = (u32)opos + lit_len + skew; r.off = off;
                 const bool all = nfit == nb;
-                const long lp_end = all ? c.lp + (long)tot_adv + (long)tot_ext : (long)W::shfl((u32)tokpos, nfit & (NL - 1));
+                const long lp_end = (long)W::shfl((u32)tok_end, nfit - 1);
                 const u32 n16 = all ? tot16 : W::shfl(P16, nfit & (NL - 1));
                 const u32 n24 = all ? tot24 : W::shfl(P24, nfit & (NL - 1));
                 const u32 last = W::shfl(off, nfit - 1);
@@ -728,12 +800,12 @@ template <u32 kStages> struct LitRingView {
     static constexpr u32 kMask = kStages * kLitStage - 1;
     const u8* ring; u32 ls;
     __device__ __forceinline__ u32 byte(long pos) const { return ring[((u32)pos + ls) & kMask]; }
-    __device__ __forceinline__ Vec16 chunk(long a, u32, u32) const
+    __device__ __forceinline__ Raw16 load(long a, u32, u32) const
     {
         const u32 x = (u32)a + ls;                       // wraps consistently for the (masked-out) bytes in front of a run
         const u32 a0 = (x & ~15u) & kMask;
-        const Vec16 v0 = tile_load(ring, a0), v1 = tile_load(ring, (a0 + 16) & kMask);
-        return realign16(v0, v1, x & 15u);
+        Raw16 r; r.v0 = tile_load(ring, a0); r.v1 = tile_load(ring, (a0 + 16) & kMask); r.delta = x & 15u;
+        return r;
     }
 };
 
@@ -801,7 +873,9 @@ template <u32 kStages> struct PairSink {
         for (;;) {
             poll_acks();
             const u32 fs = free_stage(lp);
-            while (issued < nstages && issued < fs + kStages) issue(issued++);
+            // a slot takes its next stage only when the parser has seen the previous one land (one phase per mbarrier at a time)
+            // and nobody needs the previous one any more
+            while (issued < nstages && issued < fs + kStages && issued < waited + kStages) issue(issued++);
             if (waited > need) break;
             if (waited < issued) { wait_stage(waited); ++waited; continue; }
             if (acked == msg_count) __trap();             // nothing in flight, nothing to wait for: span() is too large
@@ -878,7 +952,7 @@ template <u32 kStages> struct PairSink {
 // the copier warp's life
 template <u32 kStages> __device__ __forceinline__ void copier_loop(PairShared<kStages>* ps)
 {
-    CopyState st; st.dst_al = nullptr; st.unit_lo = 0; st.T0 = 0;
+    CopyState st; st.dst_al = nullptr; st.unit_lo = 0;
     LitRingView<kStages> lv; lv.ring = ps->ring; lv.ls = 0;
     for (u32 m = 0;; ++m) {
         const u32 slot = m % kBatchSlots;

@@ -372,7 +372,6 @@ template <class W> static int decode2_run(const unsigned char* src, int csize, u
     sk.cs = cs; sk.lits.p = nullptr; sk.nrec_total = 0; sk.span_limit = span; sk.out_pos = 0;
     sk.st.unit_lo = (lzb::u32)((size_t)dst & 15);
     sk.st.dst_al = dst - sk.st.unit_lo;
-    sk.st.T0 = 0;
     sk.resync(sk.st.unit_lo);
     return lzb::decode_unit2<W>(src, (lzb::u32)csize, dst, (lzb::u32)cap, scratch, core, sk);
 }

@@ -16,5 +16,5 @@ for K in lizard_encode_units lizard_decode_units lizard_decode2_units lizard_huf
     python tools/ncu_opcodes.py $REP $K $LIB > gpurun_out/${TAG}_opcodes_$K.txt 2>&1
   fi
 done
-SZ=$(stat -c %s $REP)
-if [ $SZ -gt 12000000 ]; then rm -f $REP; fi
+SZ=$(stat -c %s $REP 2>/dev/null)
+if [ -n "$SZ" ] && [ "$SZ" -gt 12000000 ]; then rm -f $REP; fi
