@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblizard_b200.so")
+LIB_PATH = os.environ.get("LIZARDB200_LIB") or os.path.join(_HERE, "liblizard_b200.so")     # the override is for A/B builds (tools/)
 DATAGEN_PATH = os.path.join(os.path.dirname(_HERE), "tools", "libdatagen.so")   # bench / test input generator, not product code
 
 BLOCK_SIZE = 1 << 17

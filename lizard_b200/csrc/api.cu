@@ -8,6 +8,8 @@
 
 #include <cuda_runtime.h>
 #include <mutex>
+#include <thread>
+#include <functional>
 #include <vector>
 #include <string>
 #include <atomic>
@@ -157,9 +159,10 @@ struct Context {
     bool ready = false, failed = false;
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;   // compute / H2D / D2H
-    int dec_grid = 0, dec_variant = 23;       // bits 0-1: schedule of the token loops, bit 2: Huffman pre-pass, bit 3: token pre-pass,
+    int dec_grid = 0, dec_variant = 7;        // bits 0-1: schedule of the token loops, bit 2: Huffman pre-pass, bit 3: token pre-pass,
                                               // bit 4: second-generation kernel (parser + copier warp per unit)
     int dec2_grid = 0, dec2_stages = 4;
+    int exp_ctas = 1;                         // CTAs per SM of the Huffman expand kernel
     DeviceBuffer pre_ws, pre_arena, pre_scratch, seq_ws, seq_recs;
     DeviceBuffer dec_scratch, enc_scratch, counters;
     u32 counter_slot = 0;
@@ -227,9 +230,16 @@ int ensure_context(Context& c, int device)
         return (int)(pct > 100 ? 100 : pct);
     };
     e = cudaFuncSetAttribute(lizard_huf_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(ExpWarpShared) * kExpWarps));
+    {   // as many expand CTAs per SM as their tables allow, at most kExpCtasMax (1 GiB of 128 KiB blocks is ~14 warps of
+        // bitstreams per SM; more CTAs than that find no work).  LIZARDB200_EXP_CTAS_PER_SM overrides.
+        int fit = (int)(prop.sharedMemPerMultiprocessor / (sizeof(ExpWarpShared) * kExpWarps + 1024));
+        if (fit < 1) fit = 1;
+        c.exp_ctas = fit > (int)kExpCtasMax ? (int)kExpCtasMax : fit;
+        if (const char* v = getenv("LIZARDB200_EXP_CTAS_PER_SM")) { const int w = atoi(v); if (w >= 1 && w <= fit) c.exp_ctas = w; }
+    }
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(lizard_huf_expand_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 carveout(sizeof(ExpWarpShared) * kExpWarps + 1024, "LIZARDB200_EXP_CARVEOUT"));
+                                 carveout((size_t)c.exp_ctas * (sizeof(ExpWarpShared) * kExpWarps + 1024), "LIZARDB200_EXP_CARVEOUT"));
     if (e != cudaSuccess) { c.failed = true; fail("cudaFuncSetAttribute(expand)", e); return LIZARDB200_ERR_CUDA; }
     e = cudaSuccess;
     for (int v = 0; v < 4 && e == cudaSuccess; ++v)
@@ -315,7 +325,7 @@ int launch_prepass(Context& c, DecodeBatch& b, cudaStream_t s)
     const size_t ws_bytes = 256 + n * sizeof(UnitPre) + 2 * n * sizeof(HufJob);
     size_t arena_bytes = n * kPrepassArenaPerUnit;
     if (arena_bytes > kPrepassArenaMax) arena_bytes = kPrepassArenaMax;
-    const size_t scratch_bytes = (size_t)c.sm_count * kExpWarps * kExpJobs * sizeof(HufJobScratch);
+    const size_t scratch_bytes = (size_t)c.sm_count * c.exp_ctas * kExpWarps * kExpJobs * sizeof(HufJobScratch);
     if (ws_bytes > c.pre_ws.bytes || arena_bytes > c.pre_arena.bytes || scratch_bytes > c.pre_scratch.bytes) {
         // growing a workspace is the one place where an enqueue-only call synchronises (first call, or a larger batch than
         // ever before): an earlier launch may still be reading the buffers that are about to be replaced
@@ -336,7 +346,7 @@ int launch_prepass(Context& c, DecodeBatch& b, cudaStream_t s)
     p.scratch = (HufJobScratch*)c.pre_scratch.p;
     CU_OK(cudaMemsetAsync(p.hdr, 0, sizeof(PreHeader), s));
     lizard_huf_plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(p);
-    lizard_huf_expand_kernel<<<c.sm_count, kExpWarps * 32, sizeof(ExpWarpShared) * kExpWarps, s>>>(p);
+    lizard_huf_expand_kernel<<<c.sm_count * c.exp_ctas, kExpWarps * 32, sizeof(ExpWarpShared) * kExpWarps, s>>>(p);
     g_launches += 2;
     CU_OK(cudaGetLastError());
     b.pre = p.pre; b.arena = p.arena;

@@ -39,6 +39,19 @@ struct Xxh32 {
 };
 inline u32 xxh32(const void* p, size_t n, u32 seed) { Xxh32 x; x.reset(seed); x.update(p, n); return x.digest(); }
 
+// XXH32 of one buffer on a helper thread (the frame layer's content checksum beside the GPU work of the same call)
+constexpr size_t kHashThreadMin = 1u << 20;
+struct HashJob {
+    std::thread th; bool on = false;
+    void start(Xxh32* x, const void* p, size_t n)
+    {
+        try { th = std::thread([x, p, n] { x->update(p, n); }); on = true; } catch (...) { on = false; }
+    }
+    bool running() const { return on; }
+    void join() { if (on) { th.join(); on = false; } }
+    ~HashJob() { join(); }
+};
+
 // ---- frame constants / errors (lib/lizard_frame_static.h:56-67) ----
 enum : int { FE_OK = 0, FE_GENERIC, FE_maxBlockSize_invalid, FE_blockMode_invalid, FE_contentChecksumFlag_invalid,
              FE_compressionLevel_invalid, FE_headerVersion_wrong, FE_blockChecksum_unsupported, FE_reservedFlag_set,
@@ -391,13 +404,19 @@ size_t LizardF_compressUpdate(LizardF_compressionContext_t c, void* dstBuffer, s
     const u8* sp = (const u8*)srcBuffer; const u8* const se = sp + srcSize;
     u8* const d0 = (u8*)dstBuffer; u8* d = d0; u8* const de = d0 + dstMax;
     const size_t bs = c->block_size;
+    // Content checksum (lib/lizard_frame.c:585-586): XXH32 over everything fed in, in order.  It is a serial recurrence
+    // (one host thread, ~6 GB/s), so it runs beside the GPU work of this call instead of behind it; the call returns when
+    // both are done.  Small inputs are hashed in line.
+    const bool want_hash = c->prefs.frameInfo.contentChecksumFlag == LizardF_contentChecksumEnabled;
+    HashJob hash_job;
+    if (want_hash && srcSize >= kHashThreadMin) hash_job.start(&c->xxh, srcBuffer, srcSize);
     if (!c->tmp.empty()) {                                   // complete the pending partial block first
         size_t need = bs - c->tmp.size();
         if (need > srcSize) { c->tmp.insert(c->tmp.end(), sp, se); sp = se; }
         else {
             c->tmp.insert(c->tmp.end(), sp, sp + need); sp += need;
             size_t r = frame_flush_tmp(c, d, (size_t)(de - d));
-            if (LizardF_isError(r)) return r;
+            if (LizardF_isError(r)) { hash_job.join(); return r; }
             d += r;
         }
     }
@@ -405,11 +424,11 @@ size_t LizardF_compressUpdate(LizardF_compressionContext_t c, void* dstBuffer, s
     if (c->prefs.autoFlush) whole = (size_t)(se - sp);       // autoFlush also emits the trailing partial block
     if (whole) {
         size_t r = frame_compress_blocks(g, d, (size_t)(de - d), sp, whole, bs, lvl);
-        if (LizardF_isError(r)) return r;
+        if (LizardF_isError(r)) { hash_job.join(); return r; }
         d += r; sp += whole;
     }
     if (sp < se) c->tmp.assign(sp, se);
-    if (c->prefs.frameInfo.contentChecksumFlag == LizardF_contentChecksumEnabled) c->xxh.update(srcBuffer, srcSize);
+    if (want_hash) { if (hash_job.running()) hash_job.join(); else c->xxh.update(srcBuffer, srcSize); }
     c->total_in += srcSize;
     return (size_t)(d - d0);
 }

@@ -20,7 +20,7 @@ struct PrepassBatch {
 // warps per CTA, jobs per warp round.  One CTA per SM: 1 GiB of 128 KiB blocks is 32768 literals segments = 1024 warps,
 // 7 x 148 warps take them in a single wave; 7 x 8 two-level tables are 130 KB, the rest of the SM's 256 KB stays L1 for
 // the 224 bitstreams read at once.
-enum : u32 { kExpWarps = 7, kExpJobs = 8 };
+enum : u32 { kExpWarps = 7, kExpJobs = 8, kExpCtasMax = 2 };
 
 struct ExpWarpShared {
     HufCompact table[kExpJobs];
@@ -94,7 +94,7 @@ lizard_huf_plan_kernel(PrepassBatch b)
 
 // persistent warps; every round a warp takes kExpJobs jobs of one kind (all literals streams first: similar sizes side by
 // side keep the 32 segment decoders of a warp busy for about the same time)
-__global__ void __launch_bounds__(kExpWarps * 32, 1)
+__global__ void __launch_bounds__(kExpWarps * 32, kExpCtasMax)
 lizard_huf_expand_kernel(PrepassBatch b)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -9,7 +9,7 @@ from tests import refs
 
 pytestmark = pytest.mark.gpu
 BS = lz.BLOCK_SIZE
-DEFAULT_VARIANT = 23         # the library's default (api.cu Context::dec_variant)
+DEFAULT_VARIANT = 7          # the library's default (api.cu Context::dec_variant)
 
 
 @pytest.fixture(scope="module")
