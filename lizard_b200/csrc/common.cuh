@@ -64,8 +64,8 @@ enum : u32 {
     kHufHeaderFseLog    = 6,        // MAX_FSE_TABLELOG_FOR_HUFF_HEADER
 };
 
-// Parsers on the hot path.  Levels 10/30 fastSmall, 11/31 fast, 13-17/34-38 hashChain, 21/22/41/42 priceFast.
-enum Parser : int { kParserFastSmall = 0, kParserFast = 1, kParserHashChain = 3, kParserPriceFast = 5, kParserUnsupported = -1 };
+// Parsers on the hot path.  Levels 10/30 fastSmall, 11/31 fast, 13-17/34-38 hashChain, 20/40 fastBig, 21/22/41/42 priceFast.
+enum Parser : int { kParserFastSmall = 0, kParserFast = 1, kParserFastBig = 2, kParserHashChain = 3, kParserPriceFast = 5, kParserUnsupported = -1 };
 
 struct LevelParams {
     u32 windowLog;
@@ -93,6 +93,8 @@ LZ_HD LevelParams level_params(int level)
     case 13: case 14: case 15: case 16: case 17:          // searchNum 2,4,8,16,256; searchLength 5,5,5,4,4
              p.windowLog = 16; p.hashLog = 18; p.chainLog = 16; p.parser = kParserHashChain;
              p.searchNum = base == 17 ? 256u : (2u << (base - 13)); p.searchLength = base >= 16 ? 4 : 5; break;
+    case 20: p.windowLog = 22; p.hashLog = 14; p.searchLength = 5; p.minMatchLongOff = kMmLongOff;
+             p.parser = kParserFastBig; p.lizv1 = 1; break;
     case 21: p.windowLog = 22; p.hashLog = 14; p.searchLength = 5; p.minMatchLongOff = kMmLongOff;
              p.parser = kParserPriceFast; p.lizv1 = 1; break;
     case 22: p.windowLog = 22; p.hashLog = 18; p.searchLength = 5; p.minMatchLongOff = kMmLongOff;

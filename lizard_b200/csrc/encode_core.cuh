@@ -334,7 +334,7 @@ struct PackedTable {
 #define LZB_ENC_TAGS 1
 #endif
 LZ_HD bool enc_tagged(const LevelParams& lp) { return LZB_ENC_TAGS && (lp.parser == kParserFastSmall || lp.parser == kParserFast); }
-LZ_HD bool enc_tagged_plain(const LevelParams& lp) { return LZB_ENC_TAGS && (enc_tagged(lp) || lp.parser == kParserPriceFast); }
+LZ_HD bool enc_tagged_plain(const LevelParams& lp) { return LZB_ENC_TAGS && (enc_tagged(lp) || lp.parser == kParserPriceFast || lp.parser == kParserFastBig); }
 
 // bytes of a packed table: 16-bit entries + the bit plane (+ one tag byte per entry for the fast parsers)
 LZ_HD size_t hash_packed_bytes(u32 hash_log, bool tagged)
@@ -410,7 +410,11 @@ template <class W> LZ_HD u32 extend_back_par(const u8* src, u32 ip, u32 mpos, u3
 // matches.  So lanes evaluate probes j0..j0+L-1 together; a lane's candidate is the latest earlier lane of
 // the same batch with the same bucket, else the table; the lowest hitting lane wins and only buckets of
 // lanes up to the winner are committed (last writer per bucket).
-template <class W, class TT> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u32 b0, u32 b1, EncStreams& s)
+// kBig = Lizard_compress_fastBig (lib/lizard_parser_fastbig.h:35-175, levels 20 / 40): the same walk with LIZv1 codewords
+// and one more acceptance rule -- a candidate 65536 or more bytes back is only taken when the match (backward extension
+// included; the post-match probe: forward part only) is at least MM_LONGOFF + MINMATCH long (:99, :142); a refused
+// candidate is an ordinary miss: its position stays in the table and the search goes on with the next probe.
+template <class W, class TT, bool kBig = false> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u32 b0, u32 b1, EncStreams& s)
 {
     const u8* const src = c.src;
     const TT T = c.T;
@@ -422,6 +426,7 @@ template <class W, class TT> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u3
     const u32 low_limit = (bias + max_dist >= b0 + bias) ? bias : b0 + bias - max_dist;
     u32 anchor = b0, ip = b0;
     u32 ml = 0, mpos = 0;
+    u32 last_off = 0;                                                          // LIZv1 emitter state (kBig)
     if (b1 - b0 < kMinInputForLz) goto last_literals;
     {
         const u32 mflimit = b1 - kMfLimit;
@@ -435,6 +440,8 @@ template <class W, class TT> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u3
                 u32 j0 = 0;
                 u64 v_ahead = 0; bool have_ahead = false;                      // next batch's bytes, requested one batch early
                 for (;;) {
+                  u32 j_hit = 0;
+                  for (;;) {
                     const u32 j = j0 + lane;
                     const u32 P = ip0 + probe_offset(j);
                     const bool valid = ip0 + probe_offset(j + 1) <= mflimit;   // else this probe ends the block
@@ -473,16 +480,23 @@ template <class W, class TT> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u3
                         if (highbit32(grp) == lane) T.set_t(h, cur, tag8((u32)v));
                     }
                     W::sync();
-                    if (matched) { ip = W::shfl(P, w_lane); mpos = W::shfl(cand, w_lane) - bias; break; }
+                    if (matched) { ip = W::shfl(P, w_lane); mpos = W::shfl(cand, w_lane) - bias; j_hit = j0 + w_lane; break; }
                     if (t_lane < 32) { goto last_literals; }
                     j0 += NL;
+                  }
+                  ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
+                  const u32 back = extend_back_par<W>(src, ip, mpos, anchor);
+                  if (kBig && ml + back < kMmLongOff && ip - mpos >= kMax16BitOffset) {   // refused: the search goes on behind it
+                      j0 = j_hit + 1; have_ahead = false;
+                      continue;
+                  }
+                  ip -= back; mpos -= back; ml += back;
+                  break;
                 }
-                ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
-                const u32 back = extend_back_par<W>(src, ip, mpos, anchor);
-                ip -= back; mpos -= back; ml += back;
             }
             for (;;) {   // _next_match
-                emit_lz4<W>(s, src, anchor, ip, ml + kMinMatch, ip - mpos);
+                if (kBig) emit_lizv1<W>(s, src, anchor, ip, ml + kMinMatch, ip - mpos, last_off);
+                else emit_lz4<W>(s, src, anchor, ip, ml + kMinMatch, ip - mpos);
                 ip += ml + kMinMatch;
                 anchor = ip;
                 if (ip > mflimit) goto last_literals;
@@ -501,7 +515,7 @@ template <class W, class TT> LZ_HD void parse_fast_par(const ParseCtx<TT>& c, u3
                     mpos = cand - bias;
                     if (ld32(src + mpos) == (u32)v) {
                         ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
-                        continue;
+                        if (!kBig || ml >= kMmLongOff || ip - mpos < kMax16BitOffset) continue;
                     }
                 }
                 break;
@@ -530,7 +544,7 @@ last_literals:
 // When the walk leaves the window the committed lanes write their buckets (last writer per bucket wins).
 // Consecutive positions hold while a search has made at most 65 probes (probe_offset); a longer miss run falls
 // back to the batch search with its growing stride.
-template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u32 b0, u32 b1, EncStreams& st)
+template <class W, class TT, bool kBig = false> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u32 b0, u32 b1, EncStreams& st)
 {
     const u8* const src = c.src;
     const TT T = c.T;
@@ -541,6 +555,7 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
     const u32 low_limit = (bias + max_dist >= b0 + bias) ? bias : b0 + bias - max_dist;
     const u32 lt_mask = (1u << lane) - 1;
     u32 anchor = b0;
+    u32 last_off = 0;                                              // LIZv1 emitter state (kBig)
     if (b1 - b0 >= kMinInputForLz) {
         const u32 mflimit = b1 - kMfLimit;
         const u8* const matchlimit = src + b1 - kLastLiterals;
@@ -571,6 +586,7 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
             }
             // ---- replay the reference's walk over the window ----
             u32 slow_ip0 = 0, slow_j0 = 0; bool go_slow = false, finished = false;
+            u32 refused = 0;                                       // kBig: lanes whose far candidate was too short -- plain misses
             for (;;) {
                 const u32 ge_s = ~((1u << s) - 1);
                 const u32 m = below & (committed | ge_s);
@@ -579,21 +595,23 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
                 bool hit = m ? (pv == (u32)v && lane - pl >= kMinOffset) : hit_t;
                 const u32 a = s + (has_next ? 1u : 0u);            // first lane acting as a search probe
                 hit = hit && lane >= s && (s_valid || (has_next && lane == s));
+                if (kBig) hit = hit && !((refused >> lane) & 1u);
                 const u32 hits = W::ballot(hit);
                 const u32 term = W::ballot(lane >= a && !s_valid);
                 const u32 w_lane = hits ? ctz32(hits) : 32;
                 const u32 t_lane = term ? ctz32(term) : 32;
                 if (w_lane < t_lane) {
-                    committed |= ge_s & (w_lane >= 31 ? 0xffffffffu : ((2u << w_lane) - 1));
                     const u32 cpos = m ? w0 + pl : tv - bias;
                     u32 ip = w0 + w_lane;
                     u32 mpos = W::shfl(cpos, w_lane);
                     u32 ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
-                    if (!(has_next && w_lane == s)) {               // the post-match probe is taken as it is
-                        const u32 back = extend_back_par<W>(src, ip, mpos, anchor);
-                        ip -= back; mpos -= back; ml += back;
-                    }
-                    emit_lz4<W>(st, src, anchor, ip, ml + kMinMatch, ip - mpos);
+                    u32 back = 0;
+                    if (!(has_next && w_lane == s)) back = extend_back_par<W>(src, ip, mpos, anchor);   // the post-match probe is taken as it is
+                    if (kBig && ml + back < kMmLongOff && ip - mpos >= kMax16BitOffset) { refused |= 1u << w_lane; continue; }
+                    committed |= ge_s & (w_lane >= 31 ? 0xffffffffu : ((2u << w_lane) - 1));
+                    ip -= back; mpos -= back; ml += back;
+                    if (kBig) emit_lizv1<W>(st, src, anchor, ip, ml + kMinMatch, ip - mpos, last_off);
+                    else emit_lz4<W>(st, src, anchor, ip, ml + kMinMatch, ip - mpos);
                     ip += ml + kMinMatch;
                     anchor = ip;
                     if (ip > mflimit) { finished = true; break; }
@@ -623,8 +641,10 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
             {
                 const u32 ip0 = slow_ip0;
                 u32 j0 = slow_j0;
-                u32 ip = 0, mpos = 0; bool ended = false;
+                u32 ip = 0, mpos = 0, ml = 0; bool ended = false;
                 for (;;) {
+                  u32 j_hit = 0;
+                  for (;;) {
                     const u32 j = j0 + lane;
                     const u32 Pj = ip0 + probe_offset(j);
                     const bool valid = ip0 + probe_offset(j + 1) <= mflimit;
@@ -658,15 +678,20 @@ template <class W, class TT> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u3
                         if (highbit32(grp) == lane) T.set_t(hj, cur, tag8((u32)vj));
                     }
                     W::sync();
-                    if (matched) { ip = W::shfl(Pj, w_lane); mpos = W::shfl(cand, w_lane) - bias; break; }
+                    if (matched) { ip = W::shfl(Pj, w_lane); mpos = W::shfl(cand, w_lane) - bias; j_hit = j0 + w_lane; break; }
                     if (t_lane < 32) { ended = true; break; }
                     j0 += NL;
+                  }
+                  if (ended) break;
+                  ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
+                  const u32 back = extend_back_par<W>(src, ip, mpos, anchor);
+                  if (kBig && ml + back < kMmLongOff && ip - mpos >= kMax16BitOffset) { j0 = j_hit + 1; continue; }   // refused
+                  ip -= back; mpos -= back; ml += back;
+                  break;
                 }
                 if (ended) break;
-                u32 ml = count_match_par<W>(src + ip + kMinMatch, src + mpos + kMinMatch, matchlimit);
-                const u32 back = extend_back_par<W>(src, ip, mpos, anchor);
-                ip -= back; mpos -= back; ml += back;
-                emit_lz4<W>(st, src, anchor, ip, ml + kMinMatch, ip - mpos);
+                if (kBig) emit_lizv1<W>(st, src, anchor, ip, ml + kMinMatch, ip - mpos, last_off);
+                else emit_lz4<W>(st, src, anchor, ip, ml + kMinMatch, ip - mpos);
                 ip += ml + kMinMatch;
                 anchor = ip;
                 if (ip > mflimit) break;
@@ -1231,6 +1256,10 @@ template <class W, class TT> LZ_HD int encode_unit_t(const u8* src, u32 src_size
         s.nl = s.nf = s.n16 = s.n24 = 0; s.tail_anchor = pos; s.tail_len = 0;
         if (lp.parser == kParserHashChain) parse_hash_chain<W, TT>(pc, pos, pos + part, s, cs);
         else if (lp.parser == kParserPriceFast) parse_price_fast_par<W, TT>(pc, pos, pos + part, s, lp.minMatchLongOff);
+        else if (lp.parser == kParserFastBig) {
+            if (W::kLanes >= 4) parse_fast_win<W, TT, true>(pc, pos, pos + part, s);
+            else parse_fast_par<W, TT, true>(pc, pos, pos + part, s);
+        }
         else if (W::kLanes >= 4) parse_fast_win<W, TT>(pc, pos, pos + part, s);
         else parse_fast_par<W, TT>(pc, pos, pos + part, s);
         W::sync();

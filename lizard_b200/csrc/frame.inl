@@ -94,7 +94,19 @@ inline u64 rd_le64h(const u8* p) { u64 v = 0; for (int i = 0; i < 8; ++i) v |= (
 // which the host copies that chunk back on a third stream.  H2D, kernels and D2H overlap.  The compressor's
 // block records are packed by the encode kernel itself (FramePack, encode.cuh): a separate pack kernel could
 // not become resident while the persistent encode grid holds every SM's registers.
-constexpr size_t kFrameChunkBytes = 32u << 20;
+// Chunk size of the host pipeline.  A call's last chunk can only be processed after its last byte has crossed the link, so
+// the call ends one chunk's worth of kernel latency after the H2D does: smaller chunks shorten that tail (and let the first
+// D2H start earlier) at the price of more copy calls.  LIZARDB200_FRAME_CHUNK_MIB overrides (diagnostics / sweeps).
+inline size_t frame_chunk_bytes()
+{
+    static const size_t v = [] {
+        size_t mib = 8;
+        if (const char* e = getenv("LIZARDB200_FRAME_CHUNK_MIB")) { const long t = atol(e); if (t >= 1 && t <= 1024) mib = (size_t)t; }
+        return mib << 20;
+    }();
+    return v;
+}
+#define kFrameChunkBytes frame_chunk_bytes()
 
 // LIZARDB200_TRACE=1: print a host-clock timeline of the pipelined frame paths to stderr (diagnostics only)
 struct Trace {
@@ -220,8 +232,43 @@ struct FrameBlockRef { size_t src_pos; u32 csize; size_t dst_pos; };
 
 // Decode `blocks` (compressed independent blocks inside src, ascending) into dst, each with capacity max_block.
 // sizes_out[i] = decoded size or negative.  Host pointers.
+// `hasher`: content checksum of the decoded blocks, in block order, computed on a helper thread chunk by chunk as the output
+// copies land (lib/lizard_frame.c:1159, 1264-1266 update it behind every block; XXH32 is a serial recurrence, so the only
+// way to take it off the critical path is to run it beside the copies and the kernel).  Null = the caller hashes.
+struct ChunkHasher {
+    Xxh32* x = nullptr; const std::vector<FrameBlockRef>* blocks = nullptr; const std::vector<int>* sizes = nullptr;
+    const u8* dst = nullptr; size_t per_chunk = 0, n = 0; int device = 0;
+    std::vector<cudaEvent_t> ev; std::atomic<size_t> recorded{0}; std::atomic<bool> stop{false}; std::thread th; bool on = false;
+    bool start(size_t nchunks)
+    {
+        ev.assign(nchunks, nullptr);
+        for (size_t k = 0; k < nchunks; ++k)
+            if (cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming) != cudaSuccess) { destroy(); return false; }
+        try { th = std::thread([this] { run(); }); on = true; } catch (...) { destroy(); on = false; }
+        return on;
+    }
+    void run()
+    {
+        cudaSetDevice(device);
+        for (size_t k = 0; k < ev.size(); ++k) {
+            while (recorded.load(std::memory_order_acquire) <= k) { if (stop.load()) return; std::this_thread::yield(); }
+            if (cudaEventSynchronize(ev[k]) != cudaSuccess) return;
+            const size_t first = k * per_chunk, last = (first + per_chunk < n ? first + per_chunk : n);
+            for (size_t i = first; i < last; ++i) {
+                const int sz = (*sizes)[i];
+                if (sz < 0) return;                                  // the caller reports the failure
+                x->update(dst + (*blocks)[i].dst_pos, (size_t)sz);
+            }
+        }
+    }
+    void landed(size_t k, cudaStream_t s) { cudaEventRecord(ev[k], s); recorded.store(k + 1, std::memory_order_release); }
+    void finish(bool ok) { if (!on) return; if (!ok) stop.store(true); th.join(); on = false; destroy(); }
+    void destroy() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); ev.clear(); }
+    ~ChunkHasher() { finish(false); }
+};
+
 int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::vector<FrameBlockRef>& blocks,
-                        u8* dst, size_t dst_span, u32 max_block, std::vector<int>& sizes_out)
+                        u8* dst, size_t dst_span, u32 max_block, std::vector<int>& sizes_out, Xxh32* hasher = nullptr)
 {
     const size_t n = blocks.size();
     sizes_out.assign(n, -1);
@@ -262,6 +309,11 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
         }
     }
     tr.mark("decode: kernel launched, H2D queued");
+    ChunkHasher ch;
+    if (hasher) {
+        ch.x = hasher; ch.blocks = &blocks; ch.sizes = &sizes_out; ch.dst = dst; ch.per_chunk = per_chunk; ch.n = n; ch.device = c.device;
+        if (!ch.start(nchunks)) hasher = nullptr;                    // no helper: hash here, after the copies
+    }
     bool failed = false;
     for (size_t k = 0; k < nchunks; ++k) {
         const size_t first = k * per_chunk, last = (k + 1 == nchunks ? n : first + per_chunk) - 1;
@@ -271,10 +323,17 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
         size_t lo = blocks[first].dst_pos, hi = lo;
         for (size_t i = first; i <= last; ++i) { sizes_out[i] = t_res[i]; if (t_res[i] > 0) hi = blocks[i].dst_pos + (size_t)t_res[i]; }
         if (hi > lo) cudaMemcpyAsync(dst + lo, (u8*)c.d_out.p + lo, hi - lo, cudaMemcpyDeviceToHost, c.s_out);
+        if (ch.on) ch.landed(k, c.s_out);
     }
     cudaError_t e1 = cudaStreamSynchronize(c.s_out), e2 = cudaStreamSynchronize(c.stream), e3 = cudaStreamSynchronize(c.s_in);
     tr.mark("decode: all streams idle");
-    if (failed || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return -1;
+    const bool ok = !(failed || e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess);
+    const bool hashed = ch.on;
+    ch.finish(ok);
+    tr.mark("decode: checksum thread joined");
+    if (!ok) return -1;
+    if (hasher && !hashed)
+        for (size_t i = 0; i < n; ++i) if (sizes_out[i] > 0) hasher->update(dst + blocks[i].dst_pos, (size_t)sizes_out[i]);
     return 0;
 }
 
@@ -351,7 +410,7 @@ size_t LizardF_createCompressionContext(LizardF_compressionContext_t* out, unsig
 size_t LizardF_freeCompressionContext(LizardF_compressionContext_t c) { delete c; return 0; }
 
 size_t LizardF_compressBegin(LizardF_compressionContext_t c, void* dstBuffer, size_t dstMax, const LizardF_preferences_t* prefsPtr)
-{   // lib/lizard_frame.c:363-429
+try {   // lib/lizard_frame.c:363-429
     u8* const d0 = (u8*)dstBuffer; u8* d = d0;
     if (dstMax < kMaxFH) return ferr(FE_dstMaxSize_tooSmall);
     if (c->stage != 0) return ferr(FE_GENERIC);
@@ -376,7 +435,7 @@ size_t LizardF_compressBegin(LizardF_compressionContext_t c, void* dstBuffer, si
     *d = (u8)(xxh32(hs, (size_t)(d - hs), 0) >> 8); d++;
     c->stage = 1;
     return (size_t)(d - d0);
-}
+} catch (const std::bad_alloc&) { return ferr(FE_allocation_failed); } catch (...) { return ferr(FE_GENERIC); }
 
 static size_t frame_flush_tmp(LizardF_cctx_s* c, u8* dst, size_t cap)
 {
@@ -392,7 +451,7 @@ static size_t frame_flush_tmp(LizardF_cctx_s* c, u8* dst, size_t cap)
 
 size_t LizardF_compressUpdate(LizardF_compressionContext_t c, void* dstBuffer, size_t dstMax, const void* srcBuffer, size_t srcSize,
                               const LizardF_compressOptions_t*)
-{   // lib/lizard_frame.c:501-590 (independent blocks)
+try {   // lib/lizard_frame.c:501-590 (independent blocks)
     if (c->stage != 1) return ferr(FE_GENERIC);
     if (dstMax < LizardF_compressBound(srcSize, &c->prefs)) return ferr(FE_dstMaxSize_tooSmall);
     Context& g = *frame_context();
@@ -431,10 +490,10 @@ size_t LizardF_compressUpdate(LizardF_compressionContext_t c, void* dstBuffer, s
     if (want_hash) { if (hash_job.running()) hash_job.join(); else c->xxh.update(srcBuffer, srcSize); }
     c->total_in += srcSize;
     return (size_t)(d - d0);
-}
+} catch (const std::bad_alloc&) { return ferr(FE_allocation_failed); } catch (...) { return ferr(FE_GENERIC); }
 
 size_t LizardF_flush(LizardF_compressionContext_t c, void* dstBuffer, size_t dstMax, const LizardF_compressOptions_t*)
-{   // lib/lizard_frame.c:601-629
+try {   // lib/lizard_frame.c:601-629
     if (c->tmp.empty()) return 0;
     if (c->stage != 1) return ferr(FE_GENERIC);
     if (dstMax < c->tmp.size() + 8) return ferr(FE_dstMaxSize_tooSmall);
@@ -442,10 +501,10 @@ size_t LizardF_flush(LizardF_compressionContext_t c, void* dstBuffer, size_t dst
     std::lock_guard<std::mutex> lock(g.mu);
     if (ensure_context(g, g_device) != LIZARDB200_OK) return ferr(FE_GENERIC);
     return frame_flush_tmp(c, (u8*)dstBuffer, dstMax);
-}
+} catch (const std::bad_alloc&) { return ferr(FE_allocation_failed); } catch (...) { return ferr(FE_GENERIC); }
 
 size_t LizardF_compressEnd(LizardF_compressionContext_t c, void* dstBuffer, size_t dstMax, const LizardF_compressOptions_t* o)
-{   // lib/lizard_frame.c:641-670
+try {   // lib/lizard_frame.c:641-670
     u8* const d0 = (u8*)dstBuffer; u8* d = d0;
     size_t r = LizardF_flush(c, dstBuffer, dstMax, o);
     if (LizardF_isError(r)) return r;
@@ -455,10 +514,10 @@ size_t LizardF_compressEnd(LizardF_compressionContext_t c, void* dstBuffer, size
     c->stage = 0;
     if (c->prefs.frameInfo.contentSize && c->prefs.frameInfo.contentSize != c->total_in) return ferr(FE_frameSize_wrong);
     return (size_t)(d - d0);
-}
+} catch (const std::bad_alloc&) { return ferr(FE_allocation_failed); } catch (...) { return ferr(FE_GENERIC); }
 
 size_t LizardF_compressFrame(void* dstBuffer, size_t dstMax, const void* srcBuffer, size_t srcSize, const LizardF_preferences_t* prefsPtr)
-{   // lib/lizard_frame.c:260-312
+try {   // lib/lizard_frame.c:260-312
     LizardF_cctx_s ctx;
     memset(&ctx.prefs, 0, sizeof ctx.prefs);
     ctx.version = LIZARDF_VERSION; ctx.stage = 0; ctx.block_size = 0; ctx.total_in = 0;
@@ -480,7 +539,7 @@ size_t LizardF_compressFrame(void* dstBuffer, size_t dstMax, const void* srcBuff
     if (LizardF_isError(r)) return r;
     d += r;
     return (size_t)(d - d0);
-}
+} catch (const std::bad_alloc&) { return ferr(FE_allocation_failed); } catch (...) { return ferr(FE_GENERIC); }
 
 // ---------------------------------------------------------------------------------------------------------
 size_t LizardF_createDecompressionContext(LizardF_decompressionContext_t* out, unsigned version)
@@ -546,7 +605,7 @@ static size_t frame_decode_header(LizardF_dctx_s* d, const u8* p, size_t n)
 
 size_t LizardF_decompress(LizardF_decompressionContext_t d, void* dstBuffer, size_t* dstSizePtr,
                           const void* srcBuffer, size_t* srcSizePtr, const LizardF_decompressOptions_t*)
-{   // lib/lizard_frame.c:980-1320, independent blocks; whole runs of complete blocks are decoded in one launch
+try {   // lib/lizard_frame.c:980-1320, independent blocks; whole runs of complete blocks are decoded in one launch
     const u8* const s0 = (const u8*)srcBuffer; const u8* const se = s0 + *srcSizePtr; const u8* sp = s0;
     u8* const d0 = (u8*)dstBuffer; u8* const de = d0 + *dstSizePtr; u8* dp = d0;
     const u8* sel = nullptr;
@@ -645,14 +704,17 @@ size_t LizardF_decompress(LizardF_decompressionContext_t d, void* dstBuffer, siz
             const size_t span = (size_t)(scan - span_begin);
             const size_t out_span = blocks.size() * d->max_block;
             (void)stage_buf;
-            if (frame_decode_blocks(g, span_begin, span, blocks, dp, out_span, (u32)d->max_block, sz) != 0) return ferr(FE_GENERIC);
+            // the content checksum of a large batch is computed beside the copies (frame_decode_blocks: ChunkHasher)
+            const bool hash_beside = d->info.contentChecksumFlag && out_span >= kHashThreadMin;
+            if (frame_decode_blocks(g, span_begin, span, blocks, dp, out_span, (u32)d->max_block, sz, hash_beside ? &d->xxh : nullptr) != 0)
+                return ferr(FE_GENERIC);
             // full blocks land exactly in place; a short block (the last of a frame) only shifts what follows it
             u8* w = dp;
             for (size_t i = 0; i < blocks.size(); ++i) {
                 if (sz[i] < 0) return ferr(FE_GENERIC);
                 u8* from = dp + blocks[i].dst_pos;
                 if (from != w) memmove(w, from, (size_t)sz[i]);
-                if (d->info.contentChecksumFlag) d->xxh.update(w, (size_t)sz[i]);
+                if (d->info.contentChecksumFlag && !hash_beside) d->xxh.update(w, (size_t)sz[i]);
                 if (d->info.contentSize) d->remaining -= (u64)sz[i];
                 w += sz[i];
             }
@@ -733,10 +795,10 @@ size_t LizardF_decompress(LizardF_decompressionContext_t d, void* dstBuffer, siz
     *srcSizePtr = (size_t)(sp - s0);
     *dstSizePtr = (size_t)(dp - d0);
     return hint;
-}
+} catch (const std::bad_alloc&) { return ferr(FE_allocation_failed); } catch (...) { return ferr(FE_GENERIC); }
 
 size_t LizardF_getFrameInfo(LizardF_decompressionContext_t d, LizardF_frameInfo_t* info, const void* srcBuffer, size_t* srcSizePtr)
-{   // lib/lizard_frame.c:870-893
+try {   // lib/lizard_frame.c:870-893
     if (d->stage > DS_storeHeader) {
         size_t o = 0, i = 0;
         *srcSizePtr = 0; *info = d->info;
@@ -755,6 +817,6 @@ size_t LizardF_getFrameInfo(LizardF_decompressionContext_t d, LizardF_frameInfo_
     if (d->stage <= DS_storeHeader) return ferr(FE_frameHeader_incomplete);
     *info = d->info;
     return next;
-}
+} catch (const std::bad_alloc&) { return ferr(FE_allocation_failed); } catch (...) { return ferr(FE_GENERIC); }
 
 }  // extern "C"

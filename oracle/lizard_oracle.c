@@ -7,7 +7,7 @@
  *   o_fse_*                                lib/entropy/fse_decompress.c, fse_compress.c, entropy_common.c
  *   o_decode_lz4 / o_decode_lizv1          lib/lizard_decompress_lz4.h:7-163, lizard_decompress_liz.h:14-220
  *   oracle_Lizard_decompress_safe          lib/lizard_decompress.c:115-270
- *   o_parse_fast                           lib/lizard_parser_fastsmall.h:34-189, lizard_parser_fast.h:41-196
+ *   o_parse_fast                           lib/lizard_parser_fastsmall.h:34-189, lizard_parser_fast.h:41-196, lizard_parser_fastbig.h:35-175
  *   o_parse_pricefast                      lib/lizard_parser_pricefast.h:3-249
  *   o_emit_lz4 / o_emit_lizv1              lib/lizard_compress_lz4.h:3-86, lizard_compress_liz.h:43-179
  *   o_write_block / oracle_Lizard_compress lib/lizard_compress.c:141-250, 472-606
@@ -745,7 +745,7 @@ size_t oracle_HUF_compress(void* dstv, size_t cap, const void* srcv, size_t n)
 /* =====================================================================================================
  * Block encoder
  * =================================================================================================== */
-typedef struct { int window_log, hash_log, pricefast, lizv1, huffman; u32 mm_long; int chain_log, search_num, search_len; } o_level;
+typedef struct { int window_log, hash_log, pricefast, fastbig, lizv1, huffman; u32 mm_long; int chain_log, search_num, search_len; } o_level;
 
 static int o_level_get(int level, o_level* L)
 {   /* lib/lizard_common.h:234-284, rows on the hot path */
@@ -759,6 +759,7 @@ static int o_level_get(int level, o_level* L)
         static const int snum[5] = { 2, 4, 8, 16, 256 }, slen[5] = { 5, 5, 5, 4, 4 };
         L->window_log = 16; L->hash_log = 18; L->chain_log = 16; L->search_num = snum[b - 13]; L->search_len = slen[b - 13];
         return 1; }
+    case 20: L->window_log = 22; L->hash_log = 14; L->fastbig = 1; L->lizv1 = 1; L->mm_long = 16; return 1;   /* fastBig */
     case 21: L->window_log = 22; L->hash_log = 14; L->pricefast = 1; L->lizv1 = 1; L->mm_long = 16; return 1;
     case 22: L->window_log = 22; L->hash_log = 18; L->pricefast = 1; L->lizv1 = 1; L->mm_long = 16; return 1;
     default: return 0;
@@ -824,9 +825,13 @@ static void o_emit_lizv1(o_enc* e, const u8** ip, const u8** anchor, size_t ml, 
     *ip += ml; *anchor = *ip;
 }
 
-/* lib/lizard_parser_fastsmall.h:34-189 == lizard_parser_fast.h:41-196 (noDict path) */
+/* lib/lizard_parser_fastsmall.h:34-189 == lizard_parser_fast.h:41-196 (noDict path); with L.fastbig also
+ * lib/lizard_parser_fastbig.h:35-175 (levels 20 / 40): LIZv1 codewords, and a candidate 65536 or more bytes back is only
+ * taken when the match is at least MM_LONGOFF long beyond MINMATCH (:99 with the backward extension counted, :142 without) --
+ * a refused candidate is a plain miss, the search goes on */
 static void o_parse_fast(o_enc* e, const u8* ip, const u8* const iend)
 {
+    const int big = e->L.fastbig;
     const u8* const base = e->base - O_BIAS;     /* indices are relative to this virtual base */
     const u8* const low_prefix = e->base;
     const u8* const mflimit = iend - 20; const u8* const matchlimit = iend - 16; const u8* anchor = ip;
@@ -847,18 +852,24 @@ static void o_parse_fast(o_enc* e, const u8* ip, const u8* const iend)
                 match = base + idx;
                 if ((u32)(ip - match) < 8 || rd32(match) != rd32(ip)) continue;
                 ml = o_count(ip + 4, match + 4, matchlimit);
-                while (ip > anchor && match > low_prefix && ip[-1] == match[-1]) { ip--; match--; ml++; }
+                {   const u8* bi = ip; const u8* bm = match; size_t bl = ml;
+                    while (bi > anchor && bm > low_prefix && bi[-1] == bm[-1]) { bi--; bm--; bl++; }
+                    if (big && bl < 16 && (u32)(ip - match) >= 65536) continue;
+                    ip = bi; match = bm; ml = bl; }
                 break;
             } }
         for (;;) {
             u32 h, idx;
-            o_emit_lz4(e, &ip, &anchor, ml + 4, match);
+            if (big) o_emit_lizv1(e, &ip, &anchor, ml + 4, match); else o_emit_lz4(e, &ip, &anchor, ml + 4, match);
             if (ip > mflimit) goto tail;
             T[o_hash(ip - 2, hl)] = (u32)(ip - 2 - base);
             h = o_hash(ip, hl); idx = T[h]; T[h] = (u32)(ip - base);
             if (idx >= low && idx < (u32)(ip - base) && base + idx + maxd >= ip) {
                 match = base + idx;
-                if ((u32)(ip - match) >= 8 && rd32(match) == rd32(ip)) { ml = o_count(ip + 4, match + 4, matchlimit); continue; }
+                if ((u32)(ip - match) >= 8 && rd32(match) == rd32(ip)) {
+                    ml = o_count(ip + 4, match + 4, matchlimit);
+                    if (!big || ml >= 16 || (u32)(ip - match) < 65536) continue;
+                }
             }
             break;
         }

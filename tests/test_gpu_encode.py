@@ -10,7 +10,7 @@ from tests import refs
 
 pytestmark = pytest.mark.gpu
 BS = lz.BLOCK_SIZE
-LEVELS = [10, 11, 13, 15, 17, 21, 22, 30, 31, 34, 38, 41, 42]
+LEVELS = [10, 11, 13, 15, 17, 20, 21, 22, 30, 31, 34, 38, 40, 41, 42]
 
 
 @pytest.fixture(scope="module")

@@ -14,7 +14,7 @@ import lizard_b200 as lz
 from tests import refs
 
 BS = lz.BLOCK_SIZE
-LEVELS = [10, 11, 13, 16, 21, 22, 30, 31, 34, 41, 42]      # fastSmall, fast, hashChain (13-17/34-38), priceFast
+LEVELS = [10, 11, 13, 16, 20, 21, 22, 30, 31, 34, 40, 41, 42]      # fastSmall, fast, hashChain (13-17/34-38), fastBig, priceFast
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
@@ -93,6 +93,21 @@ def o_decompress(L, comp, cap):
 
 def lz_bound(n):
     return n + 2 + (n // BS + 1) * 4
+
+
+def far_match_input(seed=3, n=BS):
+    """Matches 65536 or more bytes back, short and long: exercises the LIZv1 parsers' rule that a far candidate is only taken
+    when the match is at least MM_LONGOFF + MINMATCH long (lizard_parser_fastbig.h:99,142; lizard_parser_pricefast.h:69) and
+    the 24-bit-offset codewords."""
+    rnd = random.Random(seed)
+    head = bytes(rnd.randrange(256) for _ in range(70000))
+    out = bytearray(head)
+    while len(out) < n:
+        k = rnd.choice([5, 8, 12, 17, 19, 20, 21, 24, 40, 100])
+        at = rnd.randrange(0, 4000)                      # source near the start: offsets >= 65536
+        out += head[at:at + k]
+        out += bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 30)))
+    return bytes(out[:n])
 
 
 def _inputs(seed, count):
@@ -219,7 +234,29 @@ def test_warp_emulated_device_path_bit_exact(ref, shim, level):
         assert emu_compress(shim, d, level, cap) == refs.ref_compress(ref, d, level, cap), (level, len(d), cap)
 
 
-@pytest.mark.parametrize("level", [10, 30, 21, 41, 22])
+@pytest.mark.parametrize("level", [20, 40, 21, 41, 22])
+def test_far_matches_bit_exact(ref, oracle, shim, level):
+    """LIZv1 levels on input whose matches lie 65536 or more bytes back, shorter and longer than MM_LONGOFF + MINMATCH: the
+    far-candidate rule of fastBig / priceFast and the 24-bit-offset codewords; oracle, one lane, 32 emulated lanes, packed and
+    plain (tagged) table, a two-inner-block unit."""
+    for seed, n in ((3, BS), (4, BS), (5, 100000), (6, BS + 50000)):
+        data = far_match_input(seed, n)
+        want = refs.ref_compress(ref, data, level)
+        assert 0 < len(want) < len(data)
+        assert o_compress(oracle, data, level) == want, (level, seed)
+        assert shim_compress(shim, data, level) == want, (level, seed)
+        assert emu_compress(shim, data, level) == want, (level, seed)
+        shim.lzb_force_plain_table(1)
+        try:
+            assert shim_compress(shim, data, level) == want, (level, seed)
+            assert emu_compress(shim, data, level) == want, (level, seed)
+        finally:
+            shim.lzb_force_plain_table(0)
+        r, out = o_decompress(oracle, want, len(data))
+        assert r == len(data) and out == data
+
+
+@pytest.mark.parametrize("level", [10, 30, 21, 41, 22, 20])
 def test_plain_table_with_entry_tags_bit_exact(ref, shim, level):
     """On the device the warps of a CTA that have no shared-memory table run these levels on the plain 32-bit table,
     whose entries carry a 7-bit candidate tag while every position of the unit is below 2^17.  Same bytes as the
