@@ -161,7 +161,11 @@ template <class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* 
             b.used &= 7;
             b.win = ld64_any(b.ptr);
 #if defined(__CUDA_ARCH__)
-            if (b.ptr >= b.start + 384 && ((size_t)b.ptr & 127) < 6) asm volatile("prefetch.global.L1 [%0];" :: "l"(b.ptr - 384));
+#if !defined(LZB_HUF_PREFETCH)
+#define LZB_HUF_PREFETCH 384
+#endif
+            if (LZB_HUF_PREFETCH && b.ptr >= b.start + LZB_HUF_PREFETCH && ((size_t)b.ptr & 127) < 6)
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(b.ptr - LZB_HUF_PREFETCH));
             // four table steps on a 2 x 32-bit copy of the window kept left-aligned (<= 7 + 4*12 bits leave it)
             u32 hi = (u32)(b.win >> 32), lo = (u32)b.win;
             hi = __funnelshift_l(lo, hi, b.used); lo <<= b.used;

@@ -246,6 +246,9 @@ inline EncodeShape encode_shape(const LevelParams& lp)
     for (int ctas = kEncMaxWarpsPerSM; ctas >= 1; --ctas) if (tabs_for(1, ctas, sm_max) >= (sh.table_bytes ? 1 : 0)) { solo = ctas; break; }
     if (!sh.table_bytes || fit14 >= 8) set(kEncWarpsPerCta, tabs14 < 0 ? 0 : tabs14, kEncCtasPerSM);
     else if (solo >= 16) set(1, 1, solo);
+    // large tables next to the entropy stage's histograms (levels 40-42): the one table that would still fit costs the other
+    // thirteen warps more L1 than it saves (B200, 1 GiB, level 41: 14,0,2 36.5 ms, 14,1,2 38.8 ms; profiles/r02_SUMMARY.md)
+    else if (tabs14 >= 0 && sh.hist_bytes && sh.table_bytes >= 32 * 1024) set(kEncWarpsPerCta, 0, kEncCtasPerSM);
     else if (tabs14 >= 0) set(kEncWarpsPerCta, tabs14, kEncCtasPerSM);
     else set(1, 1, solo >= 1 ? solo : 1);
     return best;

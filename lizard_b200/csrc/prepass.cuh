@@ -20,7 +20,10 @@ struct PrepassBatch {
 // warps per CTA, jobs per warp round.  One CTA per SM: 1 GiB of 128 KiB blocks is 32768 literals segments = 1024 warps,
 // 7 x 148 warps take them in a single wave; 7 x 8 two-level tables are 130 KB, the rest of the SM's 256 KB stays L1 for
 // the 224 bitstreams read at once.
-enum : u32 { kExpWarps = 7, kExpJobs = 8, kExpCtasMax = 1 };   // a second CTA per SM (with 9- or 8-bit first-level tables so that two fit) was slower:
+#if !defined(LZB_EXP_CTAS_MAX)
+#define LZB_EXP_CTAS_MAX 1
+#endif
+enum : u32 { kExpWarps = 7, kExpJobs = 8, kExpCtasMax = LZB_EXP_CTAS_MAX };   // a second CTA per SM (with 9- or 8-bit first-level tables so that two fit) was slower:
                                                       // 448 bitstreams no longer fit the L1 left beside the tables (profiles/r02_SUMMARY.md)
 
 struct ExpWarpShared {
