@@ -14,8 +14,8 @@
  *        lib/lizard_decompress.h:73  Lizard_decompress_safe   lib/lizard_decompress.c:267-270
  *      Compression output is byte-identical to the reference built with -DLIZARD_RESET_MEM
  *      (hash table empty at the start of every call), for the levels whose parsers are implemented on
- *      the GPU: 10, 11, 30, 31 (fastSmall / fast), 13-17, 34-38 (hashChain) and 21, 22, 41, 42 (priceFast).  Any other level
- *      makes the compress entry points return 0 ("failed"), never a CPU fallback.
+ *      the GPU: 10, 11, 30, 31 (fastSmall / fast), 13-17, 34-38 (hashChain), 20, 40 (fastBig) and 21, 22, 41, 42 (priceFast).
+ *      Any other level makes the compress entry points return 0 ("failed"), never a CPU fallback.
  *      Decompression accepts every level 10..49 (the block format only has two codeword flavours).
  *
  *  (2) BATCH symbols (LizardB200_*): what the reference's per-block loops
@@ -203,8 +203,10 @@ int LizardB200_encodeShape(int compressionLevel, int* warpsPerCta, int* smemTabl
 /* number of kernel launches issued by this library since load (bench.py reports it as gpu_launches) */
 unsigned long long LizardB200_launchCount(void);
 /* diagnostics: how this thread's device decodes, four bits: 1 = pooled copy sweeps, 2 = compact length-extension chain,
- * 4 = Huffman pre-pass kernels, 8 = token pre-pass kernel ahead of the token kernel (default 7).  Results are identical
- * for every value; tools/dec_bench.py times them against each other. */
+ * 4 = Huffman pre-pass kernels, 8 = token pre-pass kernel ahead of the token kernel, 16 = second-generation kernel (one CTA
+ * per unit: a parser warp and a copier warp, literals stream staged through shared memory by TMA bulk copies; slower than the
+ * first generation on the B200 so far, see profiles/r02_SUMMARY.md).  Default 7.  Results are identical for every value;
+ * tools/dec_bench.py times them against each other. */
 int LizardB200_setDecodeVariant(int variant);
 
 #if defined(__cplusplus)

@@ -661,6 +661,9 @@ int LizardB200_compress_blocks(const void* src, size_t srcSize, int blockSize,
     }
     cudaStream_t s = c.stream;
     u8* dtab = (u8*)c.d_tab.p;
+    // the whole strided region is copied back: what the units do not write (the slack behind each compressed block) must
+    // not be bytes of an earlier call
+    CU_OK(cudaMemsetAsync(c.d_out.p, 0, n * dstStride, s));
     CU_OK(cudaMemcpyAsync(c.d_in.p, src, srcSize, cudaMemcpyHostToDevice, s));
     CU_OK(cudaMemcpyAsync(dtab, c.pin_tab.p, tab_bytes - n * 4, cudaMemcpyHostToDevice, s));
     const u64* d_in_off = (const u64*)dtab; const u64* d_out_off = d_in_off + n;
@@ -698,6 +701,7 @@ int LizardB200_decompress_blocks(const void* src, size_t srcStride, const int* c
     }
     cudaStream_t s = c.stream;
     u8* dtab = (u8*)c.d_tab.p;
+    CU_OK(cudaMemsetAsync(c.d_out.p, 0, n * (size_t)blockSize, s));      // short or failed units leave gaps: zeros, not stale data
     CU_OK(cudaMemcpyAsync(c.d_in.p, src, n * srcStride, cudaMemcpyHostToDevice, s));
     CU_OK(cudaMemcpyAsync(dtab, c.pin_tab.p, tab_bytes - n * 4, cudaMemcpyHostToDevice, s));
     const u64* d_in_off = (const u64*)dtab; const u64* d_out_off = d_in_off + n;
