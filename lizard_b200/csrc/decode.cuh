@@ -156,7 +156,10 @@ template <class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* 
             if (bits_reload(b) != kBitsUnfinished) break;
             out[p++] = (u8)huf_step(b, tab);
         }
-        while (p + 4 <= count && b.ptr >= b.start + 16 && b.used <= 64 && ((size_t)(out + p) & 3) == 0) {
+        for (int phase = 0; phase < 2; ++phase) {        // 0: four-byte rounds up to a 16-byte boundary of the output, then the
+                                                         //    sixteen-byte rounds; 1: four-byte rounds for what is left
+        while (p + 4 <= count && b.ptr >= b.start + 16 && b.used <= 64 && ((size_t)(out + p) & 3) == 0 &&
+               (phase == 1 || ((size_t)(out + p) & 15) != 0)) {
             b.ptr -= b.used >> 3;                          // bits_reload, "ptr >= start + 8" case
             b.used &= 7;
             b.win = ld64_any(b.ptr);
@@ -184,6 +187,66 @@ template <class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* 
             *reinterpret_cast<u32*>(out + p) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
 #endif
             p += 4;
+        }
+        if (phase == 0) {
+#if defined(__CUDA_ARCH__)
+        // sixteen symbols per round, stored as ONE 16-byte vector: the 32 lanes of a warp write 32 different streams, so every
+        // store instruction costs the memory pipe 32 line accesses whatever its width -- a quarter of the stores of the
+        // four-byte form below.  Same walk: four times (reload, four symbols).
+        {
+        // The bitstream is read backwards, ~3 bytes per round: the two aligned 16-byte vectors around the read position stay
+        // in registers (c0 at `wa`, c1 at wa + 16) and a new one is fetched only when the position crosses wa -- one 16-byte
+        // load per ~5 rounds instead of two 8-byte loads per round (again: 32 lanes = 32 streams = 32 line accesses per load
+        // instruction).  A vector is only fetched when it holds at least one byte of the stream.
+        const u8* wa = nullptr;
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+        const u8* const s_end = b.start + len;
+        while (p + 16 <= count && ((size_t)(out + p) & 15) == 0) {
+            u32 w4[4] = {0, 0, 0, 0};
+            int r = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (r == q && b.ptr >= b.start + 16 && b.used <= 64) {
+                    b.ptr -= b.used >> 3;
+                    b.used &= 7;
+                    const u8* const g = (const u8*)((size_t)b.ptr & ~(size_t)15);
+                    if (g != wa) {
+                        if (wa != nullptr && g + 16 == wa) c1 = c0;
+                        else c1 = (g + 16 < s_end) ? *reinterpret_cast<const uint4*>(g + 16) : make_uint4(0, 0, 0, 0);
+                        c0 = *reinterpret_cast<const uint4*>(g);
+                        wa = g;
+                        if (LZB_HUF_PREFETCH && g >= b.start + LZB_HUF_PREFETCH && ((size_t)g & 127) == 0)
+                            asm volatile("prefetch.global.L1 [%0];" :: "l"(g - LZB_HUF_PREFETCH));
+                    }
+                    const u32 off = (u32)((size_t)b.ptr & 15), bs = (off & 3) * 8;
+                    const bool k2 = (off & 8) != 0, k1 = (off & 4) != 0;
+                    const u32 x0 = k2 ? c0.z : c0.x, x1 = k2 ? c0.w : c0.y, x2 = k2 ? c1.x : c0.z, x3 = k2 ? c1.y : c0.w;
+                    const u32 y0 = k1 ? x1 : x0, y1 = k1 ? x2 : x1, y2 = k1 ? x3 : x2;
+                    u32 lo = __funnelshift_r(y0, y1, bs), hi = __funnelshift_r(y1, y2, bs);     // the 8 bytes at b.ptr
+                    hi = __funnelshift_l(lo, hi, b.used); lo <<= b.used;
+                    u32 e = tab.look(hi), n = e >> 8, word = e & 255, used = b.used + n;
+                    hi = __funnelshift_l(lo, hi, n); lo <<= n;
+                    e = tab.look(hi); n = e >> 8; word |= (e & 255) << 8; used += n;
+                    hi = __funnelshift_l(lo, hi, n); lo <<= n;
+                    e = tab.look(hi); n = e >> 8; word |= (e & 255) << 16; used += n;
+                    hi = __funnelshift_l(lo, hi, n);
+                    e = tab.look(hi); word |= e << 24; used += e >> 8;
+                    b.used = used;
+                    w4[q] = word;
+                    r = q + 1;
+                }
+            }
+            if (r == 4) { *reinterpret_cast<uint4*>(out + p) = make_uint4(w4[0], w4[1], w4[2], w4[3]); p += 16; continue; }
+            // the walk reached the last 16 bytes of the bitstream inside this round: hand over what was decoded
+            if (r > 0) *reinterpret_cast<u32*>(out + p) = w4[0];
+            if (r > 1) *reinterpret_cast<u32*>(out + p + 4) = w4[1];
+            if (r > 2) *reinterpret_cast<u32*>(out + p + 8) = w4[2];
+            p += 4 * r;
+            break;
+        }
+        }
+#endif
+        }
         }
     }
     for (;;) {

@@ -292,67 +292,45 @@ struct HufFull {                 // the reference's layout: 1 << tableLog entrie
     const u16* t; u32 down;      // down = 32 - tableLog
     LZ_HDM u32 look(u32 hi) const { return t[hi >> down]; }
 };
-// Two-level form of the same table: 2.3 KiB instead of 4 KiB at tableLog 11 with the 10-bit first level used.  The pre-pass
-// keeps 56 tables per SM in shared memory; full tables would leave the L1 28 KB for the 224 bitstreams an SM reads at once.
-// HUF_readDTableX2 lays the symbols out by ascending weight, i.e. the longest codes sit at the lowest indices, and the
-// region of weight w starts at a multiple of 1 << (w-1) -- even 1 << w, because everything above it is a multiple of that
-// and the total is 1 << tableLog.  So with drop = tableLog - kHufL1Bits: an index's top kHufL1Bits bits select either one
-// symbol whose code is at most kHufL1Bits long (l1[] entry, same content as the full table) or a slot that lies wholly
-// inside the region of the weights 1..drop (entry 0); there the symbol is sorted[C[w-1] + ((idx - S[w-1]) >> (w-1))] with
-// w found by comparing idx with the region starts S[].
-#if !defined(LZB_HUF_L1BITS)
-#define LZB_HUF_L1BITS 10
-#endif
-enum : u32 { kHufL1Bits = LZB_HUF_L1BITS };
-struct HufCompact {
-    u16 l1[1u << kHufL1Bits];
-    u8  sorted[256];             // symbols of weights 1..drop, by weight, then by symbol (the table's own order)
-    u16 S[4];                    // S[k] = first index of the region of weight k+1 (S[0] = 0)
-    u16 C[4];                    // C[k] = place in sorted[] of the first symbol of weight k+1
-    u32 tl, l1bits;
+// Compact form of the same table for the pre-pass (2.3 KiB instead of 4 KiB at tableLog 11, so that the 56 tables an SM keeps
+// in shared memory leave it an L1): the code length is a function of the SYMBOL, so the 1 << tableLog entries only hold the
+// symbol byte and a 256-byte side table holds each symbol's length.  A lookup is two dependent byte loads instead of one
+// 16-bit load, but it is the same for every code length: the lanes of a warp decode 32 different streams, and any scheme
+// with a separate path for the long codes runs that path for all lanes almost every time (round 1's two-level table spent
+// 37 % of the expand kernel's instructions there, profiles/r02_SUMMARY.md).
+struct alignas(16) HufCompact {
+    u8  sym[1u << 11];           // tableLog <= 11 (tableLog 12 streams are left to the in-kernel path)
+    u8  len[256];                // nbBits of a symbol, 0 = not in the alphabet
+    u32 tl, pad[3];
 };
 struct HufCompactView {          // what a segment decoder keeps in registers
-    const HufCompact* t; u32 down1, down, tl1;      // 32 - l1bits, 32 - tl, tl + 1
+    const HufCompact* t; u32 down;      // 32 - tl
     LZ_HDM u32 look(u32 hi) const
     {
-        const u32 e = t->l1[hi >> down1];
-        if (e >= 256) return e;
-        const u32 idx = hi >> down;
-        const u32 w = 1 + (idx >= t->S[1] ? 1u : 0u) + (idx >= t->S[2] ? 1u : 0u);
-        return (u32)t->sorted[t->C[w - 1] + ((idx - t->S[w - 1]) >> (w - 1))] | ((tl1 - w) << 8);
+        const u32 s = t->sym[hi >> down];
+        return s | ((u32)t->len[s] << 8);
     }
 };
 LZ_HD HufCompactView huf_view(const HufCompact* t)
 {
-    HufCompactView v; v.t = t; v.down1 = 32 - t->l1bits; v.down = 32 - t->tl; v.tl1 = t->tl + 1;
+    HufCompactView v; v.t = t; v.down = 32 - t->tl;
     return v;
 }
-static_assert(kHufL1Bits >= 8 && kHufL1Bits <= 11, "at most three long weights (S[1], S[2] comparisons)");
 
 // rank_count[] is consumed, like huf_fill_dtable does.  table_log <= 11.
 LZ_HD_COLD void huf_fill_compact(HufCompact* t, const u8* weights, u32* rank_count, u32 nsym, u32 table_log)
 {
-    const u32 l1bits = table_log < kHufL1Bits ? table_log : (u32)kHufL1Bits, drop = table_log - l1bits;
-    t->tl = table_log; t->l1bits = l1bits;
-    u32 start = 0, nlong = 0;
-    for (u32 k = 0; k < 4; ++k) { t->S[k] = (u16)(1u << table_log); t->C[k] = 0; }
-    for (u32 w = 1; w <= table_log; ++w) {
-        const u32 cur = start, cnt = rank_count[w];
-        start += cnt << (w - 1);
-        if (w <= 4) t->S[w - 1] = (u16)cur;
-        if (w <= drop) { t->C[w - 1] = (u16)nlong; rank_count[w] = nlong; nlong += cnt; }   // place in sorted[]
-        else rank_count[w] = cur;                                                            // place in the index space
-    }
-    const u32 long_slots = drop ? (u32)(drop < 4 ? t->S[drop] : 0) >> drop : 0;             // S[drop] = end of weight `drop`
-    for (u32 i = 0; i < long_slots; ++i) t->l1[i] = 0;
+    t->tl = table_log;
+    u32 start = 0;
+    for (u32 w = 1; w <= table_log; ++w) { const u32 cur = start; start += rank_count[w] << (w - 1); rank_count[w] = cur; }
+    for (u32 s = 0; s < 256; ++s) t->len[s] = 0;
     for (u32 s = 0; s < nsym; ++s) {
         const u32 w = weights[s];
         if (w == 0) continue;
-        if (w <= drop) { t->sorted[rank_count[w]++] = (u8)s; continue; }
-        const u32 len = (1u << (w - 1)) >> drop, at = rank_count[w] >> drop;
-        const u16 e = (u16)(s | ((table_log + 1 - w) << 8));
-        for (u32 i = 0; i < len; ++i) t->l1[at + i] = e;
-        rank_count[w] += 1u << (w - 1);
+        const u32 n = (1u << w) >> 1, at = rank_count[w];
+        t->len[s] = (u8)(table_log + 1 - w);
+        for (u32 i = 0; i < n; ++i) t->sym[at + i] = (u8)s;
+        rank_count[w] = at + n;
     }
 }
 
