@@ -141,7 +141,9 @@ template <class T> LZ_HD u32 huf_step(BitReader& b, const T& tab)          // si
 }
 
 // one segment, one lane; true when the bitstream ended exactly
-template <class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* src, u32 len, const T& tab, int* init_err)
+// kWide: the sixteen-symbol rounds with the register window (the pre-pass kernel, which has the registers for it; inside
+// the token kernel's 64-register budget they spill and lose more than they gain)
+template <bool kWide, class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* src, u32 len, const T& tab, int* init_err)
 {
     BitReader b;
     int e = bits_init(b, src, len);
@@ -188,7 +190,7 @@ template <class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* 
 #endif
             p += 4;
         }
-        if (phase == 0) {
+        if (kWide && phase == 0) {
 #if defined(__CUDA_ARCH__)
         // sixteen symbols per round, stored as ONE 16-byte vector: the 32 lanes of a warp write 32 different streams, so every
         // store instruction costs the memory pipe 32 line accesses whatever its width -- a quarter of the stores of the
@@ -199,7 +201,7 @@ template <class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* 
         // load per ~5 rounds instead of two 8-byte loads per round (again: 32 lanes = 32 streams = 32 line accesses per load
         // instruction).  A vector is only fetched when it holds at least one byte of the stream.
         const u8* wa = nullptr;
-        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, cn = c0;      // cn: the vector below c0, requested one refill early
         const u8* const s_end = b.start + len;
         while (p + 16 <= count && ((size_t)(out + p) & 15) == 0) {
             u32 w4[4] = {0, 0, 0, 0};
@@ -211,9 +213,12 @@ template <class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* 
                     b.used &= 7;
                     const u8* const g = (const u8*)((size_t)b.ptr & ~(size_t)15);
                     if (g != wa) {
-                        if (wa != nullptr && g + 16 == wa) c1 = c0;
-                        else c1 = (g + 16 < s_end) ? *reinterpret_cast<const uint4*>(g + 16) : make_uint4(0, 0, 0, 0);
-                        c0 = *reinterpret_cast<const uint4*>(g);
+                        if (wa != nullptr && g + 16 == wa) { c1 = c0; c0 = cn; }
+                        else {
+                            c1 = (g + 16 < s_end) ? *reinterpret_cast<const uint4*>(g + 16) : make_uint4(0, 0, 0, 0);
+                            c0 = *reinterpret_cast<const uint4*>(g);
+                        }
+                        cn = (g > b.start) ? *reinterpret_cast<const uint4*>(g - 16) : make_uint4(0, 0, 0, 0);   // holds byte g-1 >= start
                         wa = g;
                         if (LZB_HUF_PREFETCH && g >= b.start + LZB_HUF_PREFETCH && ((size_t)g & 127) == 0)
                             asm volatile("prefetch.global.L1 [%0];" :: "l"(g - LZB_HUF_PREFETCH));
@@ -262,7 +267,7 @@ template <class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* 
 LZ_HD_COLD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, const u16* table, u32 tl, int* init_err)
 {
     HufFull tab; tab.t = table; tab.down = 32 - tl;
-    return huf_lane_segment_t(out, count, src, len, tab, init_err);
+    return huf_lane_segment_t<false>(out, count, src, len, tab, init_err);
 }
 
 // segment k (0..3) of a stream prepared by huf_job_prepare: the pre-pass's unit of work (huf_expand.cuh).  `pay` = the
@@ -277,7 +282,7 @@ LZ_HD bool huf_job_segment(u8* dst, u32 n, const u8* pay, u32 pc, u32 k, const H
     long cnt = k < 3 ? seg : (long)n - 3 * seg;
     if (cnt < 0) cnt = 0;
     int ierr = 0;
-    const bool good = huf_lane_segment_t(dst + (long)k * seg, cnt, s, len, huf_view(&table), &ierr);
+    const bool good = huf_lane_segment_t<true>(dst + (long)k * seg, cnt, s, len, huf_view(&table), &ierr);
     return good && ierr >= 0;
 }
 
