@@ -712,9 +712,12 @@ def run_one_stream(args, torch, dist, lz, L, dev, rank, world, h_src, d_src, lev
         "leg_GBps_rank0_link": gbps,
         "nvlink_GBps_per_direction": {"nominal": NVLINK_GBPS_NOMINAL, "measured_peer_copy": NVLINK_GBPS_MEASURED},
         "codec_only_MBps": round(total / 1e6 / (codec_ms / 1e3), 1) if codec_ms > 0 else None,
-        "limiter": ("rank 0's NVLink port: all %d GiB leave and re-enter one GPU (%.1f ms of %.1f ms per step in the four "
-                    "scatter/gather legs); the codec legs shrink with N, the rank-0 legs do not"
-                    % (total >> 30, coll_ms, ms["_total"])) if world > 1 else
+        "limiter": (("rank 0's NVLink port: all {gib} GiB leave and re-enter one GPU ({coll:.1f} ms of {tot:.1f} ms per step in the "
+                     "four scatter/gather legs, codec {codec:.1f} ms); the codec legs shrink with N, the rank-0 legs do not"
+                     if coll_ms >= codec_ms else
+                     "the codec ({codec:.1f} ms of {tot:.1f} ms per step; the scatter/gather legs through rank 0's NVLink port take "
+                     "{coll:.1f} ms: all {gib} GiB leave and re-enter one GPU)")
+                    .format(gib=total >> 30, coll=coll_ms, tot=ms["_total"], codec=codec_ms)) if world > 1 else
                    "single GPU: the scatter/gather legs are local copies",
         "transport": "torch.distributed NCCL, one batch_isend_irecv (ncclGroup of send/recv) per leg, receives land at "
                      "their final prefix-summed offsets",

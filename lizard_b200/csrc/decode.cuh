@@ -725,8 +725,11 @@ template <class W> LZ_HD void run_batch_copies_pool(u8* dst, const u8* lits, u32
         return;
     }
     if (act && off != 0 && off <= mdst) W::prefetch(dst + (mdst - off));
-    pool_copy_short<W>(dst, lits, W::ballot(act && lit_len != 0 && lit_len <= LG::kMaxBytes), opos, lit_src, lit_len, pool);
-    pool_copy_long<W>(dst, lits, W::ballot(act && lit_len > LG::kMaxBytes), opos, lit_src, lit_len, pool + 32);
+#if !defined(LZB_DEC_STREAM_LITS)
+#define LZB_DEC_STREAM_LITS 0      /* evict-first literal loads: measured no gain (profiles/r02_SUMMARY.md) */
+#endif
+    pool_copy_short<W, LZB_DEC_STREAM_LITS != 0>(dst, lits, W::ballot(act && lit_len != 0 && lit_len <= LG::kMaxBytes), opos, lit_src, lit_len, pool);
+    pool_copy_long<W, LZB_DEC_STREAM_LITS != 0>(dst, lits, W::ballot(act && lit_len > LG::kMaxBytes), opos, lit_src, lit_len, pool + 32);
     W::sync();
     // A match is "free" when its source lies before the first match destination of this batch (older output, or the
     // first literal run), or inside ONE literal run of this batch: those bytes are final now.

@@ -100,7 +100,7 @@ inline u64 rd_le64h(const u8* p) { u64 v = 0; for (int i = 0; i < 8; ++i) v |= (
 inline size_t frame_chunk_bytes()
 {
     static const size_t v = [] {
-        size_t mib = 32;
+        size_t mib = 64;
         if (const char* e = getenv("LIZARDB200_FRAME_CHUNK_MIB")) { const long t = atol(e); if (t >= 1 && t <= 1024) mib = (size_t)t; }
         return mib << 20;
     }();

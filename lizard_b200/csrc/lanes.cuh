@@ -149,6 +149,13 @@ template <bool kStream = false> LZ_HD void st_vec16(u8* p, u32 a, u32 b, u32 c, 
 {
 #if defined(__CUDA_ARCH__)
     if (kStream) { __stcs(reinterpret_cast<uint4*>(p), make_uint4(a, b, c, d)); return; }
+#if defined(LZB_EVICT_LAST_OUT)
+    // experiment: output lines are what later matches read -- ask L2 to keep them in preference to streamed data
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "l"(pol) : "memory");
+    return;
+#endif
     *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
 #else
     const u32 t[4] = { a, b, c, d }; memcpy(p, t, 16);
@@ -224,14 +231,14 @@ struct alignas(16) PoolRun { u32 a, b, c, d; };
 
 // 16 bytes from an arbitrary address, fetched as the (one or two) aligned 16-byte vectors that hold them.  Branch free
 // in the byte phase, because the lanes of a sweep work on different runs.  Every byte of [p, p+16) must be readable.
-LZ_HD Vec16 ld_chunk16(const u8* p)
+template <bool kStreamLd = false> LZ_HD Vec16 ld_chunk16(const u8* p)
 {
 #if defined(__CUDA_ARCH__)
     const u32 delta = (u32)((size_t)p & 15);
     const u8* q = p - delta;
-    const Vec16 a = ld_vec16(q);
+    const Vec16 a = ld_vec16<kStreamLd>(q);
     Vec16 b = a;
-    if (delta) b = ld_vec16(q + 16);
+    if (delta) b = ld_vec16<kStreamLd>(q + 16);
     const bool w2 = (delta & 8) != 0, w1 = (delta & 4) != 0;
     const u32 bs = (delta & 3) * 8;
     const u32 y0 = w2 ? a.w[2] : a.w[0], y1 = w2 ? a.w[3] : a.w[1], y2 = w2 ? b.w[0] : a.w[2],
@@ -249,7 +256,9 @@ LZ_HD Vec16 ld_chunk16(const u8* p)
 // Short runs (each at most LaneGroups::kMaxBytes bytes): the lanes in `sel` pass their own (d, s, n); the runs are
 // packed and moved kRuns at a time, one lane group each: dst[d, d+n) = src[s, s+n).  A run must not read what another
 // run of the same call writes.  `pool` holds 32 entries; the caller orders reuse of it with a barrier.
-template <class W> LZ_HD void pool_copy_short(u8* dst, const u8* src, u32 sel, u32 d, u32 s, u32 n, PoolRun* pool)
+// kStreamLd: the source is read exactly once (the literals stream): evict-first loads, so that it does not push the output
+// the matches will read again out of L2
+template <class W, bool kStreamLd = false> LZ_HD void pool_copy_short(u8* dst, const u8* src, u32 sel, u32 d, u32 s, u32 n, PoolRun* pool)
 {
     typedef LaneGroups<W> LG;
     if (sel == 0) return;
@@ -264,7 +273,7 @@ template <class W> LZ_HD void pool_copy_short(u8* dst, const u8* src, u32 sel, u
     for (u32 i = 0; i < cnt; i += LG::kRuns) {
         const u32 k = i + sub;
         const PoolRun e = pool[k < cnt ? k : 0];
-        lanes_copy_groups<W>(dst + e.a, src + e.b, k < cnt ? e.c : 0u);
+        lanes_copy_groups<W, false, kStreamLd>(dst + e.a, src + e.b, k < cnt ? e.c : 0u);
     }
 }
 
@@ -274,7 +283,7 @@ template <class W> LZ_HD void pool_copy_short(u8* dst, const u8* src, u32 sel, u
 // vectors that hold it (ld_chunk16), two steps in flight.  The lane finds its run without a search: the runs that begin
 // inside the step's 32 chunks are marked in a bit mask (one warp reduction), and a population count below the lane
 // gives the run's index.  Heads and tails then go two runs per step, one lane group per piece.
-template <class W> LZ_HD void pool_copy_long(u8* dst, const u8* src, u32 sel, u32 d, u32 s, u32 n, PoolRun* pool)
+template <class W, bool kStreamLd = false> LZ_HD void pool_copy_long(u8* dst, const u8* src, u32 sel, u32 d, u32 s, u32 n, PoolRun* pool)
 {
     typedef LaneGroups<W> LG;
     if (sel == 0) return;
@@ -314,13 +323,13 @@ template <class W> LZ_HD void pool_copy_long(u8* dst, const u8* src, u32 sel, u3
             const PoolRun e = pool[r0 + popc32(f0 & le_mask)];
             const u32 j = 16 * (c0 - e.a);
             to0 = dst + e.b + j;
-            x0 = ld_chunk16(src + e.c + j);
+            x0 = ld_chunk16<kStreamLd>(src + e.c + j);
         }
         if (v1) {
             const PoolRun e = pool[r1 + popc32(f1 & le_mask)];
             const u32 j = 16 * (c1 - e.a);
             to1 = dst + e.b + j;
-            x1 = ld_chunk16(src + e.c + j);
+            x1 = ld_chunk16<kStreamLd>(src + e.c + j);
         }
         if (v0) st_vec16(to0, x0.w[0], x0.w[1], x0.w[2], x0.w[3]);
         if (v1) st_vec16(to1, x1.w[0], x1.w[1], x1.w[2], x1.w[3]);
@@ -338,8 +347,8 @@ template <class W> LZ_HD void pool_copy_long(u8* dst, const u8* src, u32 sel, u3
         if (q >= 2 * cnt) len = 0;
         const u8* sp = src + sb + o; u8* dp = dst + db + o;
         u8 b0 = 0, b1 = 0;
-        if (o < len) b0 = sp[0];
-        if (G < 15 && o + G < len) b1 = sp[G];
+        if (o < len) b0 = ld_u8<kStreamLd>(sp);
+        if (G < 15 && o + G < len) b1 = ld_u8<kStreamLd>(sp + G);
         if (o < len) dp[0] = b0;
         if (G < 15 && o + G < len) dp[G] = b1;
         if (2 * G < 15) for (u32 i = o + 2 * G; i < len; i += G) dp[i - o] = sp[i - o];     // groups narrower than 8 lanes (tests)
