@@ -278,14 +278,6 @@ struct PlainTable {
     }
     LZ_HDM void set_t(u32 h, u32 abs_index, u32 tag) const { t32[h] = tagged ? abs_index | (tag >> 1) << 25 : abs_index; }
     LZ_HDM bool maybe(u32 stored, u32 mine) const { return stored == kNoTag || stored == (mine >> 1); }
-    LZ_HDM void prefetch(u32 h) const          // the bucket will be read one batch from now: start its trip from DRAM / L2 now
-    {
-#if defined(__CUDA_ARCH__)
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(t32 + h));
-#else
-        (void)h;
-#endif
-    }
     template <class W> LZ_HDM void clear(u32 hash_log) const
     {
         const u32 n = 1u << hash_log;
@@ -317,7 +309,6 @@ struct PackedTable {
     LZ_HDM u32 get_t(u32 h, u32 pos_hint, u32* t) const { *t = tag ? (u32)tag[h] : (u32)kNoTag; return get(h, pos_hint); }
     LZ_HDM void set_t(u32 h, u32 abs_index, u32 t) const { set(h, abs_index); if (tag) tag[h] = (u8)t; }
     LZ_HDM bool maybe(u32 stored, u32 mine) const { return stored == kNoTag || stored == mine; }
-    LZ_HDM void prefetch(u32) const {}          // shared memory
     template <class W> LZ_HDM void clear(u32 hash_log) const
     {
         const u32 n = 1u << hash_log;
@@ -907,10 +898,10 @@ template <class W, class TT> LZ_HD void parse_price_fast_par(const ParseCtx<TT>&
     const u32 max_dist = (1u << c.window_log) - 1;
     u32 anchor = b0, ip = b0 + 1;
     u32 last_off = 0;
-    // per lane: v_ahead = bytes at position ahead_pos, v_ahead2 = bytes NL positions further (both requested early: the
-    // first one batch ahead, the second two, so that the NEXT batch's buckets can be prefetched a whole batch before they
-    // are read -- on the plain table a bucket read is a DRAM / L2 round trip and the head of every batch's dependency chain)
-    u64 v_ahead = 0, v_ahead2 = 0; u32 ahead_pos = 0xffffffffu;
+    u64 v_ahead = 0; u32 ahead_pos = 0xffffffffu;              // per lane: bytes at position ahead_pos, if loaded
+    // (Prefetching the NEXT batch's buckets one batch early -- prefetch.global.L2 on the plain table, with the input requested
+    // two batches ahead -- was measured on the B200: level 21 26.0 ms per GiB with and without, DRAM traffic 80 GB instead of
+    // 74 GB; not kept.  profiles/r02_SUMMARY.md)
     if (b1 - b0 >= kMfLimit) {
     const u32 mflimit = b1 - kMfLimit;
     const u8* const matchlimit = src + b1 - kLastLiterals;
@@ -922,16 +913,11 @@ template <class W, class TT> LZ_HD void parse_price_fast_par(const ParseCtx<TT>&
             const u32 cur = P + bias;
             const u32 low = (bias + max_dist >= cur) ? bias : cur - max_dist;
             u64 v = 0; u32 h = 0x80000000u | lane;
-            const bool primed = ahead_pos == P;
-            if (valid) { v = primed ? v_ahead : ld5(src + P); h = hash5(v, hl); }
-            {   // bytes of the next batch (requested one batch ago when primed), request the batch after it, prefetch the next
-                // batch's buckets (all of it is used only if this batch finds nothing)
-                const u32 Pn = P + NL, Pnn = P + 2 * NL;
-                const u64 vn = Pn < mflimit ? (primed ? v_ahead2 : ld5(src + Pn)) : 0;
-                v_ahead2 = Pnn < mflimit ? ld5(src + Pnn) : 0;
-                if (Pn < mflimit) T.prefetch(hash5(vn, hl));
+            if (valid) { v = (ahead_pos == P) ? v_ahead : ld5(src + P); h = hash5(v, hl); }
+            {   // request the bytes of the following NL positions one batch early (used if this batch finds nothing)
+                const u32 Pn = P + NL;
                 ahead_pos = Pn < mflimit ? Pn : 0xffffffffu;
-                v_ahead = vn;
+                v_ahead = Pn < mflimit ? ld5(src + Pn) : 0;
             }
             const u32 peers = W::match_any(h);
             u32 below = peers & ((1u << lane) - 1);

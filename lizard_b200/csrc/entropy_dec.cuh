@@ -292,23 +292,27 @@ struct HufFull {                 // the reference's layout: 1 << tableLog entrie
     const u16* t; u32 down;      // down = 32 - tableLog
     LZ_HDM u32 look(u32 hi) const { return t[hi >> down]; }
 };
-// Compact form of the same table for the pre-pass (2.3 KiB instead of 4 KiB at tableLog 11, so that the 56 tables an SM keeps
-// in shared memory leave it an L1): the code length is a function of the SYMBOL, so the 1 << tableLog entries only hold the
-// symbol byte and a 256-byte side table holds each symbol's length.  A lookup is two dependent byte loads instead of one
-// 16-bit load, but it is the same for every code length: the lanes of a warp decode 32 different streams, and any scheme
-// with a separate path for the long codes runs that path for all lanes almost every time (round 1's two-level table spent
-// 37 % of the expand kernel's instructions there, profiles/r02_SUMMARY.md).
+// Compact form of the same table for the pre-pass (3 KiB instead of 4 KiB at tableLog 11, so that the 56 tables an SM keeps
+// in shared memory leave it an L1): one byte per entry for the symbol, one NIBBLE per entry for the code length.  Both are
+// indexed by the same table index, so the two loads of a lookup are independent of each other -- a decoder's dependency chain
+// runs through the length only (window -> index -> length -> next window), one shared-memory latency per symbol -- and the
+// lookup is the same for every code length: the lanes of a warp decode 32 different streams, and any scheme with a separate
+// path for the long codes runs that path for all lanes almost every time (round 1's two-level table spent 37 % of the expand
+// kernel's instructions there; a symbol table with a per-SYMBOL length side table made the length load wait for the symbol
+// load: profiles/r02_SUMMARY.md).
 struct alignas(16) HufCompact {
     u8  sym[1u << 11];           // tableLog <= 11 (tableLog 12 streams are left to the in-kernel path)
-    u8  len[256];                // nbBits of a symbol, 0 = not in the alphabet
+    u8  len[1u << 10];           // nbBits of entry i in nibble i & 1 of byte i >> 1
     u32 tl, pad[3];
 };
 struct HufCompactView {          // what a segment decoder keeps in registers
     const HufCompact* t; u32 down;      // 32 - tl
     LZ_HDM u32 look(u32 hi) const
     {
-        const u32 s = t->sym[hi >> down];
-        return s | ((u32)t->len[s] << 8);
+        const u32 idx = hi >> down;
+        const u32 s = t->sym[idx];
+        const u32 n = ((u32)t->len[idx >> 1] >> ((idx & 1u) * 4u)) & 15u;
+        return s | (n << 8);
     }
 };
 LZ_HD HufCompactView huf_view(const HufCompact* t)
@@ -323,13 +327,16 @@ LZ_HD_COLD void huf_fill_compact(HufCompact* t, const u8* weights, u32* rank_cou
     t->tl = table_log;
     u32 start = 0;
     for (u32 w = 1; w <= table_log; ++w) { const u32 cur = start; start += rank_count[w] << (w - 1); rank_count[w] = cur; }
-    for (u32 s = 0; s < 256; ++s) t->len[s] = 0;
     for (u32 s = 0; s < nsym; ++s) {
         const u32 w = weights[s];
         if (w == 0) continue;
-        const u32 n = (1u << w) >> 1, at = rank_count[w];
-        t->len[s] = (u8)(table_log + 1 - w);
-        for (u32 i = 0; i < n; ++i) t->sym[at + i] = (u8)s;
+        const u32 n = (1u << w) >> 1, at = rank_count[w], nb = table_log + 1 - w;
+        for (u32 i = 0; i < n; ++i) {
+            const u32 e = at + i;
+            t->sym[e] = (u8)s;
+            if (e & 1u) t->len[e >> 1] = (u8)((t->len[e >> 1] & 0x0fu) | (nb << 4));
+            else        t->len[e >> 1] = (u8)((t->len[e >> 1] & 0xf0u) | nb);
+        }
         rank_count[w] = at + n;
     }
 }

@@ -13,6 +13,7 @@ import csv
 import io
 import json
 import os
+import re
 import subprocess
 
 
@@ -39,7 +40,8 @@ def main():
         u = dict(zip(hdr, units))
         for row in rows[2:]:
             d = dict(zip(hdr, row))
-            name = d["Kernel Name"].split("(")[0].split("<")[0].strip()
+            m = re.search(r"(lizard_\w+)", d["Kernel Name"])        # "void <unnamed>::lizard_decode_units_kernel<3>(...)" -> the bare name
+            name = m.group(1) if m else d["Kernel Name"].split("(")[0].strip()
             rd = float(d["dram__bytes_read.sum"].replace(",", "")) * scale.get(u["dram__bytes_read.sum"], 1.0)
             wr = float(d["dram__bytes_write.sum"].replace(",", "")) * scale.get(u["dram__bytes_write.sum"], 1.0)
             dur = float(d["gpu__time_duration.sum"].replace(",", "")) * tscale.get(u["gpu__time_duration.sum"], 1.0)
