@@ -1,11 +1,14 @@
 // encode.cuh -- device kernel around encode_core.cuh: one warp per independent unit
 // (= one Lizard_compress call, normally one 128 KiB frame block), persistent grid, atomic work queue.
 //
-// Memory placement per warp:
-//   shared : hash table when hashLog <= 14 (16 KiB at level 10/30, 64 KiB at 21/41) + 4 KiB of
-//            per-segment byte histograms for the Huffman stage
-//   global : the four token streams of the block being parsed (4 x 128 KiB, written once, read once,
-//            L2-resident), the Huffman build scratch, and the hash table when hashLog == 18 (1 MiB)
+// Memory placement per warp (launch shape per level: encode_shape() below):
+//   shared : the PACKED hash table (16-bit entries + a bit plane for position bit 16 + one tag byte per entry for the fast
+//            parsers: 12.5 KiB at level 10/30, 34 KiB untagged at 20/21/40/41) for as many of a CTA's 14 warps as the
+//            measured shape gives one (7 at level 10, 3 at 30, 2 at 20/21, 0 at 40/41), + 4 KiB of per-segment byte
+//            histograms for the Huffman stage
+//   global : for the other warps the plain 32-bit table in their scratch (tags in the spare bits of an entry; 16 KiB at
+//            hashLog 12, 64 KiB at 14, 1 MiB at 18 or for multi-inner-block units), the sequence list of the block being
+//            parsed, the flags / literals streams when an entropy stage follows, the Huffman build scratch
 #pragma once
 #include "common.cuh"
 #include "encode_core.cuh"
