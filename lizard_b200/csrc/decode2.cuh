@@ -35,9 +35,8 @@ namespace lzb {
 struct alignas(16) OutRec { u32 opos, lsrc, mdst, off; };
 
 enum : u32 {
-    kRecRing    = 128,          // records in the ring (4 batches of 32)
-    kRecMask    = kRecRing - 1,
     kBatchSlots = 4,            // batches in flight between parser and copier
+    kSlotRecs   = 40,           // record slots per batch: 32 records + the end marker, padded (the search reads up to index 31)
     kTileBytes  = 6144,         // output window of the copier: one span = at most this many bytes
     kTileChunks = kTileBytes / 16,
     kExtraCap   = 128,          // chunks waiting for the merge pass
@@ -45,12 +44,12 @@ enum : u32 {
 };
 
 struct CopyShared {                       // shared memory of one parser / copier pair
-    OutRec rec[kRecRing];                 // record ring, index = record number & kRecMask
-    u32    pos[kRecRing];                 // opos of the records (the copier's search key); pos[n & mask] of the first unpublished
-                                          // record holds the end of the published output
+    OutRec rec[kBatchSlots * kSlotRecs];  // records of batch slot k at [k * kSlotRecs, ...)
+    u32    pos[kBatchSlots * kSlotRecs];  // opos of the records (the copier's search key); every entry behind a batch's last
+                                          // record holds the batch's end position, so a search needs no bound
     alignas(16) u8 tile[kTileBytes];      // output bytes [T0, T0 + kTileBytes) under construction
     u32    extras[kExtraCap];             // chunks of the current span that need the merge pass
-    u32    late_bits[kRecRing / 32];      // records whose match reads bytes of the current span
+    u32    late_bits;                     // records (bit = index in the batch) whose match reads bytes of the current span
 };
 
 struct CopyState {                        // registers of the copier
@@ -118,17 +117,17 @@ LZ_HD Raw16 raw_none() { Raw16 r; r.v0 = vec16_zero(); r.v1 = r.v0; r.delta = 0;
 // 16 bytes X with X[i] = out[a + i] for i in [lo, hi), read from the already written output through aligned vectors.  Only
 // vectors that hold at least one needed byte are touched (a + lo >= 0 is the caller's bound check), so no access leaves the
 // 16-byte granules the needed bytes occupy.
-LZ_HD Raw16 out_load(const u8* dst_al, long a, u32 lo, u32 hi)
+LZ_HD Raw16 out_load(const u8* dst_al, int a, u32 lo, u32 hi)
 {
     Raw16 r = raw_none();
 #if defined(__CUDA_ARCH__)
-    const long a0 = a & ~15L;
-    if (a + (long)lo < a0 + 16) r.v0 = ld_vec16(dst_al + a0);
-    if (a + (long)hi > a0 + 16) r.v1 = ld_vec16(dst_al + a0 + 16);
-    r.delta = (u32)(a & 15);
+    const int a0 = a & ~15;
+    if (a + (int)lo < a0 + 16) r.v0 = ld_vec16(dst_al + a0);
+    if (a + (int)hi > a0 + 16) r.v1 = ld_vec16(dst_al + a0 + 16);
+    r.delta = (u32)a & 15u;
 #else
     u8 t[16] = {0};
-    for (u32 i = lo; i < hi; ++i) t[i] = dst_al[a + (long)i];
+    for (u32 i = lo; i < hi; ++i) t[i] = dst_al[(long)a + (long)i];
     memcpy(&r.v0, t, 16);
 #endif
     return r;
@@ -138,11 +137,11 @@ LZ_HD Raw16 out_load(const u8* dst_al, long a, u32 lo, u32 hi)
 struct LitPtr {
     const u8* p;
     LZ_HDM u32 byte(long pos) const { return p[pos]; }
-    LZ_HDM Raw16 load(long a, u32 lo, u32 hi) const
+    LZ_HDM Raw16 load(int a, u32 lo, u32 hi) const
     {
         Raw16 r = raw_none();
         u8 t[16] = {0};
-        for (u32 i = lo; i < hi; ++i) t[i] = p[a + (long)i];
+        for (u32 i = lo; i < hi; ++i) t[i] = p[(long)a + (long)i];
         memcpy(&r.v0, t, 16);
         return r;
     }
@@ -166,14 +165,13 @@ LZ_HD void tile_store(u8* tile, u32 byte_off, const Vec16& v)
 #endif
 }
 
-// largest i in [0, nrec) with pos[(r0 + i) & mask] <= p (pos[r0] <= p is the caller's invariant); `top` = a power of two >= nrec / 2
-LZ_HD u32 rec_search(const u32* pos, u32 r0, u32 nrec, u32 top, u32 p)
+// largest i in [0, 32) with pos[i] <= p: pos[0] <= p is the caller's invariant, entries behind the batch's last record hold
+// the batch's end position, which lies above every p that is searched for
+LZ_HD u32 rec_search(const u32* pos, u32 p)
 {
     u32 lo = 0;
-    for (u32 stp = top; stp; stp >>= 1) {
-        const u32 t = lo + stp;
-        if (t < nrec && pos[(r0 + t) & kRecMask] <= p) lo = t;
-    }
+#pragma unroll
+    for (u32 stp = 16; stp; stp >>= 1) if (pos[lo + stp] <= p) lo += stp;
     return lo;
 }
 
@@ -191,7 +189,7 @@ LZ_HD void copy_merge_pass(CopyShared* cs, const LV& lv, const CopyState& st, u3
             const u32 ex = cs->extras[i];
             const u32 toff = (ex & 511u) << 4;
             const u32 c0 = T0 + toff;
-            u32 s = (ex >> 9) & 127u;
+            u32 s = (ex >> 9) & 63u;
             u32 p = c0 + (ex >> 16);
             const u32 cend = c0 + 16 < cur_end ? c0 + 16 : cur_end;
             Vec16 acc = tile_load(tile, toff);
@@ -201,19 +199,19 @@ LZ_HD void copy_merge_pass(CopyShared* cs, const LV& lv, const CopyState& st, u3
                 for (int k = 0; k < 4; ++k) {
                     have[k] = false; lo[k] = 0; raw[k] = raw_none();
                     // skip what lies behind p: empty matches, empty literal runs
-                    while (p < cend && p >= cs->pos[(r0 + s + 1) & kRecMask]) ++s;
+                    while (p < cend && p >= cs->pos[r0 + s + 1]) ++s;
                     if (p < cend) {
-                        const OutRec d = cs->rec[(r0 + s) & kRecMask];
-                        const u32 nxt = cs->pos[(r0 + s + 1) & kRecMask];
+                        const OutRec d = cs->rec[r0 + s];
+                        const u32 nxt = cs->pos[r0 + s + 1];
                         lo[k] = p - c0;
                         if (p < d.mdst) {
                             const u32 e = d.mdst < cend ? d.mdst : cend;
-                            raw[k] = lv.load((long)d.lsrc + (long)c0 - (long)d.opos, p - c0, e - c0);
+                            raw[k] = lv.load((int)(d.lsrc + c0 - d.opos), p - c0, e - c0);
                             have[k] = true; p = e;
                         } else {
                             const u32 e = nxt < cend ? nxt : cend;
-                            if (e - d.off > cur_begin) lanes_or_u32(&cs->late_bits[s >> 5], 1u << (s & 31));
-                            else { raw[k] = out_load(st.dst_al, (long)c0 - (long)d.off, p - c0, e - c0); have[k] = true; }
+                            if (e - d.off > cur_begin) lanes_or_u32(&cs->late_bits, 1u << s);
+                            else { raw[k] = out_load(st.dst_al, (int)(c0 - d.off), p - c0, e - c0); have[k] = true; }
                             p = e;
                         }
                     }
@@ -222,6 +220,46 @@ LZ_HD void copy_merge_pass(CopyShared* cs, const LV& lv, const CopyState& st, u3
                 for (int k = 0; k < 4; ++k) if (have[k]) acc = merge_from(acc, raw_finish(raw[k]), lo[k]);
             }
             tile_store(tile, toff, acc);
+        }
+    }
+}
+
+// matches that read bytes produced in the same span, in record order (= output order): their source bytes are final by the
+// time they are read.  Rare (datagen: a few per cent of the matches), kept out of line.
+template <class W>
+LZ_HD_COLD void copy_late_pass(CopyShared* cs, const CopyState& st, u32 r0, u32 T0, u32 cur_begin, u32 cur_end)
+{
+    const u32 lane = W::lane(), L = W::lanes();
+    u8* const tile = cs->tile;
+    for (u32 bits = cs->late_bits; bits; bits &= bits - 1) {
+        const u32 s = ctz32(bits);
+        const OutRec d = cs->rec[r0 + s];
+        const u32 nxt = cs->pos[r0 + s + 1];
+        const u32 a = d.mdst > cur_begin ? d.mdst : cur_begin;
+        const u32 b = nxt < cur_end ? nxt : cur_end;
+        if (a >= b) continue;
+        const u32 len = b - a, off = d.off;
+        if (off == 0) {                                            // no encoder emits it: defined output (zeros), as lanes_match
+            for (u32 i = lane; i < len; i += L) tile[a + i - T0] = 0;
+            W::sync();
+        } else if (off >= L || off >= len) {
+            for (u32 base = 0; base < len; base += L) {           // row by row: a row may read what the previous one wrote
+                const u32 i = base + lane;
+                u8 v = 0;
+                if (i < len) {
+                    const u32 sp = a - off + i;
+                    v = sp >= cur_begin ? tile[sp - T0] : st.dst_al[sp];
+                }
+                W::sync();
+                if (i < len) tile[a + i - T0] = v;
+                W::sync();
+            }
+        } else {                                                   // periodic extension of the `off` bytes before a
+            for (u32 i = lane; i < len; i += L) {
+                const u32 sp = a - off + (i % off);
+                tile[a + i - T0] = sp >= cur_begin ? tile[sp - T0] : st.dst_al[sp];
+            }
+            W::sync();
         }
     }
 }
@@ -236,10 +274,8 @@ LZ_HD void copy_tile_span(CopyShared* cs, const LV& lv, const CopyState& st, u32
     const u32 lane = W::lane(), L = W::lanes();
     const u32 T0 = cur_begin & ~15u;
     u8* const tile = cs->tile;
-    u32 top = 0;
-    if (nrec > 1) { top = 1; while (top * 2 < nrec) top *= 2; }
-    if (lane < kRecRing / 32) cs->late_bits[lane] = 0;
-    if (L < kRecRing / 32) for (u32 i = 0; i < kRecRing / 32; ++i) cs->late_bits[i] = 0;
+    (void)nrec;
+    if (lane == 0) cs->late_bits = 0;
     W::sync();
     // ---- pass 1: the run a chunk starts in fills the chunk's vector; anything else in the chunk is left to the merge pass.
     //      A lane takes kGroup chunks per step (L chunks apart, so that each load instruction of the warp covers consecutive
@@ -250,7 +286,7 @@ LZ_HD void copy_tile_span(CopyShared* cs, const LV& lv, const CopyState& st, u32
 #pragma unroll
         for (u32 k = 0; k < kGroup; ++k) {
             const u32 c0 = stepb + 16 * (lane + L * k);
-            sI[k] = c0 < cur_end ? rec_search(cs->pos, r0, nrec, top, c0 < cur_begin ? cur_begin : c0) : 0u;
+            sI[k] = c0 < cur_end ? rec_search(cs->pos + r0, c0 < cur_begin ? cur_begin : c0) : 0u;
         }
 #pragma unroll
         for (u32 k = 0; k < kGroup; ++k) {
@@ -259,15 +295,15 @@ LZ_HD void copy_tile_span(CopyShared* cs, const LV& lv, const CopyState& st, u32
             if (c0 < cur_end && c0 >= cur_begin) {
                 const u32 cend = c0 + 16 < cur_end ? c0 + 16 : cur_end;
                 const u32 s = sI[k];
-                const OutRec d = cs->rec[(r0 + s) & kRecMask];
+                const OutRec d = cs->rec[r0 + s];
                 if (c0 < d.mdst) {
                     eI[k] = d.mdst < cend ? d.mdst : cend;
-                    raw[k] = lv.load((long)d.lsrc + (long)(c0 - d.opos), 0, eI[k] - c0);
+                    raw[k] = lv.load((int)(d.lsrc + (c0 - d.opos)), 0, eI[k] - c0);
                 } else {
-                    const u32 nxt = cs->pos[(r0 + s + 1) & kRecMask];
+                    const u32 nxt = cs->pos[r0 + s + 1];
                     eI[k] = nxt < cend ? nxt : cend;
-                    if (eI[k] - d.off > cur_begin) lanes_or_u32(&cs->late_bits[s >> 5], 1u << (s & 31));
-                    else raw[k] = out_load(st.dst_al, (long)c0 - (long)d.off, 0, eI[k] - c0);
+                    if (eI[k] - d.off > cur_begin) lanes_or_u32(&cs->late_bits, 1u << s);
+                    else raw[k] = out_load(st.dst_al, (int)(c0 - d.off), 0, eI[k] - c0);
                 }
             }
         }
@@ -298,41 +334,7 @@ LZ_HD void copy_tile_span(CopyShared* cs, const LV& lv, const CopyState& st, u32
     W::sync();
     copy_merge_pass<W>(cs, lv, st, r0, T0, nx, cur_begin, cur_end);
     W::sync();
-    // ---- late matches, in record order (= output order): their source bytes are final by the time they are read
-    for (u32 w = 0; w < kRecRing / 32; ++w) {
-        u32 bits = cs->late_bits[w];
-        for (; bits; bits &= bits - 1) {
-            const u32 s = 32 * w + ctz32(bits);
-            const OutRec d = cs->rec[(r0 + s) & kRecMask];
-            const u32 nxt = cs->pos[(r0 + s + 1) & kRecMask];
-            const u32 a = d.mdst > cur_begin ? d.mdst : cur_begin;
-            const u32 b = nxt < cur_end ? nxt : cur_end;
-            if (a >= b) continue;
-            const u32 len = b - a, off = d.off;
-            if (off == 0) {                                            // no encoder emits it: defined output (zeros), as lanes_match
-                for (u32 i = lane; i < len; i += L) tile[a + i - T0] = 0;
-                W::sync();
-            } else if (off >= L || off >= len) {
-                for (u32 base = 0; base < len; base += L) {           // row by row: a row may read what the previous one wrote
-                    const u32 i = base + lane;
-                    u8 v = 0;
-                    if (i < len) {
-                        const u32 sp = a - off + i;
-                        v = sp >= cur_begin ? tile[sp - T0] : st.dst_al[sp];
-                    }
-                    W::sync();
-                    if (i < len) tile[a + i - T0] = v;
-                    W::sync();
-                }
-            } else {                                                   // periodic extension of the `off` bytes before a
-                for (u32 i = lane; i < len; i += L) {
-                    const u32 sp = a - off + (i % off);
-                    tile[a + i - T0] = sp >= cur_begin ? tile[sp - T0] : st.dst_al[sp];
-                }
-                W::sync();
-            }
-        }
-    }
+    if (cs->late_bits) copy_late_pass<W>(cs, st, r0, T0, cur_begin, cur_end);
     W::sync();
     // ---- flush: complete chunks as aligned 16-byte stores (consecutive lanes, consecutive vectors); the bytes of a trailing
     //      partial chunk go out one by one so that the invariant holds, and the chunk itself moves to the front of the tile,
@@ -410,9 +412,10 @@ struct InlineSink {
     LZ_HDM const LitPtr& view() const { return lits; }
     LZ_HDM void publish(bool act, const OutRec& r, u32 n, u32 B1, u32)
     {
-        const u32 r0 = nrec_total;
-        if (act) { cs->rec[(r0 + W::lane()) & kRecMask] = r; cs->pos[(r0 + W::lane()) & kRecMask] = r.opos; }
-        if (W::lane() == 0) cs->pos[(r0 + n) & kRecMask] = B1;
+        const u32 r0 = 0;
+        for (u32 i = W::lane(); i < kSlotRecs; i += W::lanes()) cs->pos[r0 + i] = B1;     // end marker and padding
+        W::sync();
+        if (act) { cs->rec[r0 + W::lane()] = r; cs->pos[r0 + W::lane()] = r.opos; }
         W::sync();
         copy_span<W>(cs, lits, st, r0, n, out_pos, B1);
         nrec_total += n; out_pos = B1;
@@ -478,6 +481,16 @@ template <class W, class SK> LZ_HD void publish_literals(SK& sk, u32 apos, long 
         sk.publish(W::lane() == 0, r, 1, apos + part, (u32)lp);
         apos += part; lp += part; n -= part;
     }
+}
+
+// the first generation's serial token loops, out of line (a batch reaches them only when a check fails or a run is longer
+// than a batch may cover): the parser's hot loop should not share its instruction-cache footprint with them
+template <class W> LZ_HD_COLD int lz4_serial_cold(const Streams& s, u8* dst, long oend, TokCursor& c, u32 count) { return lz4_serial<W>(s, dst, oend, c, count); }
+template <class W> LZ_HD_COLD int lizv1_serial_cold(const Streams& s, u8* dst, long oend, TokCursor& c, u32 count) { return lizv1_serial<W>(s, dst, oend, c, count); }
+template <class W> LZ_HD_COLD int read_stream_cold(bool huff, const u8* src, long csize, long& ip, u8* scratch, const u8** ptr, u32* len,
+                                                   DecWarpCore* sh, const u8* expanded)
+{
+    return read_stream<W>(huff, src, csize, ip, scratch, ptr, len, sh, expanded);
 }
 
 template <class W, class LV, class SK>
@@ -552,7 +565,7 @@ LZ_HD int parse_tokens_lz4(const Streams& s, const LV& lv, SK& sk, u8* dst, u32 
         }
         if (!taken) {            // the reference's loop, one token at a time, on the output itself
             sk.drain();
-            const int e = lz4_serial<W>(s, dst, oend, c, slow ? nb : 1);
+            const int e = lz4_serial_cold<W>(s, dst, oend, c, slow ? nb : 1);
             if (e < 0) return e;
             sk.resync((u32)c.op + skew);
         }
@@ -660,7 +673,7 @@ LZ_HD int parse_tokens_lizv1(const Streams& s, const LV& lv, SK& sk, u8* dst, u3
         }
         if (!taken) {
             sk.drain();
-            const int e = lizv1_serial<W>(s, dst, oend, c, slow ? nb : 1);
+            const int e = lizv1_serial_cold<W>(s, dst, oend, c, slow ? nb : 1);
             if (e < 0) return e;
             sk.resync((u32)c.op + skew);
         }
@@ -711,13 +724,13 @@ LZ_HD int decode_unit2(const u8* src, u32 csize_u, u8* dst, u32 cap, u8* scratch
         }
         Streams s;
         s.src_begin = src; s.src_end = src + csize;
-        if (!read_stream<W>(hdr & kFlagOff16, src, csize, ip, scratch + 3 * kDecStreamScratch, &s.off16, &s.noff16, sh)) return -1;
-        if (!read_stream<W>(hdr & kFlagOff24, src, csize, ip, scratch + 2 * kDecStreamScratch, &s.off24, &s.noff24, sh)) return -1;
+        if (!read_stream_cold<W>(hdr & kFlagOff16, src, csize, ip, scratch + 3 * kDecStreamScratch, &s.off16, &s.noff16, sh, nullptr)) return -1;
+        if (!read_stream_cold<W>(hdr & kFlagOff24, src, csize, ip, scratch + 2 * kDecStreamScratch, &s.off24, &s.noff24, sh, nullptr)) return -1;
         const bool first = up != nullptr && ip0 == 1;
         const u8* const pre_flags = (first && up->state[kSlotFlags] == kPreDone) ? arena + up->off[kSlotFlags] : nullptr;
         const u8* const pre_lits = (first && up->state[kSlotLiterals] == kPreDone) ? arena + up->off[kSlotLiterals] : nullptr;
-        if (!read_stream<W>(hdr & kFlagFlags, src, csize, ip, scratch + 1 * kDecStreamScratch, &s.flags, &s.nflags, sh, pre_flags)) return -1;
-        if (!read_stream<W>(hdr & kFlagLiterals, src, csize, ip, scratch, &s.lits, &s.nlits, sh, pre_lits)) return -1;
+        if (!read_stream_cold<W>(hdr & kFlagFlags, src, csize, ip, scratch + 1 * kDecStreamScratch, &s.flags, &s.nflags, sh, pre_flags)) return -1;
+        if (!read_stream_cold<W>(hdr & kFlagLiterals, src, csize, ip, scratch, &s.lits, &s.nlits, sh, pre_lits)) return -1;
         if (ip > csize) return -1;
         sk.drain();                                                      // the previous inner block's stream is still being read
         sk.set_stream(s.lits, s.nlits);
@@ -785,9 +798,12 @@ __device__ __forceinline__ bool mbar_try(unsigned long long* bar, u32 parity)
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity)
 {
     if (mbar_try(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try(bar, parity)) {
-        if (clock64() - t0 > 8000000000LL) __trap();          // ~4 s: a protocol bug must not hang the GPU
+    // the partner is behind: wait without taking its issue slots (try_wait parks the warp for a while by itself; the sleep
+    // keeps the retry rate down), and trap instead of hanging if a protocol bug ever leaves nothing to wait for
+    for (u32 spins = 1;; ++spins) {
+        __nanosleep(64);
+        if (mbar_try(bar, parity)) return;
+        if ((spins & 0x3fffffu) == 0) __trap();               // ~4 M retries of >= 64 ns: seconds
     }
 }
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, u32 bytes, unsigned long long* bar)
@@ -800,7 +816,7 @@ template <u32 kStages> struct LitRingView {
     static constexpr u32 kMask = kStages * kLitStage - 1;
     const u8* ring; u32 ls;
     __device__ __forceinline__ u32 byte(long pos) const { return ring[((u32)pos + ls) & kMask]; }
-    __device__ __forceinline__ Raw16 load(long a, u32, u32) const
+    __device__ __forceinline__ Raw16 load(int a, u32, u32) const
     {
         const u32 x = (u32)a + ls;                       // wraps consistently for the (masked-out) bytes in front of a run
         const u32 a0 = (x & ~15u) & kMask;
@@ -911,7 +927,7 @@ template <u32 kStages> struct PairSink {
     }
     __device__ __forceinline__ void send(const PairMsg& m, u32 lit_st)
     {
-        while (msg_count - acked > kBatchSlots - 2) wait_ack();      // <= 3 batches outstanding: 96 records + the end marker fit the ring
+        while (msg_count - acked > kBatchSlots - 1) wait_ack();      // a message slot (and its record rows) is reused only when consumed
         const u32 slot = msg_count % kBatchSlots;
         if ((threadIdx.x & 31) == 0) ps->msg[slot] = m;
         lit_stage = (lit_stage & ~(0xffu << (8 * slot))) | ((lit_st & 0xffu) << (8 * slot));
@@ -921,11 +937,14 @@ template <u32 kStages> struct PairSink {
     }
     __device__ __forceinline__ void publish(bool act, const OutRec& r, u32 n, u32 B1, u32 lp0)
     {
-        while (msg_count - acked > kBatchSlots - 2) wait_ack();
+        while (msg_count - acked > kBatchSlots - 1) wait_ack();
         const u32 lane = threadIdx.x & 31;
-        if (act) { ps->cs.rec[(nrec_total + lane) & kRecMask] = r; ps->cs.pos[(nrec_total + lane) & kRecMask] = r.opos; }
-        if (lane == 0) ps->cs.pos[(nrec_total + n) & kRecMask] = B1;
-        PairMsg m; m.kind = kMsgData; m.r0 = nrec_total; m.nrec = n; m.B0 = out_pos; m.B1 = B1; m.ls = lv.ls;
+        const u32 r0 = (msg_count % kBatchSlots) * kSlotRecs;
+        // the whole position row is written by this warp before the batch is published: opos for the records, the batch's end
+        // position for the end marker and the padding behind it
+        { const u32 i = lane; ps->cs.pos[r0 + i] = act ? r.opos : B1; if (i < kSlotRecs - 32) ps->cs.pos[r0 + 32 + i] = B1; }
+        if (act) ps->cs.rec[r0 + lane] = r;
+        PairMsg m; m.kind = kMsgData; m.r0 = r0; m.nrec = n; m.B0 = out_pos; m.B1 = B1; m.ls = lv.ls;
         m.dst_al = dst_al; m.unit_lo = unit_lo; m.apos = 0;
         send(m, (lp0 + lv.ls) / kLitStage);
         nrec_total += n; out_pos = B1;
