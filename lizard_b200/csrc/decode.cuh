@@ -140,10 +140,69 @@ template <class T> LZ_HD u32 huf_step(BitReader& b, const T& tab)          // si
     return e & 255;
 }
 
+// ---- pieces of the sixteen-symbol rounds (huf_lane_segment_t<true>) ----
+#if !defined(LZB_SHIM_CHECK)
+#define LZB_SHIM_CHECK(cond) ((void)0)          /* the CPU test build turns this into an abort */
+#endif
+#if defined(__CUDA_ARCH__)
+enum : u32 { kHufRingStride = 32 };             // shared memory, word j of lane l at [j][l]: every access is conflict-free
+#else
+enum : u32 { kHufRingStride = 1 };
+#endif
+enum : u32 { kHufRingWords = 16 };              // 64 bytes per lane
+struct HufVec { u32 x, y, z, w; };
+LZ_HD HufVec huf_vec_zero() { HufVec v; v.x = v.y = v.z = v.w = 0; return v; }
+// the aligned 16 bytes at `a`; bytes outside [lo, hi) read as zero, a vector wholly outside is not touched
+LZ_HD HufVec huf_vec_load(const u8* a, const u8* lo, const u8* hi)
+{
+    HufVec v = huf_vec_zero();
+    if (a + 16 <= lo || a >= hi) return v;
+#if defined(__CUDA_ARCH__)
+    const uint4 q = *reinterpret_cast<const uint4*>(a);      // an aligned vector with one valid byte lies inside the allocation
+    v.x = q.x; v.y = q.y; v.z = q.z; v.w = q.w;
+#else
+    u32 wv[4] = {0, 0, 0, 0};
+    for (u32 i = 0; i < 16; ++i) if (a + i >= lo && a + i < hi) wv[i >> 2] |= (u32)a[i] << (8 * (i & 3));
+    v.x = wv[0]; v.y = wv[1]; v.z = wv[2]; v.w = wv[3];
+#endif
+    return v;
+}
+LZ_HD void huf_ring_put(u32* ring, const u8* a, const HufVec& v)
+{
+    const u32 j = ((u32)(size_t)a >> 2) & (kHufRingWords - 4);
+    ring[(j + 0) * kHufRingStride] = v.x; ring[(j + 1) * kHufRingStride] = v.y;
+    ring[(j + 2) * kHufRingStride] = v.z; ring[(j + 3) * kHufRingStride] = v.w;
+}
+LZ_HD void huf_store16(u8* p, u32 a, u32 b, u32 c, u32 d)    // p is 16-byte aligned
+{
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+#else
+    u32* q = reinterpret_cast<u32*>(p); q[0] = a; q[1] = b; q[2] = c; q[3] = d;
+#endif
+}
+LZ_HD u32 fsh_r(u32 lo, u32 hi, u32 s)          // low word of (hi:lo) >> s, s < 32
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+#endif
+}
+LZ_HD u32 fsh_l(u32 lo, u32 hi, u32 s)          // high word of (hi:lo) << s, s < 32
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, s);
+#else
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+
 // one segment, one lane; true when the bitstream ended exactly
-// kWide: the sixteen-symbol rounds with the register window (the pre-pass kernel, which has the registers for it; inside
-// the token kernel's 64-register budget they spill and lose more than they gain)
-template <bool kWide, class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* src, u32 len, const T& tab, int* init_err)
+// kWide + ring: the sixteen-symbol rounds with the bitstream window in a per-lane ring (the pre-pass kernel; inside the
+// token kernel's 64-register budget they spill and lose more than they gain)
+template <bool kWide, class T> LZ_HD bool huf_lane_segment_t(u8* out, long count, const u8* src, u32 len, const T& tab, int* init_err,
+                                                           u32* ring = nullptr)
 {
     BitReader b;
     int e = bits_init(b, src, len);
@@ -190,58 +249,73 @@ template <bool kWide, class T> LZ_HD bool huf_lane_segment_t(u8* out, long count
 #endif
             p += 4;
         }
-        if (kWide && phase == 0) {
-#if defined(__CUDA_ARCH__)
+        if (kWide && phase == 0 && ring != nullptr) {
         // sixteen symbols per round, stored as ONE 16-byte vector: the 32 lanes of a warp write 32 different streams, so every
         // store instruction costs the memory pipe 32 line accesses whatever its width -- a quarter of the stores of the
-        // four-byte form below.  Same walk: four times (reload, four symbols).
+        // four-byte form.  Same walk: four times (reload, four symbols).
+        //
+        // The bitstream is read backwards, ~3 bytes per reload.  Its bytes around the read position live in a 64-byte ring of
+        // this lane (address-mapped: the word at address a is ring word (a >> 2) & 15), refilled at ONE place, at the top of a
+        // round, for all lanes together: the aligned 16-byte vector below the ring is requested a whole round before it is
+        // stored into the ring (`nx`), and a reload reads its 8 bytes from the ring.  A round moves the read position down by
+        // at most 32 bytes (four reloads of <= 64 bits), so with the ring's lowest vector at floor16(ptr - 32) every reload of
+        // the round finds its bytes.
+        // Why not in registers: a lane needs a new vector every ~5 reloads, each lane at its own time.  With the window in
+        // registers the refill is a lane-divergent branch, and the scoreboard that guards the loaded registers is the WARP's:
+        // whichever lanes refill next wait for the load the previous lanes issued one reload ago -- a memory latency per
+        // reload, ~36 % of the kernel's stall samples (profiles/r02_SUMMARY.md, section 4).  Here a loaded register is first
+        // read a round (~1000 cycles) after its load was issued, by construction.
         {
-        // The bitstream is read backwards, ~3 bytes per round: the two aligned 16-byte vectors around the read position stay
-        // in registers (c0 at `wa`, c1 at wa + 16) and a new one is fetched only when the position crosses wa -- one 16-byte
-        // load per ~5 rounds instead of two 8-byte loads per round (again: 32 lanes = 32 streams = 32 line accesses per load
-        // instruction).  A vector is only fetched when it holds at least one byte of the stream.
-        const u8* wa = nullptr;
-        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, cn = c0;      // cn: the vector below c0, requested one refill early
         const u8* const s_end = b.start + len;
+        const u8* wa = nullptr;                                   // address of the ring's lowest vector
+        HufVec nx = huf_vec_zero();                               // the vector at wa - 16, in flight
         while (p + 16 <= count && ((size_t)(out + p) & 15) == 0) {
+            if (b.ptr >= b.start + 16 && b.used <= 64) {
+                const u8* const tgt = (const u8*)(((size_t)b.ptr - 32) & ~(size_t)15);
+                if (wa == nullptr) {
+                    wa = tgt;
+                    for (u32 k = 0; k < 4; ++k) huf_ring_put(ring, wa + 16 * k, huf_vec_load(wa + 16 * k, b.start, s_end));
+                    nx = huf_vec_load(wa - 16, b.start, s_end);
+                } else {
+                    while (wa > tgt) {                            // once; twice after a round of codes longer than 8 bits
+                        wa -= 16;
+                        huf_ring_put(ring, wa, nx);
+                        nx = huf_vec_load(wa - 16, b.start, s_end);
+#if defined(__CUDA_ARCH__)
+                        if (LZB_HUF_PREFETCH && wa >= b.start + LZB_HUF_PREFETCH && ((size_t)wa & 127) == 0)
+                            asm volatile("prefetch.global.L1 [%0];" :: "l"(wa - LZB_HUF_PREFETCH));
+#endif
+                    }
+                }
+            }
             u32 w4[4] = {0, 0, 0, 0};
             int r = 0;
+#if defined(__CUDA_ARCH__)
 #pragma unroll
+#endif
             for (int q = 0; q < 4; ++q) {
                 if (r == q && b.ptr >= b.start + 16 && b.used <= 64) {
                     b.ptr -= b.used >> 3;
                     b.used &= 7;
-                    const u8* const g = (const u8*)((size_t)b.ptr & ~(size_t)15);
-                    if (g != wa) {
-                        if (wa != nullptr && g + 16 == wa) { c1 = c0; c0 = cn; }
-                        else {
-                            c1 = (g + 16 < s_end) ? *reinterpret_cast<const uint4*>(g + 16) : make_uint4(0, 0, 0, 0);
-                            c0 = *reinterpret_cast<const uint4*>(g);
-                        }
-                        cn = (g > b.start) ? *reinterpret_cast<const uint4*>(g - 16) : make_uint4(0, 0, 0, 0);   // holds byte g-1 >= start
-                        wa = g;
-                        if (LZB_HUF_PREFETCH && g >= b.start + LZB_HUF_PREFETCH && ((size_t)g & 127) == 0)
-                            asm volatile("prefetch.global.L1 [%0];" :: "l"(g - LZB_HUF_PREFETCH));
-                    }
-                    const u32 off = (u32)((size_t)b.ptr & 15), bs = (off & 3) * 8;
-                    const bool k2 = (off & 8) != 0, k1 = (off & 4) != 0;
-                    const u32 x0 = k2 ? c0.z : c0.x, x1 = k2 ? c0.w : c0.y, x2 = k2 ? c1.x : c0.z, x3 = k2 ? c1.y : c0.w;
-                    const u32 y0 = k1 ? x1 : x0, y1 = k1 ? x2 : x1, y2 = k1 ? x3 : x2;
-                    u32 lo = __funnelshift_r(y0, y1, bs), hi = __funnelshift_r(y1, y2, bs);     // the 8 bytes at b.ptr
-                    hi = __funnelshift_l(lo, hi, b.used); lo <<= b.used;
+                    LZB_SHIM_CHECK(b.ptr >= wa && b.ptr + 8 <= wa + 64);
+                    const u32 a = (u32)(size_t)b.ptr, t = a >> 2, bs = (a & 3) * 8;
+                    const u32 y0 = ring[(t & 15u) * kHufRingStride], y1 = ring[((t + 1) & 15u) * kHufRingStride];
+                    const u32 y2 = ring[((t + 2) & 15u) * kHufRingStride];
+                    u32 lo = fsh_r(y0, y1, bs), hi = fsh_r(y1, y2, bs);                  // the 8 bytes at b.ptr
+                    hi = fsh_l(lo, hi, b.used); lo <<= b.used;
                     u32 e = tab.look(hi), n = e >> 8, word = e & 255, used = b.used + n;
-                    hi = __funnelshift_l(lo, hi, n); lo <<= n;
+                    hi = fsh_l(lo, hi, n); lo <<= n;
                     e = tab.look(hi); n = e >> 8; word |= (e & 255) << 8; used += n;
-                    hi = __funnelshift_l(lo, hi, n); lo <<= n;
+                    hi = fsh_l(lo, hi, n); lo <<= n;
                     e = tab.look(hi); n = e >> 8; word |= (e & 255) << 16; used += n;
-                    hi = __funnelshift_l(lo, hi, n);
+                    hi = fsh_l(lo, hi, n);
                     e = tab.look(hi); word |= e << 24; used += e >> 8;
                     b.used = used;
                     w4[q] = word;
                     r = q + 1;
                 }
             }
-            if (r == 4) { *reinterpret_cast<uint4*>(out + p) = make_uint4(w4[0], w4[1], w4[2], w4[3]); p += 16; continue; }
+            if (r == 4) { huf_store16(out + p, w4[0], w4[1], w4[2], w4[3]); p += 16; continue; }
             // the walk reached the last 16 bytes of the bitstream inside this round: hand over what was decoded
             if (r > 0) *reinterpret_cast<u32*>(out + p) = w4[0];
             if (r > 1) *reinterpret_cast<u32*>(out + p + 4) = w4[1];
@@ -250,7 +324,6 @@ template <bool kWide, class T> LZ_HD bool huf_lane_segment_t(u8* out, long count
             break;
         }
         }
-#endif
         }
         }
     }
@@ -272,7 +345,8 @@ LZ_HD_COLD bool huf_lane_segment(u8* out, long count, const u8* src, u32 len, co
 
 // segment k (0..3) of a stream prepared by huf_job_prepare: the pre-pass's unit of work (huf_expand.cuh).  `pay` = the
 // stream behind its weight header, `pc` its size.  Same split and same walk as huf_decompress_lanes below.
-LZ_HD bool huf_job_segment(u8* dst, u32 n, const u8* pay, u32 pc, u32 k, const HufCompact& table)
+// `ring`: this lane's kHufRingWords words (stride kHufRingStride) for the bitstream window
+LZ_HD bool huf_job_segment(u8* dst, u32 n, const u8* pay, u32 pc, u32 k, const HufCompact& table, u32* ring)
 {
     const u32 l1 = rd_le16(pay), l2 = rd_le16(pay + 2), l3 = rd_le16(pay + 4);
     const u32 l4 = pc - (l1 + l2 + l3 + 6);
@@ -282,7 +356,7 @@ LZ_HD bool huf_job_segment(u8* dst, u32 n, const u8* pay, u32 pc, u32 k, const H
     long cnt = k < 3 ? seg : (long)n - 3 * seg;
     if (cnt < 0) cnt = 0;
     int ierr = 0;
-    const bool good = huf_lane_segment_t<true>(dst + (long)k * seg, cnt, s, len, huf_view(&table), &ierr);
+    const bool good = huf_lane_segment_t<true>(dst + (long)k * seg, cnt, s, len, huf_view(&table), &ierr, ring);
     return good && ierr >= 0;
 }
 

@@ -3,6 +3,9 @@
 // __host__ __device__ code (entropy_dec.cuh / entropy_enc.cuh / encode_core.cuh, instantiated with the
 // one-lane policy HostLanes) against the reference library without a GPU.  Nothing in the product
 // path links or loads this file; liblizard_b200.so has no CPU code path.
+#include <stdio.h>
+#include <stdlib.h>
+#define LZB_SHIM_CHECK(cond) do { if (!(cond)) { fprintf(stderr, "host shim check failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); abort(); } } while (0)
 #include "entropy_dec.cuh"
 #include "encode_core.cuh"
 #include "decode.cuh"
@@ -94,8 +97,9 @@ static void host_prepass(const unsigned char* src, int csize, HostPre* hp, int s
         j.dst = cursor; cursor += (size_t)lzb::pre_slot_bytes(j.n);
         lzb::u32 h = 0;
         bool ok = lzb::huf_job_prepare(src + j.src, j.c, j.n, table, ws, &h);
+        lzb::u32 ring[lzb::kHufRingWords];
         for (lzb::u32 k = 0; ok && k < 4; ++k)
-            ok = lzb::huf_job_segment(hp->arena + j.dst, j.n, src + j.src + h, j.c - h, k, *table);
+            ok = lzb::huf_job_segment(hp->arena + j.dst, j.n, src + j.src + h, j.c - h, k, *table, ring);
         if (sabotage && ok) memset(hp->arena + j.dst, 0x5A, j.n);     // tests: proves the token decoder reads the arena
         hp->up.off[j.slot] = j.dst;
         hp->up.state[j.slot] = ok ? lzb::kPreDone : lzb::kPreNone;

@@ -28,6 +28,7 @@ enum : u32 { kExpWarps = 7, kExpJobs = 8, kExpCtasMax = LZB_EXP_CTAS_MAX };   //
 
 struct ExpWarpShared {
     HufCompact table[kExpJobs];
+    u32 ring[kHufRingWords * 32];              // bitstream windows of the 32 segment decoders (decode.cuh), [word][lane]
     u32 hdr_len[kExpJobs], ok[kExpJobs];
 };
 
@@ -128,7 +129,7 @@ lizard_huf_expand_kernel(PrepassBatch b)
                 j = list[first + jj];
                 if (sh->ok[jj]) {
                     const u32 h = sh->hdr_len[jj];
-                    good = huf_job_segment(b.arena + j.dst, j.n, b.src_base + j.src + h, j.c - h, k, sh->table[jj]);
+                    good = huf_job_segment(b.arena + j.dst, j.n, b.src_base + j.src + h, j.c - h, k, sh->table[jj], sh->ring + lane);
                 }
             }
             const u32 g = __ballot_sync(LZB_FULL, good);
