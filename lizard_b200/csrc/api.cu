@@ -23,7 +23,10 @@ using namespace lzb;
 
 namespace {
 
-constexpr int kDecWarps = 8;                 // warps per CTA in the decode kernel
+#if !defined(LZB_DEC_WARPS)
+#define LZB_DEC_WARPS 8
+#endif
+constexpr int kDecWarps = LZB_DEC_WARPS;     // warps per CTA in the decode kernel (x 4 CTAs per SM)
 constexpr int kMaxDevices = 16;
 
 // V = schedule of the token loops, two bits: 1 = pooled copy sweeps, 2 = compact length-extension chain (default 3 = both;

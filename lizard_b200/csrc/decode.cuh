@@ -140,6 +140,20 @@ template <class T> LZ_HD u32 huf_step(BitReader& b, const T& tab)          // si
     return e & 255;
 }
 
+// literals-stream prefetch of the token loops: every batch requests LINES 128-byte lines from DIST bytes behind the batch's
+// first literal byte (a batch consumes ~2.7 KB of the stream at level 10; an SM's L1 is ~5 KB per resident warp)
+#if !defined(LZB_HUF_PREFETCH_L2)
+#define LZB_HUF_PREFETCH_ASM(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
+#else
+#define LZB_HUF_PREFETCH_ASM(p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p))
+#endif
+#if !defined(LZB_DEC_LIT_PF_DIST)
+#define LZB_DEC_LIT_PF_DIST 4096
+#endif
+#if !defined(LZB_DEC_LIT_PF_LINES)
+#define LZB_DEC_LIT_PF_LINES 32
+#endif
+
 // ---- pieces of the sixteen-symbol rounds (huf_lane_segment_t<true>) ----
 #if !defined(LZB_SHIM_CHECK)
 #define LZB_SHIM_CHECK(cond) ((void)0)          /* the CPU test build turns this into an abort */
@@ -283,7 +297,7 @@ template <bool kWide, class T> LZ_HD bool huf_lane_segment_t(u8* out, long count
                         nx = huf_vec_load(wa - 16, b.start, s_end);
 #if defined(__CUDA_ARCH__)
                         if (LZB_HUF_PREFETCH && wa >= b.start + LZB_HUF_PREFETCH && ((size_t)wa & 127) == 0)
-                            asm volatile("prefetch.global.L1 [%0];" :: "l"(wa - LZB_HUF_PREFETCH));
+                            LZB_HUF_PREFETCH_ASM(wa - LZB_HUF_PREFETCH);
 #endif
                     }
                 }
@@ -881,7 +895,7 @@ template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst,
     while (c.fp < s.nflags) {
         const u32 nb = s.nflags - c.fp < NL ? s.nflags - c.fp : NL;
         const bool act = lane < nb;
-        if (c.lp + 4096 + 128 * (long)lane < nl) W::prefetch(s.lits + c.lp + 4096 + 128 * (long)lane);
+        if (lane < LZB_DEC_LIT_PF_LINES && c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane < nl) W::prefetch(s.lits + c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane);
         const u32 tok = act ? s.flags[c.fp + lane] : 0;
         const u32 litn = tok & 15, mln = tok >> 4;
         const bool need = act && litn == 15;
@@ -987,7 +1001,7 @@ template <class W, int V> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* ds
     while (c.fp < s.nflags) {
         const u32 nb = s.nflags - c.fp < NL ? s.nflags - c.fp : NL;
         const bool act = lane < nb;
-        if (c.lp + 4096 + 128 * (long)lane < nl) W::prefetch(s.lits + c.lp + 4096 + 128 * (long)lane);
+        if (lane < LZB_DEC_LIT_PF_LINES && c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane < nl) W::prefetch(s.lits + c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane);
         const u32 tok = act ? s.flags[c.fp + lane] : 32;           // inactive lanes: an empty short token
         const bool shortf = tok >= 32;                              // [r_MMMM_LLL] with a 16-bit or repeated offset
         const u32 litn = shortf ? (tok & 7) : 0;

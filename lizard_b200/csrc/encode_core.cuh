@@ -535,6 +535,9 @@ last_literals:
 // When the walk leaves the window the committed lanes write their buckets (last writer per bucket wins).
 // Consecutive positions hold while a search has made at most 65 probes (probe_offset); a longer miss run falls
 // back to the batch search with its growing stride.
+#if !defined(LZB_ENC_SRC_PF)
+#define LZB_ENC_SRC_PF 384
+#endif
 template <class W, class TT, bool kBig = false> LZ_HD void parse_fast_win(const ParseCtx<TT>& c, u32 b0, u32 b1, EncStreams& st)
 {
     const u8* const src = c.src;
@@ -563,7 +566,7 @@ template <class W, class TT, bool kBig = false> LZ_HD void parse_fast_win(const 
             const bool s_valid = P + 1 <= mflimit;                 // as a search probe: else it ends the block
             u64 v = 0; u32 h = 0x80000000u | lane;                 // unique key: shares a bucket with nobody
             if (ld_ok) { v = ld5(src + P); h = hash5(v, hl); }
-            if (P + 384 < b1) W::prefetch(src + P + 384);          // the input is walked once, front to back
+            if (P + LZB_ENC_SRC_PF < b1) W::prefetch(src + P + LZB_ENC_SRC_PF);   // the input is walked once, front to back
             const u32 same = W::match_any(h);
             const u32 below = same & lt_mask;
             const u32 mytag = tag8((u32)v);
