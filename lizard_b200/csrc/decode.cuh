@@ -141,17 +141,25 @@ template <class T> LZ_HD u32 huf_step(BitReader& b, const T& tab)          // si
 }
 
 // literals-stream prefetch of the token loops: every batch requests LINES 128-byte lines from DIST bytes behind the batch's
-// first literal byte (a batch consumes ~2.7 KB of the stream at level 10; an SM's L1 is ~5 KB per resident warp)
+// first literal byte.  A batch consumes ~2.7 KB of the stream at level 10 and an SM's L1 is ~5 KB per resident warp, so the
+// lines have to be requested just in time: distance 0 (the batch's own bytes, all 32 lines in flight at once before the
+// extension chain starts walking them) beat 512 / 1024 / 2048 / 4096 in that order -- level 10: 1.562 / 1.575 / 1.587 /
+// 1.629 / 1.675 ms per GiB, no prefetch 1.673 (profiles/r02_SUMMARY.md, section 6).
+// LZB_DEC_LIT_PF_NEXT: request the NEXT batch's lines before this batch's copy sweeps instead (A/B builds).
+#if !defined(LZB_DEC_LIT_PF_DIST)
+#define LZB_DEC_LIT_PF_DIST 0
+#endif
+#if !defined(LZB_DEC_LIT_PF_LINES)
+#define LZB_DEC_LIT_PF_LINES 32
+#endif
+#if !defined(LZB_DEC_LIT_PF_NEXT)
+#define LZB_DEC_LIT_PF_NEXT 0
+#endif
+// expand kernel (A/B builds): level of the optional bitstream prefetch
 #if !defined(LZB_HUF_PREFETCH_L2)
 #define LZB_HUF_PREFETCH_ASM(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
 #else
 #define LZB_HUF_PREFETCH_ASM(p) asm volatile("prefetch.global.L2 [%0];" :: "l"(p))
-#endif
-#if !defined(LZB_DEC_LIT_PF_DIST)
-#define LZB_DEC_LIT_PF_DIST 4096
-#endif
-#if !defined(LZB_DEC_LIT_PF_LINES)
-#define LZB_DEC_LIT_PF_LINES 32
 #endif
 
 // ---- pieces of the sixteen-symbol rounds (huf_lane_segment_t<true>) ----
@@ -240,7 +248,7 @@ template <bool kWide, class T> LZ_HD bool huf_lane_segment_t(u8* out, long count
             b.win = ld64_any(b.ptr);
 #if defined(__CUDA_ARCH__)
 #if !defined(LZB_HUF_PREFETCH)
-#define LZB_HUF_PREFETCH 384
+#define LZB_HUF_PREFETCH 0           /* with the ring's loads issued a round ahead an L1 / L2 prefetch changes nothing (0 / 128 / 384 / 1024) */
 #endif
             if (LZB_HUF_PREFETCH && b.ptr >= b.start + LZB_HUF_PREFETCH && ((size_t)b.ptr & 127) < 6)
                 asm volatile("prefetch.global.L1 [%0];" :: "l"(b.ptr - LZB_HUF_PREFETCH));
@@ -317,15 +325,13 @@ template <bool kWide, class T> LZ_HD bool huf_lane_segment_t(u8* out, long count
                     const u32 y2 = ring[((t + 2) & 15u) * kHufRingStride];
                     u32 lo = fsh_r(y0, y1, bs), hi = fsh_r(y1, y2, bs);                  // the 8 bytes at b.ptr
                     hi = fsh_l(lo, hi, b.used); lo <<= b.used;
-                    u32 e = tab.look(hi), n = e >> 8, word = e & 255, used = b.used + n;
-                    hi = fsh_l(lo, hi, n); lo <<= n;
-                    e = tab.look(hi); n = e >> 8; word |= (e & 255) << 8; used += n;
-                    hi = fsh_l(lo, hi, n); lo <<= n;
-                    e = tab.look(hi); n = e >> 8; word |= (e & 255) << 16; used += n;
-                    hi = fsh_l(lo, hi, n);
-                    e = tab.look(hi); word |= e << 24; used += e >> 8;
-                    b.used = used;
-                    w4[q] = word;
+                    u32 s0, s1, s2, s3, n0, n1, n2, n3;
+                    tab.look2(hi, &s0, &n0); hi = fsh_l(lo, hi, n0); lo <<= n0;
+                    tab.look2(hi, &s1, &n1); hi = fsh_l(lo, hi, n1); lo <<= n1;
+                    tab.look2(hi, &s2, &n2); hi = fsh_l(lo, hi, n2);
+                    tab.look2(hi, &s3, &n3);
+                    b.used += n0 + n1 + n2 + n3;
+                    w4[q] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
                     r = q + 1;
                 }
             }
@@ -895,7 +901,8 @@ template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst,
     while (c.fp < s.nflags) {
         const u32 nb = s.nflags - c.fp < NL ? s.nflags - c.fp : NL;
         const bool act = lane < nb;
-        if (lane < LZB_DEC_LIT_PF_LINES && c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane < nl) W::prefetch(s.lits + c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane);
+        if ((!LZB_DEC_LIT_PF_NEXT || c.fp == 0) && lane < LZB_DEC_LIT_PF_LINES && c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane < nl)
+            W::prefetch(s.lits + c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane);
         const u32 tok = act ? s.flags[c.fp + lane] : 0;
         const u32 litn = tok & 15, mln = tok >> 4;
         const bool need = act && litn == 15;
@@ -972,6 +979,7 @@ template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst,
             }
             if (W::ballot(bad) == 0) {
                 LZB_COUNT_FAST(W::lane() == 0 ? nb : 0);
+                if (LZB_DEC_LIT_PF_NEXT) { const long nx = c.lp + (long)tot_adv + (long)tot_ext + 128 * (long)lane; if (lane < LZB_DEC_LIT_PF_LINES && nx < nl) W::prefetch(s.lits + nx); }
                 if ((V & 1) == 0) run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, sh->desc);
                 else run_batch_copies_pool<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, sh->desc);
                 c.fp += nb; c.lp += (long)tot_adv + (long)tot_ext; c.op += (long)tot_out;
@@ -1001,7 +1009,8 @@ template <class W, int V> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* ds
     while (c.fp < s.nflags) {
         const u32 nb = s.nflags - c.fp < NL ? s.nflags - c.fp : NL;
         const bool act = lane < nb;
-        if (lane < LZB_DEC_LIT_PF_LINES && c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane < nl) W::prefetch(s.lits + c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane);
+        if ((!LZB_DEC_LIT_PF_NEXT || c.fp == 0) && lane < LZB_DEC_LIT_PF_LINES && c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane < nl)
+            W::prefetch(s.lits + c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane);
         const u32 tok = act ? s.flags[c.fp + lane] : 32;           // inactive lanes: an empty short token
         const bool shortf = tok >= 32;                              // [r_MMMM_LLL] with a 16-bit or repeated offset
         const u32 litn = shortf ? (tok & 7) : 0;
@@ -1092,6 +1101,7 @@ template <class W, int V> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* ds
             }
             if (W::ballot(bad) == 0) {
                 LZB_COUNT_FAST(W::lane() == 0 ? nb : 0);
+                if (LZB_DEC_LIT_PF_NEXT) { const long nx = c.lp + (long)tot_adv + (long)tot_ext + 128 * (long)lane; if (lane < LZB_DEC_LIT_PF_LINES && nx < nl) W::prefetch(s.lits + nx); }
                 if ((V & 1) == 0) run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, sh->desc);
                 else run_batch_copies_pool<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, sh->desc);
                 c.fp += nb; c.lp += (long)tot_adv + (long)tot_ext; c.op += (long)tot_out;

@@ -291,6 +291,7 @@ LZ_HD_COLD void huf_fill_dtable(u16* table, const u8* weights, u32* rank_count, 
 struct HufFull {                 // the reference's layout: 1 << tableLog entries (HUF_readDTableX2, huf_decompress.c:87-133)
     const u16* t; u32 down;      // down = 32 - tableLog
     LZ_HDM u32 look(u32 hi) const { return t[hi >> down]; }
+    LZ_HDM void look2(u32 hi, u32* sym, u32* nbits) const { const u32 e = t[hi >> down]; *sym = e & 255u; *nbits = e >> 8; }
 };
 // Compact form of the same table for the pre-pass (3 KiB instead of 4 KiB at tableLog 11, so that the 56 tables an SM keeps
 // in shared memory leave it an L1): one byte per entry for the symbol, one NIBBLE per entry for the code length.  Both are
@@ -307,6 +308,30 @@ struct alignas(16) HufCompact {
 };
 struct HufCompactView {          // what a segment decoder keeps in registers
     const HufCompact* t; u32 down;      // 32 - tl
+#if defined(__CUDA_ARCH__)
+    // The tables live in shared memory (prepass.cuh).  Their two base addresses are kept as opaque 32-bit shared-space
+    // registers: left to itself the compiler re-derives `warp's block + job * sizeof(table)` with a multiply-add in front
+    // of every one of the eight loads of a reload, two of them on the length chain.
+    u32 sym_at, len_at;
+    LZ_HDM u32 look(u32 hi) const
+    {
+        const u32 idx = hi >> down;
+        u32 s, b;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(s) : "r"(sym_at + idx));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(len_at + (idx >> 1)));
+        const u32 n = (b >> ((idx & 1u) * 4u)) & 15u;
+        return s | (n << 8);
+    }
+    LZ_HDM void look2(u32 hi, u32* sym, u32* nbits) const      // symbol and length apart: the length is the decoder's chain
+    {
+        const u32 idx = hi >> down;
+        u32 s, b;
+        asm("ld.shared.u8 %0, [%1];" : "=r"(s) : "r"(sym_at + idx));
+        asm("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(len_at + (idx >> 1)));
+        *sym = s; *nbits = (b >> ((idx & 1u) * 4u)) & 15u;
+    }
+#else
+    LZ_HDM void look2(u32 hi, u32* sym, u32* nbits) const { const u32 e = look(hi); *sym = e & 255u; *nbits = e >> 8; }
     LZ_HDM u32 look(u32 hi) const
     {
         const u32 idx = hi >> down;
@@ -314,10 +339,16 @@ struct HufCompactView {          // what a segment decoder keeps in registers
         const u32 n = ((u32)t->len[idx >> 1] >> ((idx & 1u) * 4u)) & 15u;
         return s | (n << 8);
     }
+#endif
 };
 LZ_HD HufCompactView huf_view(const HufCompact* t)
 {
     HufCompactView v; v.t = t; v.down = 32 - t->tl;
+#if defined(__CUDA_ARCH__)
+    v.sym_at = (u32)__cvta_generic_to_shared(t->sym);
+    v.len_at = (u32)__cvta_generic_to_shared(t->len);
+    asm volatile("" : "+r"(v.sym_at), "+r"(v.len_at));
+#endif
     return v;
 }
 
