@@ -189,9 +189,9 @@ LZ_HD HufVec huf_vec_load(const u8* a, const u8* lo, const u8* hi)
 #endif
     return v;
 }
-LZ_HD void huf_ring_put(u32* ring, const u8* a, const HufVec& v)
+LZ_HD void huf_ring_put(u32* ring, u32 a, const HufVec& v)      // a = low address bits of the (16-byte aligned) vector
 {
-    const u32 j = ((u32)(size_t)a >> 2) & (kHufRingWords - 4);
+    const u32 j = (a >> 2) & (kHufRingWords - 4);
     ring[(j + 0) * kHufRingStride] = v.x; ring[(j + 1) * kHufRingStride] = v.y;
     ring[(j + 2) * kHufRingStride] = v.z; ring[(j + 3) * kHufRingStride] = v.w;
 }
@@ -288,24 +288,30 @@ template <bool kWide, class T> LZ_HD bool huf_lane_segment_t(u8* out, long count
         // reload, ~36 % of the kernel's stall samples (profiles/r02_SUMMARY.md, section 4).  Here a loaded register is first
         // read a round (~1000 cycles) after its load was issued, by construction.
         {
+        // loop state in 32 bits: positions relative to the start of the bitstream (`rel`, `wa`: may run below zero by less
+        // than 48), addresses by their low 32 bits (`a0` + position: all the ring mapping and the alignment need)
         const u8* const s_end = b.start + len;
-        const u8* wa = nullptr;                                   // address of the ring's lowest vector
+        const u32 a0 = (u32)(size_t)b.start;
+        int rel = (int)(b.ptr - b.start);
+        u32 used = b.used;
+        int wa = 0; bool primed = false;                          // position of the ring's lowest vector
         HufVec nx = huf_vec_zero();                               // the vector at wa - 16, in flight
-        while (p + 16 <= count && ((size_t)(out + p) & 15) == 0) {
-            if (b.ptr >= b.start + 16 && b.used <= 64) {
-                const u8* const tgt = (const u8*)(((size_t)b.ptr - 32) & ~(size_t)15);
-                if (wa == nullptr) {
-                    wa = tgt;
-                    for (u32 k = 0; k < 4; ++k) huf_ring_put(ring, wa + 16 * k, huf_vec_load(wa + 16 * k, b.start, s_end));
-                    nx = huf_vec_load(wa - 16, b.start, s_end);
+        u32 po = (u32)p; const u32 cnt = (u32)count, o0 = (u32)(size_t)out;
+        while (po + 16 <= cnt && ((o0 + po) & 15u) == 0) {
+            if (rel >= 16 && used <= 64) {
+                const int tgt = (int)(((a0 + (u32)rel - 32u) & ~15u) - a0);
+                if (!primed) {
+                    primed = true; wa = tgt;
+                    for (int k = 0; k < 4; ++k) huf_ring_put(ring, a0 + (u32)(wa + 16 * k), huf_vec_load(b.start + (wa + 16 * k), b.start, s_end));
+                    nx = huf_vec_load(b.start + (wa - 16), b.start, s_end);
                 } else {
                     while (wa > tgt) {                            // once; twice after a round of codes longer than 8 bits
                         wa -= 16;
-                        huf_ring_put(ring, wa, nx);
-                        nx = huf_vec_load(wa - 16, b.start, s_end);
+                        huf_ring_put(ring, a0 + (u32)wa, nx);
+                        nx = huf_vec_load(b.start + (wa - 16), b.start, s_end);
 #if defined(__CUDA_ARCH__)
-                        if (LZB_HUF_PREFETCH && wa >= b.start + LZB_HUF_PREFETCH && ((size_t)wa & 127) == 0)
-                            LZB_HUF_PREFETCH_ASM(wa - LZB_HUF_PREFETCH);
+                        if (LZB_HUF_PREFETCH && wa >= LZB_HUF_PREFETCH && ((a0 + (u32)wa) & 127u) == 0)
+                            LZB_HUF_PREFETCH_ASM(b.start + (wa - LZB_HUF_PREFETCH));
 #endif
                     }
                 }
@@ -316,33 +322,34 @@ template <bool kWide, class T> LZ_HD bool huf_lane_segment_t(u8* out, long count
 #pragma unroll
 #endif
             for (int q = 0; q < 4; ++q) {
-                if (r == q && b.ptr >= b.start + 16 && b.used <= 64) {
-                    b.ptr -= b.used >> 3;
-                    b.used &= 7;
-                    LZB_SHIM_CHECK(b.ptr >= wa && b.ptr + 8 <= wa + 64);
-                    const u32 a = (u32)(size_t)b.ptr, t = a >> 2, bs = (a & 3) * 8;
+                if (r == q && rel >= 16 && used <= 64) {
+                    rel -= (int)(used >> 3);
+                    used &= 7;
+                    LZB_SHIM_CHECK(rel >= wa && rel + 8 <= wa + 64);
+                    const u32 a = a0 + (u32)rel, t = a >> 2, bs = (a & 3) * 8;
                     const u32 y0 = ring[(t & 15u) * kHufRingStride], y1 = ring[((t + 1) & 15u) * kHufRingStride];
                     const u32 y2 = ring[((t + 2) & 15u) * kHufRingStride];
-                    u32 lo = fsh_r(y0, y1, bs), hi = fsh_r(y1, y2, bs);                  // the 8 bytes at b.ptr
-                    hi = fsh_l(lo, hi, b.used); lo <<= b.used;
+                    u32 lo = fsh_r(y0, y1, bs), hi = fsh_r(y1, y2, bs);                  // the 8 bytes at the read position
+                    hi = fsh_l(lo, hi, used); lo <<= used;
                     u32 s0, s1, s2, s3, n0, n1, n2, n3;
                     tab.look2(hi, &s0, &n0); hi = fsh_l(lo, hi, n0); lo <<= n0;
                     tab.look2(hi, &s1, &n1); hi = fsh_l(lo, hi, n1); lo <<= n1;
                     tab.look2(hi, &s2, &n2); hi = fsh_l(lo, hi, n2);
                     tab.look2(hi, &s3, &n3);
-                    b.used += n0 + n1 + n2 + n3;
+                    used += n0 + n1 + n2 + n3;
                     w4[q] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
                     r = q + 1;
                 }
             }
-            if (r == 4) { huf_store16(out + p, w4[0], w4[1], w4[2], w4[3]); p += 16; continue; }
+            if (r == 4) { huf_store16(out + po, w4[0], w4[1], w4[2], w4[3]); po += 16; continue; }
             // the walk reached the last 16 bytes of the bitstream inside this round: hand over what was decoded
-            if (r > 0) *reinterpret_cast<u32*>(out + p) = w4[0];
-            if (r > 1) *reinterpret_cast<u32*>(out + p + 4) = w4[1];
-            if (r > 2) *reinterpret_cast<u32*>(out + p + 8) = w4[2];
-            p += 4 * r;
+            if (r > 0) *reinterpret_cast<u32*>(out + po) = w4[0];
+            if (r > 1) *reinterpret_cast<u32*>(out + po + 4) = w4[1];
+            if (r > 2) *reinterpret_cast<u32*>(out + po + 8) = w4[2];
+            po += 4 * (u32)r;
             break;
         }
+        b.ptr = b.start + rel; b.used = used; p = (long)po;
         }
         }
         }

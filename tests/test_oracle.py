@@ -496,6 +496,49 @@ def test_prepasses_match_reference(ref, shim):
     assert expanded > 0
 
 
+def test_huffman_ring_window_misaligned_sources_and_long_codes(ref, shim):
+    """The expand pre-pass's sixteen-symbol rounds read the bitstream through an address-mapped 64-byte ring refilled once
+    per round (decode.cuh: huf_lane_segment_t<true>); the CPU shim runs the same loop with an abort on any reload that
+    would miss the ring.  Sources at every alignment mod 16, and streams whose tail is made of 10/11-bit codes (a round
+    then consumes more than 16 bytes: two refills in one round)."""
+    shim.lzb_decompress_with_prepass.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.POINTER(ctypes.c_int)]
+    rnd = random.Random(11)
+
+    def check(blk, level, mis):
+        comp = refs.ref_compress(ref, blk, level)
+        raw = ctypes.create_string_buffer(len(comp) + 32)
+        ctypes.memmove(ctypes.addressof(raw) + mis, comp, len(comp))
+        buf = ctypes.create_string_buffer(len(blk) + 64)
+        jd = ctypes.c_int(0)
+        r = shim.lzb_decompress_with_prepass(ctypes.cast(ctypes.addressof(raw) + mis, ctypes.c_char_p), len(comp), buf, len(blk),
+                                             0, ctypes.byref(jd))
+        assert r == len(blk) and buf.raw[:len(blk)] == blk, (level, len(blk), mis, r)
+        return jd.value & 15
+
+    data = lz.datagen(BS + 16)
+    jobs = 0
+    for mis in range(16):
+        jobs += check(data[mis:mis + BS], 41 if mis & 1 else 30, mis)
+
+    def skewed(n, nrare, tail):
+        common = [rnd.randrange(256) for _ in range(3)]
+        rare = rnd.sample(range(256), nrare)
+        out = bytearray()
+        cut = int(n * (1 - tail))
+        while len(out) < cut:
+            out.append(rnd.choice(common) if rnd.random() < 0.97 else rnd.choice(rare))
+        while len(out) < n:
+            out.append(rnd.choice(rare) if rnd.random() < 0.9 else rnd.choice(common))
+        return bytes(out)
+
+    for trial in range(10):
+        blk = skewed(rnd.choice([BS, 70000, 40000]), rnd.choice([60, 120, 200, 250]), rnd.choice([0.05, 0.1, 0.25]))
+        for level in (30, 41):
+            jobs += check(blk, level, trial % 16)
+    assert jobs >= 30
+
+
 def test_huffman_two_level_table_equals_reference_layout(shim):
     """The pre-pass's two-level decode table (HufCompact) answers every lookup like the 1 << tableLog table of
     HUF_readDTableX2 (huf_decompress.c:87-133), for random complete codes of every table log."""
