@@ -155,6 +155,9 @@ template <class T> LZ_HD u32 huf_step(BitReader& b, const T& tab)          // si
 #if !defined(LZB_DEC_LIT_PF_NEXT)
 #define LZB_DEC_LIT_PF_NEXT 0
 #endif
+#if !defined(LZB_DEC_LIT_PF_LOAD)
+#define LZB_DEC_LIT_PF_LOAD 0
+#endif
 // expand kernel (A/B builds): level of the optional bitstream prefetch
 #if !defined(LZB_HUF_PREFETCH_L2)
 #define LZB_HUF_PREFETCH_ASM(p) asm volatile("prefetch.global.L1 [%0];" :: "l"(p))
@@ -826,6 +829,12 @@ template <class W> LZ_HD void run_batch_copies_pool(u8* dst, const u8* lits, u32
         return;
     }
     if (act && off != 0 && off <= mdst) W::prefetch(dst + (mdst - off));
+#if defined(LZB_DEC_MATCH_PF2)
+    if (act && off != 0 && off <= mdst && ml > 1) {           // A/B: the source's last line as well, when it is another one
+        const u8* const e = dst + (mdst - off) + (ml < off ? ml : off) - 1;
+        if ((((size_t)e) ^ ((size_t)(dst + (mdst - off)))) >> 7) W::prefetch(e);
+    }
+#endif
 #if !defined(LZB_DEC_STREAM_LITS)
 #define LZB_DEC_STREAM_LITS 0      /* evict-first literal loads: measured no gain (profiles/r02_SUMMARY.md) */
 #endif
@@ -908,8 +917,23 @@ template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst,
     while (c.fp < s.nflags) {
         const u32 nb = s.nflags - c.fp < NL ? s.nflags - c.fp : NL;
         const bool act = lane < nb;
+#if LZB_DEC_LIT_PF_LOAD && defined(__CUDA_ARCH__)
+        u32 warm = 0;                                               // A/B: a real load per line instead of the prefetch hint
+        if (lane < LZB_DEC_LIT_PF_LINES && c.lp + 128 * (long)lane < nl) {
+#if LZB_DEC_LIT_PF_LOAD == 2
+            asm volatile("ld.global.L1::evict_last.u8 %0, [%1];" : "=r"(warm) : "l"(s.lits + c.lp + 128 * (long)lane));
+#else
+            asm volatile("ld.global.u8 %0, [%1];" : "=r"(warm) : "l"(s.lits + c.lp + 128 * (long)lane));
+#endif
+        }
+#else
         if ((!LZB_DEC_LIT_PF_NEXT || c.fp == 0) && lane < LZB_DEC_LIT_PF_LINES && c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane < nl)
             W::prefetch(s.lits + c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane);
+#endif
+#if defined(LZB_DEC_LIT_PF_FAR_L2) && defined(__CUDA_ARCH__)
+        if (c.lp + LZB_DEC_LIT_PF_FAR_L2 + 128 * (long)lane < nl)      // A/B: the lines of the batches after this one, into L2 only
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(s.lits + c.lp + LZB_DEC_LIT_PF_FAR_L2 + 128 * (long)lane));
+#endif
         const u32 tok = act ? s.flags[c.fp + lane] : 0;
         const u32 litn = tok & 15, mln = tok >> 4;
         const bool need = act && litn == 15;
@@ -987,6 +1011,9 @@ template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst,
             if (W::ballot(bad) == 0) {
                 LZB_COUNT_FAST(W::lane() == 0 ? nb : 0);
                 if (LZB_DEC_LIT_PF_NEXT) { const long nx = c.lp + (long)tot_adv + (long)tot_ext + 128 * (long)lane; if (lane < LZB_DEC_LIT_PF_LINES && nx < nl) W::prefetch(s.lits + nx); }
+#if LZB_DEC_LIT_PF_LOAD && defined(__CUDA_ARCH__)
+                asm volatile("" :: "r"(warm));
+#endif
                 if ((V & 1) == 0) run_batch_copies<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, sh->desc);
                 else run_batch_copies_pool<W>(dst, s.lits, nb, (u32)lit_src, lit_len, (u32)opos, off, ml, sh->desc);
                 c.fp += nb; c.lp += (long)tot_adv + (long)tot_ext; c.op += (long)tot_out;

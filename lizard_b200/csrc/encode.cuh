@@ -4,7 +4,7 @@
 // Memory placement per warp (launch shape per level: encode_shape() below):
 //   shared : the PACKED hash table (16-bit entries + a bit plane for position bit 16 + one tag byte per entry for the fast
 //            parsers: 12.5 KiB at level 10/30, 34 KiB untagged at 20/21/40/41) for as many of a CTA's 14 warps as the
-//            measured shape gives one (7 at level 10, 3 at 30, 2 at 20/21, 0 at 40/41), + 4 KiB of per-segment byte
+//            measured shape gives one (3 at levels 10 and 30, 2 at 20/21, 0 at 40/41), + 4 KiB of per-segment byte
 //            histograms for the Huffman stage
 //   global : for the other warps the plain 32-bit table in their scratch (tags in the spare bits of an entry; 16 KiB at
 //            hashLog 12, 64 KiB at 14, 1 MiB at 18 or for multi-inner-block units), the sequence list of the block being
@@ -247,7 +247,9 @@ inline EncodeShape encode_shape(const LevelParams& lp)
     if (tabs14 < 0) tabs14 = fit14 < 0 ? -1 : 0;
     int solo = 0;                                                   // shape B: resident single-warp CTAs
     for (int ctas = kEncMaxWarpsPerSM; ctas >= 1; --ctas) if (tabs_for(1, ctas, sm_max) >= (sh.table_bytes ? 1 : 0)) { solo = ctas; break; }
-    if (!sh.table_bytes || fit14 >= 8) set(kEncWarpsPerCta, tabs14 < 0 ? 0 : tabs14, kEncCtasPerSM);
+    // shape A's small tables: a few in shared memory are enough, the rest of the array serves better as L1 (B200, 1 GiB,
+    // level 10: 14,7,2 8.69 ms; 14,5,2 8.48; 14,4,2 8.54; 14,3,2 8.48; 14,2,2 8.49; profiles/r02_SUMMARY.md section 5)
+    if (!sh.table_bytes || fit14 >= 8) set(kEncWarpsPerCta, tabs14 < 0 ? 0 : (tabs14 > 3 ? 3 : tabs14), kEncCtasPerSM);
     else if (solo >= 16) set(1, 1, solo);
     // large tables next to the entropy stage's histograms (levels 40-42): the one table that would still fit costs the other
     // thirteen warps more L1 than it saves (B200, 1 GiB, level 41: 14,0,2 36.5 ms, 14,1,2 38.8 ms; profiles/r02_SUMMARY.md)

@@ -139,7 +139,7 @@ def test_encoder_launch_shapes_are_the_measured_ones():
     """The per-level launch shapes were picked from sweeps on the B200 (profiles/r01_SUMMARY.md section 8); a refactoring of
     encode_shape() must not move them silently.  (warps per CTA, shared-memory tables per CTA, CTAs per SM)"""
     L = lz.lib()
-    want = {10: (14, 7, 2), 30: (14, 3, 2), 11: (14, 0, 2), 31: (14, 0, 2), 21: (14, 2, 2), 22: (14, 0, 2), 41: (14, 0, 2), 20: (14, 2, 2), 40: (14, 0, 2),
+    want = {10: (14, 3, 2), 30: (14, 3, 2), 11: (14, 0, 2), 31: (14, 0, 2), 21: (14, 2, 2), 22: (14, 0, 2), 41: (14, 0, 2), 20: (14, 2, 2), 40: (14, 0, 2),
             13: (14, 0, 2), 17: (14, 0, 2), 34: (14, 0, 2)}
     for level, shape in want.items():
         w, t, k, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
