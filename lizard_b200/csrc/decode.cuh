@@ -91,7 +91,8 @@ struct DecWarpCore {               // per-warp shared memory every decoder gener
                                    // warp in shared memory for the rest would cost the token loops their L1)
     union {
         HufStatsScratch stats;                       // while a Huffman header is being read
-        struct { u32 ent[32]; u32 epre[32]; } chain; // during the token loops: length-extension chain of a batch
+        struct { u32 ent[32]; u32 epre[32]; u32 vl[32]; u32 vm[32]; } chain;   // during the token loops: length-extension
+                                                     // chain of a batch (vl / vm: value | size << 24 of an entry's two fields)
     };
     u8  weights[256];
     u32 rank[kHufTableLogMax + 1];
@@ -906,6 +907,79 @@ template <class W> LZ_HD bool ext_chain(const u8* lits, long nl, long lp, u32 np
     return true;
 }
 
+// ---- the same chain through a shared-memory window of the literals stream ------------------------------------------
+// The chain is a pointer chase: ~28 dependent one-byte loads per batch, each an L2 round trip (~370 cycles measured: the
+// lines are not in an L1 that 32 resident warps share).  Here the warp copies 1 KiB of the stream -- from the 16-byte
+// aligned address at or below the position the chain has reached -- into shared memory with two coalesced vector loads per
+// lane and walks on from there; a batch needs ~3 windows.  The window lives in the batch's copy descriptors, which are only
+// written after the chain.  The fields' values are handed to the lanes through vl / vm (value | size << 24), so that no
+// lane goes back to the stream for them.
+#if !defined(LZB_DEC_CHAIN_WIN)
+#define LZB_DEC_CHAIN_WIN 1
+#endif
+enum : u32 { kChainWinBytes = 1024 };
+struct LitWin { u8* buf; long lo, hi; };          // stream positions [lo, hi) are buf[0, hi - lo)
+template <class W> LZ_HD void litwin_stage(LitWin& w, const u8* lits, long nl, long p)
+{
+    const long lo = p - (long)((size_t)(lits + p) & 15);
+    W::sync();                                                  // the previous window's readers are done
+    for (u32 c = W::lane(); c < kChainWinBytes / 16; c += W::lanes()) {
+        const long cp = lo + 16 * (long)c;
+        if (cp >= nl) continue;                                 // chunks wholly behind the stream are never read
+#if defined(__CUDA_ARCH__)
+        // an aligned chunk that holds a byte of the stream lies inside the stream's allocation
+        *reinterpret_cast<uint4*>(w.buf + 16 * c) = *reinterpret_cast<const uint4*>(lits + cp);
+#else
+        for (long i = 0; i < 16; ++i) w.buf[16 * c + i] = (cp + i >= 0 && cp + i < nl) ? lits[cp + i] : 0;
+#endif
+    }
+    W::sync();
+    w.lo = lo; w.hi = lo + (long)kChainWinBytes;
+}
+// ext_field through the window (p is the same in every lane)
+template <class W> LZ_HD bool litwin_field(LitWin& w, const u8* lits, long nl, long p, u32* v, u32* size)
+{
+    if (p >= nl) return false;
+    if (p < w.lo || p + 4 > w.hi) litwin_stage<W>(w, lits, nl, p);
+    const u8* q = w.buf + (p - w.lo);
+    const u32 b = q[0];
+    if (b < 254) { *v = b; *size = 1; return true; }
+    const u32 sz = b == 254 ? 3u : 4u;
+    if (p + (long)sz > nl) return false;
+    *v = b == 254 ? rd_le16(q + 1) : rd_le24(q + 1);
+    *size = sz;
+    return true;
+}
+template <class W> LZ_HD bool ext_chain_win(const u8* lits, long nl, long lp, u32 npend, const u32* ent, u32* epre, u32* vl, u32* vm,
+                                            u8* win_buf, u32 lbias, long room, u32 gap, u32* total)
+{
+    LitWin w; w.buf = win_buf; w.lo = 0; w.hi = 0;
+    u32 E = 0;
+    for (u32 j = 0; j < npend; ++j) {
+        const u32 e = ent[j];
+        const long base = lp + (long)(e & 0xffffu) + (long)E;
+        u32 xl = 0, xm = 0;
+        const u32 E0 = E;
+        long pm;
+        if (e & (1u << 24)) {
+            u32 v, sz;
+            if (base > nl - room || !litwin_field<W>(w, lits, nl, base, &v, &sz)) return false;
+            E += lbias + v + (sz - 1);
+            pm = base + (long)sz + (long)(lbias + v) + (long)gap;
+            xl = v | (sz << 24);
+        } else pm = base + (long)((e >> 16) & 255u) + (long)gap;
+        if (e & (1u << 25)) {
+            u32 v, sz;
+            if (pm > nl - room || !litwin_field<W>(w, lits, nl, pm, &v, &sz)) return false;
+            E += sz - 1;
+            xm = v | (sz << 24);
+        }
+        if (W::lane() == 0) { epre[j] = E0; vl[j] = xl; vm[j] = xm; }
+    }
+    *total = E;
+    return true;
+}
+
 // fastLZ4 codewords (lib/lizard_decompress_lz4.h:7-163).  `op0` is the offset inside the unit's output,
 // `oend` the unit's capacity; matches may reach back to offset 0 of the unit.
 template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst, u32 op0, u32 oend_u, DecWarpShared* sh)
@@ -978,6 +1052,16 @@ template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst,
             const u32 npend = popc32(pendmask), myidx = popc32(pendmask & ((1u << lane) - 1));
             if (need || needm) sh->chain.ent[myidx] = A | (litn << 16) | (need ? 1u << 24 : 0u) | (needm ? 1u << 25 : 0u);
             W::sync();
+            if (LZB_DEC_CHAIN_WIN) {
+                slow = !ext_chain_win<W>(s.lits, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, sh->chain.vl, sh->chain.vm,
+                                         reinterpret_cast<u8*>(sh->desc), 15, 5, 2, &tot_ext);
+                W::sync();                                      // the window is the copy descriptors' memory: all lanes are done with it
+                if (!slow) {
+                    tokpos = c.lp + (long)A + (long)(myidx < npend ? sh->chain.epre[myidx] : tot_ext);
+                    if (need) { const u32 x = sh->chain.vl[myidx]; my_lit = 15 + (x & 0xffffffu); my_lx = x >> 24; }
+                    if (needm) { const u32 x = sh->chain.vm[myidx]; my_mlv = x & 0xffffffu; my_mx = x >> 24; }
+                }
+            } else {
             slow = !ext_chain<W>(s.lits, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, 15, 5, 2, &tot_ext);
             if (!slow) {
                 W::sync();
@@ -985,6 +1069,7 @@ template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst,
                 // every lane reads its own fields (the chain has checked that they are inside the stream)
                 if (need) { u32 v = 0, sz = 1; ext_field(s.lits, nl, tokpos, &v, &sz); my_lit = 15 + v; my_lx = sz; }
                 if (needm) { u32 v = 0, sz = 1; ext_field(s.lits, nl, tokpos + (need ? (long)(my_lx + my_lit) : (long)litn) + 2, &v, &sz); my_mlv = v; my_mx = sz; }
+            }
             }
         }
         if (!slow) {
@@ -1091,12 +1176,23 @@ template <class W, int V> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* ds
             const u32 npend = popc32(pendmask), myidx = popc32(pendmask & ((1u << lane) - 1));
             if (need || mlext) sh->chain.ent[myidx] = A | (litn << 16) | (need ? 1u << 24 : 0u) | (mlext ? 1u << 25 : 0u);
             W::sync();
+            if (LZB_DEC_CHAIN_WIN) {
+                slow = !ext_chain_win<W>(s.lits, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, sh->chain.vl, sh->chain.vm,
+                                         reinterpret_cast<u8*>(sh->desc), 7, 1, 0, &tot_ext);
+                W::sync();
+                if (!slow) {
+                    tokpos = c.lp + (long)A + (long)(myidx < npend ? sh->chain.epre[myidx] : tot_ext);
+                    if (need) { const u32 x = sh->chain.vl[myidx]; my_lit = 7 + (x & 0xffffffu); my_lx = x >> 24; }
+                    if (mlext) { const u32 x = sh->chain.vm[myidx]; my_mlv = x & 0xffffffu; my_mx = x >> 24; }
+                }
+            } else {
             slow = !ext_chain<W>(s.lits, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, 7, 1, 0, &tot_ext);
             if (!slow) {
                 W::sync();
                 tokpos = c.lp + (long)A + (long)(myidx < npend ? sh->chain.epre[myidx] : tot_ext);
                 if (need) { u32 v = 0, sz = 1; ext_field(s.lits, nl, tokpos, &v, &sz); my_lit = 7 + v; my_lx = sz; }
                 if (mlext) { u32 v = 0, sz = 1; ext_field(s.lits, nl, tokpos + (need ? (long)(my_lx + my_lit) : (long)litn), &v, &sz); my_mlv = v; my_mx = sz; }
+            }
             }
         }
         if (!slow) {
