@@ -37,6 +37,9 @@ lizard_decode_units_kernel(DecodeBatch b)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     DecWarpShared* sh = reinterpret_cast<DecWarpShared*>(smem_raw) + warp;
+#if defined(LZB_DEC_SH_OPAQUE)
+    asm volatile("" : "+l"(sh));                 // A/B: one register for the warp's block instead of re-deriving it per access (generic loads then)
+#endif
     const size_t gwarp = (size_t)blockIdx.x * kDecWarps + warp;
     u8* scratch = b.scratch + gwarp * kDecScratchPerWarp;
     if (lane == 0) sh->big_table = reinterpret_cast<u16*>(scratch + 4 * kDecStreamScratch);

@@ -85,14 +85,16 @@ enum : u32 { kDecStreamScratch = kBlockSize + 64, kDecBigTableBytes = 2u << kHuf
 
 typedef PoolRun SeqDesc;                          // 16-byte sequence descriptor (see run_batch_copies)
 
+struct alignas(16) ChainRec { u32 ent, epre, vl, vm; };   // list entry, bytes of extension data before it, value | size << 24 of its two fields
+
 struct DecWarpCore {               // per-warp shared memory every decoder generation needs
     u16* big_table;                // single-symbol table of the in-kernel Huffman expansion: 2^12 entries in the warp's
                                    // global scratch (the pre-pass expands the streams of real batches; keeping 4 KiB per
                                    // warp in shared memory for the rest would cost the token loops their L1)
     union {
         HufStatsScratch stats;                       // while a Huffman header is being read
-        struct { u32 ent[32]; u32 epre[32]; u32 vl[32]; u32 vm[32]; } chain;   // during the token loops: length-extension
-                                                     // chain of a batch (vl / vm: value | size << 24 of an entry's two fields)
+        struct { u32 ent[32]; u32 epre[32]; } chain; // during the token loops: length-extension chain of a batch
+        ChainRec chainw[32];                         // the same for the windowed chain (ext_chain_win)
     };
     u8  weights[256];
     u32 rank[kHufTableLogMax + 1];
@@ -912,69 +914,137 @@ template <class W> LZ_HD bool ext_chain(const u8* lits, long nl, long lp, u32 np
 // lines are not in an L1 that 32 resident warps share).  Here the warp copies 1 KiB of the stream -- from the 16-byte
 // aligned address at or below the position the chain has reached -- into shared memory with two coalesced vector loads per
 // lane and walks on from there; a batch needs ~3 windows.  The window lives in the batch's copy descriptors, which are only
-// written after the chain.  The fields' values are handed to the lanes through vl / vm (value | size << 24), so that no
-// lane goes back to the stream for them.
+// written after the chain.  An entry's results go back through its record (one 16-byte store by lane 0, one 16-byte load
+// by the entry's lane), so that no lane returns to the stream for its fields.  Everything is 32-bit: stream positions,
+// and addresses by their low bits (`a0` + position), which is all the window mapping needs.
 #if !defined(LZB_DEC_CHAIN_WIN)
 #define LZB_DEC_CHAIN_WIN 1
 #endif
 enum : u32 { kChainWinBytes = 1024 };
-struct LitWin { u8* buf; long lo, hi; };          // stream positions [lo, hi) are buf[0, hi - lo)
-template <class W> LZ_HD void litwin_stage(LitWin& w, const u8* lits, long nl, long p)
+struct ChainMem {                 // the chain's shared memory: 32-bit shared-space addresses on the device (kept opaque: the
+#if defined(__CUDA_ARCH__)        // compiler otherwise re-derives "block base + warp * size" in front of every access)
+    u32 rec_at, win_at;
+#else
+    ChainRec* rec; u8* win;
+#endif
+};
+LZ_HD ChainMem chain_mem(ChainRec* rec, void* win)
 {
-    const long lo = p - (long)((size_t)(lits + p) & 15);
+    ChainMem m;
+#if defined(__CUDA_ARCH__)
+    m.rec_at = (u32)__cvta_generic_to_shared(rec); m.win_at = (u32)__cvta_generic_to_shared(win);
+    asm volatile("" : "+r"(m.rec_at), "+r"(m.win_at));
+#else
+    m.rec = rec; m.win = (u8*)win;
+#endif
+    return m;
+}
+LZ_HD void chain_set_ent(const ChainMem& m, u32 j, u32 ent)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(m.rec_at + 16 * j), "r"(ent) : "memory");
+#else
+    m.rec[j].ent = ent;
+#endif
+}
+LZ_HD u32 chain_ent(const ChainMem& m, u32 j)
+{
+#if defined(__CUDA_ARCH__)
+    u32 e; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(m.rec_at + 16 * j) : "memory"); return e;
+#else
+    return m.rec[j].ent;
+#endif
+}
+LZ_HD void chain_put(const ChainMem& m, u32 j, u32 ent, u32 epre, u32 vl, u32 vm)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(m.rec_at + 16 * j), "r"(ent), "r"(epre), "r"(vl), "r"(vm) : "memory");
+#else
+    m.rec[j].ent = ent; m.rec[j].epre = epre; m.rec[j].vl = vl; m.rec[j].vm = vm;
+#endif
+}
+LZ_HD ChainRec chain_get(const ChainMem& m, u32 j)
+{
+    ChainRec r;
+#if defined(__CUDA_ARCH__)
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.ent), "=r"(r.epre), "=r"(r.vl), "=r"(r.vm) : "r"(m.rec_at + 16 * j) : "memory");
+#else
+    r = m.rec[j];
+#endif
+    return r;
+}
+LZ_HD u32 chain_win_byte(const ChainMem& m, u32 off)
+{
+#if defined(__CUDA_ARCH__)
+    u32 b; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(b) : "r"(m.win_at + off) : "memory"); return b;
+#else
+    return m.win[off];
+#endif
+}
+// copy 1 KiB of the stream, from the 16-byte aligned address at or below position p, into the window; returns that address
+// (low bits)
+template <class W> LZ_HD u32 chain_win_stage(const ChainMem& m, const u8* lits, u32 nl, u32 a0, u32 p)
+{
+    const u32 d = (a0 + p) & 15u;
+    const int cp0 = (int)p - (int)d;                            // stream position of the window's first byte (>= -15)
     W::sync();                                                  // the previous window's readers are done
     for (u32 c = W::lane(); c < kChainWinBytes / 16; c += W::lanes()) {
-        const long cp = lo + 16 * (long)c;
-        if (cp >= nl) continue;                                 // chunks wholly behind the stream are never read
+        const int cp = cp0 + 16 * (int)c;
+        if (cp >= (int)nl) continue;                            // chunks wholly behind the stream are never read
 #if defined(__CUDA_ARCH__)
         // an aligned chunk that holds a byte of the stream lies inside the stream's allocation
-        *reinterpret_cast<uint4*>(w.buf + 16 * c) = *reinterpret_cast<const uint4*>(lits + cp);
+        const uint4 v = *reinterpret_cast<const uint4*>(lits + cp);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(m.win_at + 16 * c), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 #else
-        for (long i = 0; i < 16; ++i) w.buf[16 * c + i] = (cp + i >= 0 && cp + i < nl) ? lits[cp + i] : 0;
+        for (int i = 0; i < 16; ++i) m.win[16 * c + i] = (cp + i >= 0 && cp + i < (int)nl) ? lits[cp + i] : 0;
 #endif
     }
     W::sync();
-    w.lo = lo; w.hi = lo + (long)kChainWinBytes;
+    return a0 + p - d;
 }
-// ext_field through the window (p is the same in every lane)
-template <class W> LZ_HD bool litwin_field(LitWin& w, const u8* lits, long nl, long p, u32* v, u32* size)
+// ext_field through the window (p is the same in every lane, p < nl); `wa` = the window's first address (low bits)
+template <class W> LZ_HD bool chain_win_field(const ChainMem& m, const u8* lits, u32 nl, u32 a0, u32& wa, u32 p, u32* v, u32* size)
 {
-    if (p >= nl) return false;
-    if (p < w.lo || p + 4 > w.hi) litwin_stage<W>(w, lits, nl, p);
-    const u8* q = w.buf + (p - w.lo);
-    const u32 b = q[0];
+    u32 off = a0 + p - wa;
+    if (off > kChainWinBytes - 4) { wa = chain_win_stage<W>(m, lits, nl, a0, p); off = a0 + p - wa; }
+    const u32 b = chain_win_byte(m, off);
     if (b < 254) { *v = b; *size = 1; return true; }
     const u32 sz = b == 254 ? 3u : 4u;
-    if (p + (long)sz > nl) return false;
-    *v = b == 254 ? rd_le16(q + 1) : rd_le24(q + 1);
-    *size = sz;
+    if (p + sz > nl) return false;
+    u32 x = chain_win_byte(m, off + 1) | (chain_win_byte(m, off + 2) << 8);
+    if (b == 255) x |= chain_win_byte(m, off + 3) << 16;
+    *v = x; *size = sz;
     return true;
 }
-template <class W> LZ_HD bool ext_chain_win(const u8* lits, long nl, long lp, u32 npend, const u32* ent, u32* epre, u32* vl, u32* vm,
-                                            u8* win_buf, u32 lbias, long room, u32 gap, u32* total)
+template <class W> LZ_HD bool ext_chain_win(const u8* lits, u32 nl, u32 lp, u32 npend, const ChainMem& m,
+                                            u32 lbias, u32 room, u32 gap, u32* total)
 {
-    LitWin w; w.buf = win_buf; w.lo = 0; w.hi = 0;
+    *total = 0;
+    if (npend == 0) return true;
+    if (nl < room) return false;                                // no field fits
+    const u32 limit = nl - room;                                // last position a field may start at
+    const u32 a0 = (u32)(size_t)lits;
+    u32 wa = (a0 & ~15u) ^ 0x80000000u;                         // no position of the stream is inside this window
     u32 E = 0;
     for (u32 j = 0; j < npend; ++j) {
-        const u32 e = ent[j];
-        const long base = lp + (long)(e & 0xffffu) + (long)E;
-        u32 xl = 0, xm = 0;
+        const u32 e = chain_ent(m, j);
+        const u32 base = lp + (e & 0xffffu) + E;
         const u32 E0 = E;
-        long pm;
+        u32 xl = 0, xm = 0, pm;
         if (e & (1u << 24)) {
             u32 v, sz;
-            if (base > nl - room || !litwin_field<W>(w, lits, nl, base, &v, &sz)) return false;
+            if (base > limit || !chain_win_field<W>(m, lits, nl, a0, wa, base, &v, &sz)) return false;
             E += lbias + v + (sz - 1);
-            pm = base + (long)sz + (long)(lbias + v) + (long)gap;
+            pm = base + sz + lbias + v + gap;
             xl = v | (sz << 24);
-        } else pm = base + (long)((e >> 16) & 255u) + (long)gap;
+        } else pm = base + ((e >> 16) & 255u) + gap;
         if (e & (1u << 25)) {
             u32 v, sz;
-            if (pm > nl - room || !litwin_field<W>(w, lits, nl, pm, &v, &sz)) return false;
+            if (pm > limit || !chain_win_field<W>(m, lits, nl, a0, wa, pm, &v, &sz)) return false;
             E += sz - 1;
             xm = v | (sz << 24);
         }
-        if (W::lane() == 0) { epre[j] = E0; vl[j] = xl; vm[j] = xm; }
+        if (W::lane() == 0) chain_put(m, j, e, E0, xl, xm);
     }
     *total = E;
     return true;
@@ -1050,18 +1120,22 @@ template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst,
         } else {
             const u32 pendmask = W::ballot(need || needm);
             const u32 npend = popc32(pendmask), myidx = popc32(pendmask & ((1u << lane) - 1));
-            if (need || needm) sh->chain.ent[myidx] = A | (litn << 16) | (need ? 1u << 24 : 0u) | (needm ? 1u << 25 : 0u);
-            W::sync();
             if (LZB_DEC_CHAIN_WIN) {
-                slow = !ext_chain_win<W>(s.lits, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, sh->chain.vl, sh->chain.vm,
-                                         reinterpret_cast<u8*>(sh->desc), 15, 5, 2, &tot_ext);
+                const ChainMem cm = chain_mem(sh->chainw, sh->desc);
+                if (need || needm) chain_set_ent(cm, myidx, A | (litn << 16) | (need ? 1u << 24 : 0u) | (needm ? 1u << 25 : 0u));
+                W::sync();
+                slow = !ext_chain_win<W>(s.lits, (u32)nl, (u32)c.lp, npend, cm, 15, 5, 2, &tot_ext);
                 W::sync();                                      // the window is the copy descriptors' memory: all lanes are done with it
                 if (!slow) {
-                    tokpos = c.lp + (long)A + (long)(myidx < npend ? sh->chain.epre[myidx] : tot_ext);
-                    if (need) { const u32 x = sh->chain.vl[myidx]; my_lit = 15 + (x & 0xffffffu); my_lx = x >> 24; }
-                    if (needm) { const u32 x = sh->chain.vm[myidx]; my_mlv = x & 0xffffffu; my_mx = x >> 24; }
+                    ChainRec r; r.epre = tot_ext; r.vl = r.vm = 0;
+                    if (myidx < npend) r = chain_get(cm, myidx);
+                    tokpos = c.lp + (long)A + (long)r.epre;
+                    if (need) { my_lit = 15 + (r.vl & 0xffffffu); my_lx = r.vl >> 24; }
+                    if (needm) { my_mlv = r.vm & 0xffffffu; my_mx = r.vm >> 24; }
                 }
             } else {
+            if (need || needm) sh->chain.ent[myidx] = A | (litn << 16) | (need ? 1u << 24 : 0u) | (needm ? 1u << 25 : 0u);
+            W::sync();
             slow = !ext_chain<W>(s.lits, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, 15, 5, 2, &tot_ext);
             if (!slow) {
                 W::sync();
@@ -1174,18 +1248,22 @@ template <class W, int V> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* ds
         } else {
             const u32 pendmask = W::ballot(need || mlext);
             const u32 npend = popc32(pendmask), myidx = popc32(pendmask & ((1u << lane) - 1));
-            if (need || mlext) sh->chain.ent[myidx] = A | (litn << 16) | (need ? 1u << 24 : 0u) | (mlext ? 1u << 25 : 0u);
-            W::sync();
             if (LZB_DEC_CHAIN_WIN) {
-                slow = !ext_chain_win<W>(s.lits, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, sh->chain.vl, sh->chain.vm,
-                                         reinterpret_cast<u8*>(sh->desc), 7, 1, 0, &tot_ext);
+                const ChainMem cm = chain_mem(sh->chainw, sh->desc);
+                if (need || mlext) chain_set_ent(cm, myidx, A | (litn << 16) | (need ? 1u << 24 : 0u) | (mlext ? 1u << 25 : 0u));
+                W::sync();
+                slow = !ext_chain_win<W>(s.lits, (u32)nl, (u32)c.lp, npend, cm, 7, 1, 0, &tot_ext);
                 W::sync();
                 if (!slow) {
-                    tokpos = c.lp + (long)A + (long)(myidx < npend ? sh->chain.epre[myidx] : tot_ext);
-                    if (need) { const u32 x = sh->chain.vl[myidx]; my_lit = 7 + (x & 0xffffffu); my_lx = x >> 24; }
-                    if (mlext) { const u32 x = sh->chain.vm[myidx]; my_mlv = x & 0xffffffu; my_mx = x >> 24; }
+                    ChainRec r; r.epre = tot_ext; r.vl = r.vm = 0;
+                    if (myidx < npend) r = chain_get(cm, myidx);
+                    tokpos = c.lp + (long)A + (long)r.epre;
+                    if (need) { my_lit = 7 + (r.vl & 0xffffffu); my_lx = r.vl >> 24; }
+                    if (mlext) { my_mlv = r.vm & 0xffffffu; my_mx = r.vm >> 24; }
                 }
             } else {
+            if (need || mlext) sh->chain.ent[myidx] = A | (litn << 16) | (need ? 1u << 24 : 0u) | (mlext ? 1u << 25 : 0u);
+            W::sync();
             slow = !ext_chain<W>(s.lits, nl, c.lp, npend, sh->chain.ent, sh->chain.epre, 7, 1, 0, &tot_ext);
             if (!slow) {
                 W::sync();
