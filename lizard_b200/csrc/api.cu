@@ -23,6 +23,9 @@ using namespace lzb;
 
 namespace {
 
+#if !defined(LZB_DEC_SH_OPAQUE)
+#define LZB_DEC_SH_OPAQUE 1
+#endif
 #if !defined(LZB_DEC_WARPS)
 #define LZB_DEC_WARPS 8
 #endif
@@ -37,8 +40,11 @@ lizard_decode_units_kernel(DecodeBatch b)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     DecWarpShared* sh = reinterpret_cast<DecWarpShared*>(smem_raw) + warp;
-#if defined(LZB_DEC_SH_OPAQUE)
-    asm volatile("" : "+l"(sh));                 // A/B: one register for the warp's block instead of re-deriving it per access (generic loads then)
+#if LZB_DEC_SH_OPAQUE
+    // one register for the warp's block: left to itself the compiler re-derives `base + warp * size` in front of every access
+    // (10 % of the kernel's instructions); the price is generic instead of shared-space loads.  B200, 1 GiB, level 10: 1.495 ms
+    // against 1.501; level 21: 2.432 against 2.497 (profiles/r02_SUMMARY.md section 6)
+    asm volatile("" : "+l"(sh));
 #endif
     const size_t gwarp = (size_t)blockIdx.x * kDecWarps + warp;
     u8* scratch = b.scratch + gwarp * kDecScratchPerWarp;

@@ -982,31 +982,37 @@ LZ_HD u32 chain_win_byte(const ChainMem& m, u32 off)
 #endif
 }
 // copy 1 KiB of the stream, from the 16-byte aligned address at or below position p, into the window; returns that address
-// (low bits)
-template <class W> LZ_HD u32 chain_win_stage(const ChainMem& m, const u8* lits, u32 nl, u32 a0, u32 p)
+// (low bits).  Two halves: `issue` starts the copy (cp.async: no registers, the data goes from L1/L2 straight to shared
+// memory) and `wait` makes it visible to the warp, so that the first window of a batch travels while the batch's scans run.
+template <class W> LZ_HD u32 chain_win_issue(const ChainMem& m, const u8* lits, u32 nl, u32 a0, u32 p)
 {
     const u32 d = (a0 + p) & 15u;
     const int cp0 = (int)p - (int)d;                            // stream position of the window's first byte (>= -15)
-    W::sync();                                                  // the previous window's readers are done
+    W::sync();                                                  // whoever read this memory before is done
     for (u32 c = W::lane(); c < kChainWinBytes / 16; c += W::lanes()) {
         const int cp = cp0 + 16 * (int)c;
         if (cp >= (int)nl) continue;                            // chunks wholly behind the stream are never read
 #if defined(__CUDA_ARCH__)
         // an aligned chunk that holds a byte of the stream lies inside the stream's allocation
-        const uint4 v = *reinterpret_cast<const uint4*>(lits + cp);
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" :: "r"(m.win_at + 16 * c), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(m.win_at + 16 * c), "l"(lits + cp) : "memory");
 #else
         for (int i = 0; i < 16; ++i) m.win[16 * c + i] = (cp + i >= 0 && cp + i < (int)nl) ? lits[cp + i] : 0;
 #endif
     }
-    W::sync();
     return a0 + p - d;
+}
+template <class W> LZ_HD void chain_win_wait()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+    W::sync();
 }
 // ext_field through the window (p is the same in every lane, p < nl); `wa` = the window's first address (low bits)
 template <class W> LZ_HD bool chain_win_field(const ChainMem& m, const u8* lits, u32 nl, u32 a0, u32& wa, u32 p, u32* v, u32* size)
 {
     u32 off = a0 + p - wa;
-    if (off > kChainWinBytes - 4) { wa = chain_win_stage<W>(m, lits, nl, a0, p); off = a0 + p - wa; }
+    if (off > kChainWinBytes - 4) { wa = chain_win_issue<W>(m, lits, nl, a0, p); chain_win_wait<W>(); off = a0 + p - wa; }
     const u32 b = chain_win_byte(m, off);
     if (b < 254) { *v = b; *size = 1; return true; }
     const u32 sz = b == 254 ? 3u : 4u;
@@ -1016,15 +1022,16 @@ template <class W> LZ_HD bool chain_win_field(const ChainMem& m, const u8* lits,
     *v = x; *size = sz;
     return true;
 }
-template <class W> LZ_HD bool ext_chain_win(const u8* lits, u32 nl, u32 lp, u32 npend, const ChainMem& m,
+// `wa`: first address (low bits) of the window the caller has issued for this batch (chain_win_issue at position lp)
+template <class W> LZ_HD bool ext_chain_win(const u8* lits, u32 nl, u32 lp, u32 npend, const ChainMem& m, u32 wa,
                                             u32 lbias, u32 room, u32 gap, u32* total)
 {
     *total = 0;
+    chain_win_wait<W>();                                        // also orders the lanes' entries before the walk
     if (npend == 0) return true;
     if (nl < room) return false;                                // no field fits
     const u32 limit = nl - room;                                // last position a field may start at
     const u32 a0 = (u32)(size_t)lits;
-    u32 wa = (a0 & ~15u) ^ 0x80000000u;                         // no position of the stream is inside this window
     u32 E = 0;
     for (u32 j = 0; j < npend; ++j) {
         const u32 e = chain_ent(m, j);
@@ -1078,6 +1085,9 @@ template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst,
         if (c.lp + LZB_DEC_LIT_PF_FAR_L2 + 128 * (long)lane < nl)      // A/B: the lines of the batches after this one, into L2 only
             asm volatile("prefetch.global.L2 [%0];" :: "l"(s.lits + c.lp + LZB_DEC_LIT_PF_FAR_L2 + 128 * (long)lane));
 #endif
+        const ChainMem cm = chain_mem(sh->chainw, sh->desc);
+        u32 cwa = 0;
+        if (LZB_DEC_CHAIN_WIN && (V & 2) != 0) cwa = chain_win_issue<W>(cm, s.lits, (u32)nl, (u32)(size_t)s.lits, (u32)c.lp);
         const u32 tok = act ? s.flags[c.fp + lane] : 0;
         const u32 litn = tok & 15, mln = tok >> 4;
         const bool need = act && litn == 15;
@@ -1121,10 +1131,8 @@ template <class W, int V> LZ_HD int decode_tokens_lz4(const Streams& s, u8* dst,
             const u32 pendmask = W::ballot(need || needm);
             const u32 npend = popc32(pendmask), myidx = popc32(pendmask & ((1u << lane) - 1));
             if (LZB_DEC_CHAIN_WIN) {
-                const ChainMem cm = chain_mem(sh->chainw, sh->desc);
                 if (need || needm) chain_set_ent(cm, myidx, A | (litn << 16) | (need ? 1u << 24 : 0u) | (needm ? 1u << 25 : 0u));
-                W::sync();
-                slow = !ext_chain_win<W>(s.lits, (u32)nl, (u32)c.lp, npend, cm, 15, 5, 2, &tot_ext);
+                slow = !ext_chain_win<W>(s.lits, (u32)nl, (u32)c.lp, npend, cm, cwa, 15, 5, 2, &tot_ext);
                 W::sync();                                      // the window is the copy descriptors' memory: all lanes are done with it
                 if (!slow) {
                     ChainRec r; r.epre = tot_ext; r.vl = r.vm = 0;
@@ -1204,6 +1212,9 @@ template <class W, int V> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* ds
         const bool act = lane < nb;
         if ((!LZB_DEC_LIT_PF_NEXT || c.fp == 0) && lane < LZB_DEC_LIT_PF_LINES && c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane < nl)
             W::prefetch(s.lits + c.lp + LZB_DEC_LIT_PF_DIST + 128 * (long)lane);
+        const ChainMem cm = chain_mem(sh->chainw, sh->desc);
+        u32 cwa = 0;
+        if (LZB_DEC_CHAIN_WIN && (V & 2) != 0) cwa = chain_win_issue<W>(cm, s.lits, (u32)nl, (u32)(size_t)s.lits, (u32)c.lp);
         const u32 tok = act ? s.flags[c.fp + lane] : 32;           // inactive lanes: an empty short token
         const bool shortf = tok >= 32;                              // [r_MMMM_LLL] with a 16-bit or repeated offset
         const u32 litn = shortf ? (tok & 7) : 0;
@@ -1249,10 +1260,8 @@ template <class W, int V> LZ_HD int decode_tokens_lizv1(const Streams& s, u8* ds
             const u32 pendmask = W::ballot(need || mlext);
             const u32 npend = popc32(pendmask), myidx = popc32(pendmask & ((1u << lane) - 1));
             if (LZB_DEC_CHAIN_WIN) {
-                const ChainMem cm = chain_mem(sh->chainw, sh->desc);
                 if (need || mlext) chain_set_ent(cm, myidx, A | (litn << 16) | (need ? 1u << 24 : 0u) | (mlext ? 1u << 25 : 0u));
-                W::sync();
-                slow = !ext_chain_win<W>(s.lits, (u32)nl, (u32)c.lp, npend, cm, 7, 1, 0, &tot_ext);
+                slow = !ext_chain_win<W>(s.lits, (u32)nl, (u32)c.lp, npend, cm, cwa, 7, 1, 0, &tot_ext);
                 W::sync();
                 if (!slow) {
                     ChainRec r; r.epre = tot_ext; r.vl = r.vm = 0;
