@@ -200,6 +200,10 @@ int LizardB200_gather_device(const void* dSrc, const uint64_t* dSrcOff, const in
  * keep their hash table in shared memory, CTAs per SM, dynamic shared memory per CTA.  LIZARDB200_ERR_LEVEL for levels
  * whose parser is not implemented. */
 int LizardB200_encodeShape(int compressionLevel, int* warpsPerCta, int* smemTables, int* ctasPerSM, int* smemBytes);
+/* diagnostics (no device needed): pipeline chunk of a unit in a host-buffer call of nUnits units with unitsPerChunk units per
+ * chunk (ramp != 0: the decoder's doubling ramp of small first chunks), computed by the host code and by the kernels'
+ * arithmetic; returns the number of chunks, -1 if the two disagree. */
+int LizardB200_chunkPlan(unsigned nUnits, unsigned unitsPerChunk, int ramp, unsigned unit, unsigned* chunk, unsigned* first, unsigned* count);
 /* number of kernel launches issued by this library since load (bench.py reports it as gpu_launches) */
 unsigned long long LizardB200_launchCount(void);
 /* diagnostics: how this thread's device decodes, four bits: 1 = pooled copy sweeps, 2 = compact length-extension chain,

@@ -39,7 +39,24 @@ struct Progress {
     volatile u32*       host_done;  // mapped pinned: [n_chunks] set to 1 when a chunk is complete
     u32                 chunk_units;
     u32                 n_units;
+    u32                 ramp_unit;  // 0, or the size of chunk 0 of a doubling ramp: chunks of ramp_unit << i units (i < ramp_chunks,
+    u32                 ramp_chunks;//    ramp_unit << ramp_chunks == chunk_units) in front of the chunk_units-sized ones
 };
+// chunk of a unit, the chunk's first unit and its size (the same arithmetic as FrameChunks on the host, frame.inl)
+LZ_HD u32 progress_chunk(const Progress& pg, u32 unit, u32* first, u32* cnt)
+{
+    u32 c, f, size;
+    const u32 ramp_total = pg.ramp_unit ? pg.chunk_units - pg.ramp_unit : 0u;       // ramp_unit * (2^ramp_chunks - 1)
+    if (unit < ramp_total) {
+        c = highbit32(unit / pg.ramp_unit + 1u);
+        f = pg.ramp_unit * ((1u << c) - 1u); size = pg.ramp_unit << c;
+    } else {
+        const u32 k = (unit - ramp_total) / pg.chunk_units;
+        c = (pg.ramp_unit ? pg.ramp_chunks : 0u) + k; f = ramp_total + k * pg.chunk_units; size = pg.chunk_units;
+    }
+    *first = f; *cnt = pg.n_units - f < size ? pg.n_units - f : size;
+    return c;
+}
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ void progress_wait(const Progress& pg, u32 unit, u32 lane)
@@ -54,9 +71,8 @@ __device__ __forceinline__ void progress_done(const Progress& pg, u32 unit, u32 
 {
     if (pg.done_count && lane == 0) {
         __threadfence_system();                        // the unit's result may live in pinned host memory
-        const u32 c = unit / pg.chunk_units;
-        const u32 first = c * pg.chunk_units;
-        const u32 cnt = (pg.n_units - first < pg.chunk_units) ? pg.n_units - first : pg.chunk_units;
+        u32 first, cnt;
+        const u32 c = progress_chunk(pg, unit, &first, &cnt);
         if (atomicAdd(&pg.done_count[c], 1u) == cnt - 1) { __threadfence_system(); pg.host_done[c] = 1u; }
     }
 }

@@ -129,9 +129,8 @@ __device__ __forceinline__ void pack_done(const EncodeBatch& b, u32 unit, u32 la
     const Progress& pg = b.progress;
     if (pg.done_count && lane == 0) {
         __threadfence();
-        const u32 c = unit / pg.chunk_units;
-        const u32 first = c * pg.chunk_units;
-        const u32 cnt = (pg.n_units - first < pg.chunk_units) ? pg.n_units - first : pg.chunk_units;
+        u32 first, cnt;
+        const u32 c = progress_chunk(pg, unit, &first, &cnt);
         if (atomicAdd(&pg.done_count[c], 1u) == cnt - 1) {
             __threadfence();
             volatile u64* st = b.pack.state;

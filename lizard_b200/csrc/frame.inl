@@ -135,14 +135,46 @@ bool wait_chunk(Context& c, volatile u32* flag)
     return true;
 }
 
+// How the units of a call are cut into pipeline chunks: `per_chunk` units each, optionally behind a doubling ramp (chunks
+// of per_chunk/16, /8, /4, /2 units first).  The decoder's calls are bound by the copy back to the host, which can only
+// start when the first chunk is done: with a 4 MiB first chunk that is ~1.4 ms earlier than with a 64 MiB one.  The
+// compressor's calls end one block latency after the last input byte has arrived whatever the chunking, so they keep
+// uniform chunks.  Same arithmetic as progress_chunk() on the device (decode.cuh).
+struct FrameChunks {
+    size_t n = 0, per_chunk = 1, ramp_unit = 0, ramp_chunks = 0;
+    void plan(size_t n_units, size_t units_per_chunk, bool ramp)
+    {
+        n = n_units; per_chunk = units_per_chunk ? units_per_chunk : 1; ramp_unit = ramp_chunks = 0;
+        if (ramp && per_chunk % 16 == 0 && n_units >= 2 * per_chunk) { ramp_unit = per_chunk / 16; ramp_chunks = 4; }
+    }
+    size_t ramp_total() const { return ramp_unit ? per_chunk - ramp_unit : 0; }
+    size_t first(size_t k) const
+    {
+        if (k < ramp_chunks) return ramp_unit * (((size_t)1 << k) - 1);
+        return ramp_total() + (k - ramp_chunks) * per_chunk;
+    }
+    size_t count(size_t k) const
+    {
+        const size_t f = first(k), size = k < ramp_chunks ? ramp_unit << k : per_chunk;
+        return f >= n ? 0 : (n - f < size ? n - f : size);
+    }
+    size_t chunks() const
+    {
+        if (n <= ramp_total()) { size_t k = 0; while (first(k) < n) ++k; return k; }
+        return ramp_chunks + (n - ramp_total() + per_chunk - 1) / per_chunk;
+    }
+};
+
 struct StreamProgress {
     Progress pg; u32* d_ready; volatile u32* h_done; u32* h_ready_vals; size_t nchunks;
+    FrameChunks plan;
     cudaEvent_t tables_ready = nullptr;
     ~StreamProgress() { if (tables_ready) cudaEventDestroy(tables_ready); }
     // d_progress layout: [ready][pad x3][done_count x nchunks]; flags in pinned memory
-    cudaError_t init(Context& c, size_t n_units, size_t per_chunk)
+    cudaError_t init(Context& c, size_t n_units, size_t per_chunk, bool ramp = false)
     {
-        nchunks = (n_units + per_chunk - 1) / per_chunk;
+        plan.plan(n_units, per_chunk, ramp);
+        nchunks = plan.chunks();
         cudaError_t e;
         if ((e = c.d_progress.reserve((4 + nchunks) * 4 + 64)) != cudaSuccess) return e;
         if ((e = c.pin_flags.reserve(nchunks * 8 + 64)) != cudaSuccess) return e;
@@ -151,12 +183,12 @@ struct StreamProgress {
         h_ready_vals = (u32*)c.pin_flags.p + nchunks;
         for (size_t k = 0; k < nchunks; ++k) {
             h_done[k] = 0;
-            const size_t upto = (k + 1) * per_chunk;
-            h_ready_vals[k] = (u32)(upto < n_units ? upto : n_units);
+            h_ready_vals[k] = (u32)(plan.first(k) + plan.count(k));
         }
         if ((e = cudaMemsetAsync(c.d_progress.p, 0, (4 + nchunks) * 4, c.stream)) != cudaSuccess) return e;
         pg.ready = d_ready; pg.done_count = d_ready + 4; pg.host_done = h_done;
-        pg.chunk_units = (u32)per_chunk; pg.n_units = (u32)n_units;
+        pg.chunk_units = (u32)plan.per_chunk; pg.n_units = (u32)n_units;
+        pg.ramp_unit = (u32)plan.ramp_unit; pg.ramp_chunks = (u32)plan.ramp_chunks;
         return cudaEventCreateWithFlags(&tables_ready, cudaEventDisableTiming);
     }
 };
@@ -237,7 +269,7 @@ struct FrameBlockRef { size_t src_pos; u32 csize; size_t dst_pos; };
 // way to take it off the critical path is to run it beside the copies and the kernel).  Null = the caller hashes.
 struct ChunkHasher {
     Xxh32* x = nullptr; const std::vector<FrameBlockRef>* blocks = nullptr; const std::vector<int>* sizes = nullptr;
-    const u8* dst = nullptr; size_t per_chunk = 0, n = 0; int device = 0;
+    const u8* dst = nullptr; FrameChunks plan; int device = 0;
     std::vector<cudaEvent_t> ev; std::atomic<size_t> recorded{0}; std::atomic<bool> stop{false}; std::thread th; bool on = false;
     bool start(size_t nchunks)
     {
@@ -253,7 +285,7 @@ struct ChunkHasher {
         for (size_t k = 0; k < ev.size(); ++k) {
             while (recorded.load(std::memory_order_acquire) <= k) { if (stop.load()) return; std::this_thread::yield(); }
             if (cudaEventSynchronize(ev[k]) != cudaSuccess) return;
-            const size_t first = k * per_chunk, last = (first + per_chunk < n ? first + per_chunk : n);
+            const size_t first = plan.first(k), last = first + plan.count(k);
             for (size_t i = first; i < last; ++i) {
                 const int sz = (*sizes)[i];
                 if (sz < 0) return;                                  // the caller reports the failure
@@ -277,7 +309,7 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
     const size_t tab_bytes = n * (8 + 4 + 8 + 4);
     Trace tr; tr.mark("decode: begin");
     StreamProgress sp;
-    if (sp.init(c, n, per_chunk) != cudaSuccess) return -1;
+    if (sp.init(c, n, per_chunk, true) != cudaSuccess) return -1;
     const size_t nchunks = sp.nchunks;
     if (c.pin_tab.reserve(tab_bytes + n * 4 + 64) != cudaSuccess || c.d_tab.reserve(tab_bytes + n * 4 + 64) != cudaSuccess ||
         c.d_in.reserve(src_span + 256) != cudaSuccess || c.d_out.reserve(dst_span + 64) != cudaSuccess) return -1;
@@ -300,7 +332,7 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
         // with the next chunk's first unit is final the first time an SM touches it
         size_t copied_to = 0;
         for (size_t k = 0; k < nchunks; ++k) {
-            const size_t first = k * per_chunk, last = (k + 1 == nchunks ? n : first + per_chunk) - 1;
+            const size_t first = sp.plan.first(k), last = first + sp.plan.count(k) - 1;
             size_t lo = blocks[first].src_pos; if (lo > copied_to) lo = lo & ~(size_t)127; if (lo < copied_to) lo = copied_to;
             size_t hi = (blocks[last].src_pos + blocks[last].csize + 127) & ~(size_t)127; if (hi > src_span) hi = src_span;
             if (hi > lo) cudaMemcpyAsync((u8*)c.d_in.p + lo, src + lo, hi - lo, cudaMemcpyHostToDevice, c.s_in);
@@ -311,12 +343,12 @@ int frame_decode_blocks(Context& c, const u8* src, size_t src_span, const std::v
     tr.mark("decode: kernel launched, H2D queued");
     ChunkHasher ch;
     if (hasher) {
-        ch.x = hasher; ch.blocks = &blocks; ch.sizes = &sizes_out; ch.dst = dst; ch.per_chunk = per_chunk; ch.n = n; ch.device = c.device;
+        ch.x = hasher; ch.blocks = &blocks; ch.sizes = &sizes_out; ch.dst = dst; ch.plan = sp.plan; ch.device = c.device;
         if (!ch.start(nchunks)) hasher = nullptr;                    // no helper: hash here, after the copies
     }
     bool failed = false;
     for (size_t k = 0; k < nchunks; ++k) {
-        const size_t first = k * per_chunk, last = (k + 1 == nchunks ? n : first + per_chunk) - 1;
+        const size_t first = sp.plan.first(k), last = first + sp.plan.count(k) - 1;
         if (!wait_chunk(c, &sp.h_done[k])) { failed = true; break; }
         tr.mark("decode: chunk done", (long)k);
         // copy back exactly what was produced: contiguous up to the end of the last good block of the chunk
@@ -818,5 +850,25 @@ try {   // lib/lizard_frame.c:870-893
     *info = d->info;
     return next;
 } catch (const std::bad_alloc&) { return ferr(FE_allocation_failed); } catch (...) { return ferr(FE_GENERIC); }
+
+
+// diagnostics (no device needed): the pipeline chunk of unit `unit` in a call of nUnits units cut into chunks of
+// unitsPerChunk (ramp != 0: the decoder's doubling ramp in front), computed the host's way (FrameChunks) and the kernels' way
+// (progress_chunk); returns the number of chunks, or -1 if the two disagree about the unit's chunk, its first unit or its size.
+int LizardB200_chunkPlan(unsigned nUnits, unsigned unitsPerChunk, int ramp, unsigned unit, unsigned* chunk, unsigned* first, unsigned* count)
+{
+    FrameChunks fc; fc.plan(nUnits, unitsPerChunk, ramp != 0);
+    Progress pg; memset(&pg, 0, sizeof pg);
+    pg.chunk_units = (u32)fc.per_chunk; pg.n_units = nUnits; pg.ramp_unit = (u32)fc.ramp_unit; pg.ramp_chunks = (u32)fc.ramp_chunks;
+    const size_t nch = fc.chunks();
+    if (unit >= nUnits) return (int)nch;
+    u32 f = 0, cnt = 0;
+    const u32 c = progress_chunk(pg, unit, &f, &cnt);
+    if (chunk) *chunk = c;
+    if (first) *first = f;
+    if (count) *count = cnt;
+    if (c >= nch || fc.first(c) != f || fc.count(c) != cnt || unit < f || unit >= f + cnt) return -1;
+    return (int)nch;
+}
 
 }  // extern "C"

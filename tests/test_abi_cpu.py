@@ -147,3 +147,31 @@ def test_encoder_launch_shapes_are_the_measured_ones():
         assert (w.value, t.value, k.value) == shape, (level, w.value, t.value, k.value)
         assert 2 * (b.value + 1024) <= 196 * 1024          # two CTAs inside the 196 KB carve-out step
     assert L.LizardB200_encodeShape(12, None, None, None, None) < 0
+
+
+def test_pipeline_chunk_plan_host_and_kernel_arithmetic_agree():
+    """The host-buffer calls cut their units into pipeline chunks (frame.inl: FrameChunks; the decoder's calls start with a
+    doubling ramp of small chunks); the kernels find a unit's chunk with their own arithmetic (decode.cuh: progress_chunk).
+    Every unit of a range of shapes must get the same chunk, first unit and size from both, and the chunks must tile the
+    units exactly."""
+    L = lz.lib()
+    L.LizardB200_chunkPlan.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_uint] + [ctypes.POINTER(ctypes.c_uint)] * 3
+    for n, per, ramp in [(8192, 512, 1), (8192, 512, 0), (1025, 512, 1), (1024, 512, 1), (1023, 512, 1), (100, 512, 1), (5000, 48, 1),
+                         (5000, 40, 1), (1, 512, 1), (33, 16, 1), (7, 1, 1), (4097, 2048, 1)]:
+        c, f, k = ctypes.c_uint(), ctypes.c_uint(), ctypes.c_uint()
+        seen = {}
+        nch = None
+        for u in range(n):
+            r = L.LizardB200_chunkPlan(n, per, ramp, u, ctypes.byref(c), ctypes.byref(f), ctypes.byref(k))
+            assert r > 0, (n, per, ramp, u, r)
+            nch = r
+            seen.setdefault(c.value, (f.value, k.value))
+            assert seen[c.value] == (f.value, k.value)
+        assert sorted(seen) == list(range(nch)), (n, per, ramp, sorted(seen)[:8], nch)
+        pos = 0
+        for ci in range(nch):
+            assert seen[ci][0] == pos and seen[ci][1] >= 1
+            pos += seen[ci][1]
+        assert pos == n
+        if ramp and per % 16 == 0 and n >= 2 * per:
+            assert seen[0][1] == per // 16 and seen[4][1] == per          # 1/16, 1/8, 1/4, 1/2, then full chunks

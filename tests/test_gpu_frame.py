@@ -121,3 +121,39 @@ def test_linked_blocks_are_refused(ours):
     p = lz.make_prefs(10, 1, False, False, 0)
     with pytest.raises(lz.LizardB200Error, match="blockMode"):
         lz.frame_compress(ours, lz.datagen(3 * BS), p)
+
+
+def test_decoder_chunk_ramp_small_chunks_subprocess():
+    """The decoder's host pipeline starts with a doubling ramp of small chunks when a call has at least two full chunks
+    (frame.inl: FrameChunks).  With LIZARDB200_FRAME_CHUNK_MIB=2 (16 blocks per chunk, ramp 1 / 2 / 4 / 8 blocks) a 6 MiB
+    frame exercises the ramp, full chunks and a ragged last chunk; the variable is read once per process, hence the
+    subprocess.  Frames from the reference, checksummed, levels 10 and 41, decoded whole and in pieces."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys
+import lizard_b200 as lz
+from tests import refs
+BS = lz.BLOCK_SIZE
+ref = lz.bind_frame_api(refs.ref_parity())
+ours = lz.bind_frame_api(lz.lib())
+L = lz.lib()
+import ctypes
+L.LizardB200_chunkPlan.argtypes = [ctypes.c_uint, ctypes.c_uint, ctypes.c_int, ctypes.c_uint] + [ctypes.POINTER(ctypes.c_uint)] * 3
+assert L.LizardB200_chunkPlan(50, 16, 1, 0, None, None, None) == 4 + 3          # ramp of four chunks, then 16 + 16 + 3 units
+for level in (10, 41):
+    for nblk, extra in ((50, 777), (32, 0), (47, 1)):
+        data = lz.datagen(nblk * BS + extra, 50, level + nblk)
+        p = lz.make_prefs(level, 1, True, True, 1)
+        frame = lz.frame_compress(ref, data, p)
+        assert lz.frame_compress(ours, data, p) == frame
+        for chunk, dchunk in ((0, 0), (3 << 20, 0)):
+            r, back = lz.frame_decompress(ours, frame, len(data), chunk, dchunk)
+            assert r == 0 and back == data, (level, nblk, chunk, r, len(back))
+print("ramp ok")
+'''
+    env = dict(os.environ, LIZARDB200_FRAME_CHUNK_MIB="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ramp ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
