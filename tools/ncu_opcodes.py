@@ -24,7 +24,14 @@ for l in dis[start + 1:]:
         ins_of[int(m.group(1), 16)] = m.group(2)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-hdr = rows[1]
+# a report with several launches prints one table per launch: keep the one whose instruction count is this kernel's
+# (NCU_SECTION picks among several launches of the same kernel, default the last) -- as tools/ncu_lines.py does
+heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+sections = [rows[h:(heads[k + 1] if k + 1 < len(heads) else len(rows))] for k, h in enumerate(heads)]
+mine = [sec for sec in sections if abs(sum(1 for r in sec[1:] if len(r) > 5) - len(ins_of)) <= 2] or sections
+sec = mine[int(os.environ.get("NCU_SECTION", "-1"))]
+hdr = sec[0]
+rows = [None, hdr] + [r for r in sec[1:] if len(r) > 5]
 iI, iA = hdr.index("Instructions Executed"), hdr.index("Address")
 base = int(rows[2][iA], 16)
 f = lo = hi = None
