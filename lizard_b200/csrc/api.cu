@@ -38,7 +38,7 @@ template <int V> __global__ void __launch_bounds__(kDecWarps * 32, 4)
 lizard_decode_units_kernel(DecodeBatch b)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 warp = threadIdx.x >> 5, lane = WarpLanes::lane();
     DecWarpShared* sh = reinterpret_cast<DecWarpShared*>(smem_raw) + warp;
 #if LZB_DEC_SH_OPAQUE
     // one register for the warp's block: left to itself the compiler re-derives `base + warp * size` in front of every access
@@ -93,7 +93,7 @@ template <u32 kStages> __global__ void __launch_bounds__(64, kStages >= 8 ? 8 : 
 lizard_decode2_units_kernel(DecodeBatch b)
 {
     __shared__ PairShared<kStages> ps;
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 warp = threadIdx.x >> 5, lane = WarpLanes::lane();
     if (threadIdx.x == 0) {
         for (u32 i = 0; i < kStages; ++i) mbar_init(&ps.full_bar[i], 1);
         for (u32 i = 0; i < kBatchSlots; ++i) { mbar_init(&ps.pub_bar[i], 1); mbar_init(&ps.free_bar[i], 1); }

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(32 * kEncWarpsPerCta, kEncCtasPerSM)
 lizard_encode_units_kernel(EncodeBatch b, u32 smem_tables, u32 table_bytes, u32 hist_bytes, size_t per_warp_bytes)
 {
     extern __shared__ __align__(16) unsigned char enc_smem[];
-    const u32 lane = threadIdx.x & 31, wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    const u32 lane = WarpLanes::lane(), wic = threadIdx.x >> 5, wpc = blockDim.x >> 5;
     u8* my = b.scratch + ((size_t)blockIdx.x * wpc + wic) * per_warp_bytes;
 #if LZB_ENC_OPAQUE
     // the warp's scratch base and table base stay in registers: left to itself the compiler re-derives them (a 64-bit

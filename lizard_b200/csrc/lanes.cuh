@@ -28,7 +28,10 @@ struct HostLanes {
 struct WarpLanes {
     static constexpr bool kDevice = true;
     static constexpr u32 kLanes = 32;
-    __device__ __forceinline__ static u32 lane() { return threadIdx.x & 31; }
+    // %laneid, not threadIdx.x & 31 (the same number in these one-dimensional blocks): the kernels run at their register
+    // caps and ptxas re-reads the special register at most of the ~150 use sites instead of keeping the value -- one
+    // instruction per site this way, two the other
+    __device__ __forceinline__ static u32 lane() { u32 l; asm("mov.u32 %0, %%laneid;" : "=r"(l)); return l; }
     __device__ __forceinline__ static u32 lanes() { return 32; }
     __device__ __forceinline__ static void sync() { __syncwarp(); }
     __device__ __forceinline__ static int bcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
@@ -40,7 +43,7 @@ struct WarpLanes {
     __device__ __forceinline__ static u32 excl_scan(u32 v, u32* total)
     {
         u32 x = v;
-        for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= (u32)o) x += y; }
+        for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(0xffffffffu, x, o); if (lane() >= (u32)o) x += y; }
         *total = __shfl_sync(0xffffffffu, x, 31);
         return x - v;
     }

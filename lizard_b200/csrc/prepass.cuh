@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kExpWarps * 32, kExpCtasMax)
 lizard_huf_expand_kernel(PrepassBatch b)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u32 warp = threadIdx.x >> 5, lane = WarpLanes::lane();
     ExpWarpShared* sh = reinterpret_cast<ExpWarpShared*>(smem_raw) + warp;
     HufJobScratch* ws = b.scratch + ((size_t)blockIdx.x * kExpWarps + warp) * kExpJobs + (lane & (kExpJobs - 1));
     for (u32 slot = 0; slot < 2; ++slot) {
