@@ -65,7 +65,13 @@ int Lizard_compress(const char* src, char* dst, int srcSize, int maxDstSize, int
 /* `state` is accepted for signature compatibility (must be pointer-aligned, else 0); the device keeps its own */
 int Lizard_compress_extState(void* state, const char* src, char* dst, int srcSize, int maxDstSize, int compressionLevel);
 /* returns decoded size (>= 0) or a negative error exactly as the reference:
- * -1 for a bad level byte / block header / stream, -(tokenIndex)-1 from the token loops */
+ * -1 for a bad level byte / block header / stream, -(tokenIndex)-1 from the token loops.
+ * Two deliberate differences, both on streams no encoder produces: a match offset below 8 is decoded with
+ * byte-serial semantics (the reference's 8-byte granule copies give bytes that depend on stale memory), and a call whose
+ * raw inner block is followed by a compressed one, decoded into less room than it needs, returns a negative value -- the
+ * reference does not charge raw inner blocks against maxDecompressedSize (lib/lizard_decompress.c:164-180), decodes the
+ * following block past dst + maxDecompressedSize and reports success.  This library never writes outside
+ * [dst, dst + maxDecompressedSize): it is the safer of the two. */
 int Lizard_decompress_safe(const char* src, char* dst, int compressedSize, int maxDecompressedSize);
 
 /* ---------------------------------------------------------------------------------------------
