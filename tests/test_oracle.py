@@ -448,6 +448,48 @@ def test_emulated_decoder_full_blocks_all_schedules(ref, shim, level):
     shim.lzb_emu_lane_order(0)
 
 
+def test_emulated_decoder_chain_window_source_alignments(ref, shim):
+    """The compact extension chain walks a 1 KiB window of the literals stream that starts at the 16-byte aligned ADDRESS at
+    or below the chain's position (decode.cuh: ext_chain_win), so its behaviour depends on where the compressed stream lies in
+    memory.  Every source alignment mod 16, both codeword flavours, inputs with long literal runs (multi-byte extension
+    fields, several windows per batch) and with only short ones, plus damaged copies of one stream: same code (and bytes)
+    as the reference."""
+    rnd = random.Random(17)
+    data = lz.datagen(BS + 64, 30, 5)
+    runs = bytearray()
+    while len(runs) < 70000:                      # literal runs of 300-5000 bytes between short matches
+        runs += bytes(rnd.randrange(256) for _ in range(rnd.choice([300, 700, 1021, 1024, 1030, 5000]))) + runs[-40:-8] * 2
+    cases = [data[:BS], bytes(runs[:70000]), lz.datagen(40000, 90, 3)]
+    shim.lzb_set_decode_variant(3)
+    for level in (10, 21):
+        for ci, c in enumerate(cases):
+            comp = refs.ref_compress(ref, c, level)
+            for mis in range(16):
+                raw = ctypes.create_string_buffer(len(comp) + 32)
+                ctypes.memmove(ctypes.addressof(raw) + mis, comp, len(comp))
+                buf = ctypes.create_string_buffer(len(c) + 64)
+                r = shim.lzb_emu_decompress(ctypes.cast(ctypes.addressof(raw) + mis, ctypes.c_char_p), len(comp), buf, len(c))
+                assert r == len(c) and buf.raw[:len(c)] == c, (level, ci, mis, r)
+        comp = refs.ref_compress(ref, cases[1], level)
+        for t in range(60):
+            bad = bytearray(comp)
+            if t % 3 == 0:
+                bad = bad[:rnd.randrange(len(bad) // 2, len(bad))]
+            else:
+                for _ in range(rnd.randrange(1, 4)):
+                    bad[rnd.randrange(16, len(bad))] = rnd.randrange(256)
+            bad = bytes(bad)
+            mis = t % 16
+            raw = ctypes.create_string_buffer(len(bad) + 32)
+            ctypes.memmove(ctypes.addressof(raw) + mis, bad, len(bad))
+            buf = ctypes.create_string_buffer(len(cases[1]) + 64)
+            rr, ro = refs.ref_decompress(ref, bad, len(cases[1]))
+            r = shim.lzb_emu_decompress(ctypes.cast(ctypes.addressof(raw) + mis, ctypes.c_char_p), len(bad), buf, len(cases[1]))
+            assert r == rr, (level, t, r, rr)
+            if rr > 0 and refs.stream_obeys_min_offset(bad, len(cases[1])):
+                assert buf.raw[:rr] == ro
+
+
 def test_prepasses_match_reference(ref, shim):
     """The decoder's two pre-passes run serially on the host -- Huffman pre-pass (plan the first inner block, expand the
     planned streams segment by segment) and token pre-pass (one-lane parse of the block into sequence records, mode bit
